@@ -1,0 +1,489 @@
+// rp_host.cu — C-ABI (include/roboplay.h) over the step kernel: model packing, device state,
+// launches.  No CPU fallback: every entry point that computes needs a CUDA device.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/roboplay.h"
+#include "rp_kernels.h"
+#include "rp_math.cuh"
+
+static thread_local std::string g_err;
+static int fail(const std::string& msg) { g_err = msg; return 1; }
+#define CUDA_OK(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+struct rp_model {
+  RpDevModel dm;
+  std::vector<uint8_t> goal;
+  std::vector<int8_t> fingering;
+  int nv, nu, nhand, obs_dim, act_dim;
+};
+
+struct rp_batch {
+  const rp_model* model;
+  int nenv, device;
+  cudaStream_t stream;
+  RpDevModel* d_dm;
+  uint8_t* d_goal;
+  int8_t* d_fingering;
+  double *qpos, *qvel, *qacc_ws, *ctrl, *sustain, *act_force, *site_xpos, *dbg;
+  int32_t *t_idx, *step_type_state, *diag;
+  uint8_t* activation;
+  // staging for rp_step_host
+  double *h_action, *h_out;  // pinned
+  double *d_action, *d_out;
+  int iterations;
+  double tolerance;
+  int64_t launches;
+};
+
+extern "C" const char* rp_last_error(void) { return g_err.c_str(); }
+extern "C" int rp_version(void) { return 1; }
+
+static void quat_to_mat(const double* q, double* m) { rp::quat2mat(m, q); }
+
+static void copy_gp(RpGeomParams& gp, const rp_flat_model* m, int g) {
+  for (int k = 0; k < 2; k++) gp.solref[k] = m->geom_solref[2 * g + k];
+  for (int k = 0; k < 5; k++) gp.solimp[k] = m->geom_solimp[5 * g + k];
+  for (int k = 0; k < 3; k++) gp.friction[k] = m->geom_friction[3 * g + k];
+  gp.solmix = m->geom_solmix[g]; gp.margin = m->geom_margin[g]; gp.gap = m->geom_gap[g];
+  gp.priority = m->geom_priority[g]; gp.contype = m->geom_contype[g]; gp.conaffinity = m->geom_conaffinity[g];
+  gp.pad = 0;
+}
+
+extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task) {
+  if (!m || !task) { fail("null model/task"); return nullptr; }
+  if (m->nkey != RP_NK) { fail("model must have 88 keys"); return nullptr; }
+  if (m->nhand != 0 && m->nhand != 2) { fail("nhand must be 0 or 2"); return nullptr; }
+  if (m->nv != RP_NK + m->nhand * RP_NL) { fail("unexpected nv (need 88 + nhand*26)"); return nullptr; }
+  rp_model* M = new rp_model();
+  RpDevModel& d = M->dm;
+  memset(&d, 0, sizeof(d));
+  d.nhand = m->nhand; d.nu = m->nu; d.nsub = m->nsubstep; d.iterations = m->iterations;
+  d.task_kind = task->kind;
+  d.h = m->timestep; d.tol = m->tolerance; d.impratio = m->impratio;
+  d.solver_scale = 1.0 / (m->meaninertia * (m->nv > 1 ? m->nv : 1));
+  for (int k = 0; k < 3; k++) d.gravity[k] = m->gravity[k];
+  auto bad = [&](const char* msg) -> rp_model* { fail(msg); delete M; return nullptr; };
+  // ---------------- keys
+  for (int k = 0; k < RP_NK; k++) {
+    int j = m->key_dofid[k], b = m->key_bodyid[k], g = m->key_geomid[k];
+    if (j != k) return bad("key dofs must be dofs 0..87 in key order");
+    if (m->body_parentid[b] != 0 || m->jnt_bodyid[j] != b || m->jnt_type[j] != 3) return bad("key body layout");
+    const double* bq = m->body_quat + 4 * b;
+    if (fabs(bq[0] - 1) > 1e-12) return bad("key bodies must have identity orientation");
+    const double* gq = m->geom_quat + 4 * g;
+    if (fabs(gq[0] - 1) > 1e-12 || fabs(m->geom_pos[3 * g]) + fabs(m->geom_pos[3 * g + 1]) + fabs(m->geom_pos[3 * g + 2]) > 1e-12)
+      return bad("key geoms must sit at the body origin");
+    const double* iq = m->body_iquat + 4 * b;
+    if (fabs(iq[0] - 1) > 1e-12) return bad("key inertial frame must be axis aligned");
+    for (int c = 0; c < 3; c++) {
+      d.key_pos[k][c] = m->body_pos[3 * b + c];
+      d.key_jpos[k][c] = m->jnt_pos[3 * j + c];
+      d.key_axis[k][c] = m->jnt_axis[3 * j + c];
+      d.key_ipos[k][c] = m->body_ipos[3 * b + c];
+      d.key_half[k][c] = m->geom_size[3 * g + c];
+    }
+    d.key_mass[k] = m->body_mass[b];
+    // inertia about the hinge: axis' I axis + m |r_perp|^2 + armature
+    const double *ax = d.key_axis[k], *I = m->body_inertia + 3 * b;
+    double r[3] = {d.key_ipos[k][0] - d.key_jpos[k][0], d.key_ipos[k][1] - d.key_jpos[k][1], d.key_ipos[k][2] - d.key_jpos[k][2]};
+    double ra = rp::dot3(r, ax), r2 = rp::dot3(r, r) - ra * ra;
+    d.key_M[k] = ax[0] * ax[0] * I[0] + ax[1] * ax[1] * I[1] + ax[2] * ax[2] * I[2] + d.key_mass[k] * r2 + m->dof_armature[j];
+    d.key_stiffness[k] = m->jnt_stiffness[j]; d.key_springref[k] = m->jnt_springref[j];
+    d.key_damping[k] = m->dof_damping[j];
+    if (!m->jnt_limited[j]) return bad("key joints must be limited");
+    if (m->dof_frictionloss[j] != 0) return bad("key joints must have no frictionloss");
+    d.key_range[k][0] = m->jnt_range[2 * j]; d.key_range[k][1] = m->jnt_range[2 * j + 1];
+    rp::ref_KB(m->jnt_solref + 2 * j, m->jnt_solimp[5 * j + 1], m->timestep, &d.key_lim_K[k], &d.key_lim_B[k]);
+    for (int c = 0; c < 5; c++) d.key_lim_solimp[k][c] = m->jnt_solimp[5 * j + c];
+    d.key_dof_invw[k] = m->dof_invweight0[j];
+    d.key_body_invw[k] = m->body_invweight0[2 * b];
+    copy_gp(d.key_gp[k], m, g);
+  }
+  for (int g = 0; g < m->ngeom; g++)
+    if (m->geom_key[g] == -2) {
+      int b = m->geom_bodyid[g];
+      if (m->body_dofnum[b] != 0 || m->body_parentid[b] != 0) return bad("piano base must be static");
+      for (int c = 0; c < 3; c++) { d.base_pos[c] = m->body_pos[3 * b + c] + m->geom_pos[3 * g + c]; d.base_half[c] = m->geom_size[3 * g + c]; }
+      copy_gp(d.base_gp, m, g);
+      d.has_base = 1;
+    }
+  // white-key lattice
+  {
+    int nw = 0;
+    double ys[RP_NK];
+    for (int k = 0; k < RP_NK; k++) ys[k] = d.key_pos[k][1];
+    for (int i = 0; i < 52; i++) d.black_after[i] = -1;
+    for (int k = 0; k < RP_NK; k++) {
+      bool white = d.key_half[k][1] > 0.008;
+      if (white) { if (nw >= 52) return bad("more than 52 white keys"); d.white_of_slot[nw++] = k; }
+    }
+    if (nw != 52) return bad("expected 52 white keys");
+    d.lattice_y0 = ys[d.white_of_slot[0]];
+    d.lattice_pitch = ys[d.white_of_slot[1]] - ys[d.white_of_slot[0]];
+    for (int k = 0; k < RP_NK; k++) {
+      bool white = d.key_half[k][1] > 0.008;
+      if (white) continue;
+      int slot = (int)floor((ys[k] - d.lattice_y0) / d.lattice_pitch);
+      if (slot < 0 || slot >= 52 || d.black_after[slot] >= 0) return bad("black key lattice");
+      d.black_after[slot] = k;
+    }
+  }
+  // ---------------- actuators on keys (self-actuated piano)
+  int nkey_act = 0;
+  for (int a = 0; a < m->nu; a++) {
+    if (m->actuator_trntype[a] == 0 && m->actuator_trnid[a] < RP_NK) {
+      int k = m->actuator_trnid[a];
+      if (a != k) return bad("key actuators must be in key order");
+      d.key_act_gain[k] = m->actuator_gainprm[a] * m->actuator_gear[a];
+      d.key_act_range[k][0] = m->actuator_ctrllimited[a] ? m->actuator_ctrlrange[2 * a] : -1e300;
+      d.key_act_range[k][1] = m->actuator_ctrllimited[a] ? m->actuator_ctrlrange[2 * a + 1] : 1e300;
+      nkey_act++;
+    }
+  }
+  if (nkey_act != 0 && nkey_act != RP_NK) return bad("either all or no keys may be actuated");
+  d.nkey_act = nkey_act;
+  // ---------------- hands
+  int nact_hand = m->nhand ? (m->nu - nkey_act) / m->nhand : 0;
+  int order = 0;
+  for (int h = 0; h < m->nhand; h++) {
+    int base = RP_NK + h * RP_NL;
+    int maxdepth = 0;
+    for (int l = 0; l < RP_NL; l++) {
+      int j = base + l, b = m->jnt_bodyid[j];
+      bool first = m->body_dofadr[b] == j, last = (m->body_dofadr[b] + m->body_dofnum[b] - 1) == j;
+      int parent;
+      if (first) {
+        int pj = m->dof_parentid[j];
+        parent = pj < 0 ? -1 : pj - base;
+        int pb = m->body_parentid[b];
+        if (pj < 0 && pb != 0) return bad("hand root body must hang off the world");
+        if (pj >= 0 && m->jnt_bodyid[pj] != pb) return bad("hand bodies without joints are not supported");
+        for (int c = 0; c < 3; c++) d.link_pos[h][l][c] = m->body_pos[3 * b + c];
+        for (int c = 0; c < 4; c++) d.link_quat[h][l][c] = m->body_quat[4 * b + c];
+      } else {
+        parent = l - 1;
+        d.link_quat[h][l][0] = 1;
+      }
+      if (parent >= l || parent < -1) return bad("hand dofs must be in depth-first order");
+      d.link_parent[h][l] = parent;
+      d.link_depth[h][l] = parent < 0 ? 0 : d.link_depth[h][parent] + 1;
+      if (d.link_depth[h][l] >= RP_MAXD) return bad("hand chain too deep");
+      maxdepth = d.link_depth[h][l] > maxdepth ? d.link_depth[h][l] : maxdepth;
+      for (int dd = 0; dd < RP_MAXD; dd++) d.link_anc[h][l][dd] = -1;
+      if (parent >= 0) for (int dd = 0; dd < d.link_depth[h][l]; dd++) d.link_anc[h][l][dd] = d.link_anc[h][parent][dd];
+      d.link_anc[h][l][d.link_depth[h][l]] = l;
+      d.link_jtype[h][l] = m->jnt_type[j];
+      d.link_limited[h][l] = m->jnt_limited[j];
+      for (int c = 0; c < 3; c++) { d.link_jpos[h][l][c] = m->jnt_pos[3 * j + c]; d.link_jaxis[h][l][c] = m->jnt_axis[3 * j + c]; }
+      d.link_iquat[h][l][0] = 1;
+      if (last) {
+        for (int c = 0; c < 3; c++) { d.link_ipos[h][l][c] = m->body_ipos[3 * b + c]; d.link_inertia[h][l][c] = m->body_inertia[3 * b + c]; }
+        for (int c = 0; c < 4; c++) d.link_iquat[h][l][c] = m->body_iquat[4 * b + c];
+        d.link_mass[h][l] = m->body_mass[b];
+        d.link_gravcomp[h][l] = m->body_gravcomp[b];
+      }
+      d.link_body_invw[h][l] = m->body_invweight0[2 * b];
+      d.link_damping[h][l] = m->dof_damping[j]; d.link_armature[h][l] = m->dof_armature[j];
+      d.link_frictionloss[h][l] = m->dof_frictionloss[j];
+      d.link_stiffness[h][l] = m->jnt_stiffness[j]; d.link_springref[h][l] = m->jnt_springref[j];
+      d.link_range[h][l][0] = m->jnt_range[2 * j]; d.link_range[h][l][1] = m->jnt_range[2 * j + 1];
+      rp::ref_KB(m->jnt_solref + 2 * j, m->jnt_solimp[5 * j + 1], m->timestep, &d.link_lim_K[h][l], &d.link_lim_B[h][l]);
+      for (int c = 0; c < 5; c++) d.link_lim_solimp[h][l][c] = m->jnt_solimp[5 * j + c];
+      d.link_dof_invw[h][l] = m->dof_invweight0[j];
+      double imp = rp::impedance(m->dof_solimp + 5 * j, 0.0, 0.0), K;
+      d.link_fr_R[h][l] = fmax(RP_MINVAL, (1 - imp) * m->dof_invweight0[j] / imp);
+      rp::ref_KB(m->dof_solref + 2 * j, m->dof_solimp[5 * j + 1], m->timestep, &K, &d.link_fr_B[h][l]);
+      d.dof_act[h][l] = -1;
+    }
+    d.maxdepth[h] = maxdepth;
+    // subtree sizes, sibling ranks
+    for (int l = RP_NL - 1; l >= 0; l--) {
+      d.link_subtree[h][l] += 1;
+      if (d.link_parent[h][l] >= 0) d.link_subtree[h][d.link_parent[h][l]] += d.link_subtree[h][l];
+    }
+    {
+      int nchild[RP_NL] = {0};
+      for (int l = 0; l < RP_NL; l++) {
+        int p = d.link_parent[h][l];
+        if (p >= 0) {
+          d.link_childrank[h][l] = nchild[p]++;
+          int dd = d.link_depth[h][l];
+          if (nchild[p] > d.link_nchild_slots[h][dd]) d.link_nchild_slots[h][dd] = nchild[p];
+        }
+      }
+    }
+    // actuators of this hand
+    d.nact[h] = nact_hand;
+    if (nact_hand > RP_NAH) return bad("too many actuators per hand");
+    for (int ai = 0; ai < nact_hand; ai++) {
+      int a = nkey_act + h * nact_hand + ai;
+      double gear = m->actuator_gear[a];
+      int d0, d1 = -1;
+      double c0 = gear, c1 = 0;
+      if (m->actuator_trntype[a] == 0) d0 = m->actuator_trnid[a] - base;
+      else {
+        int t = m->actuator_trnid[a];
+        if (m->tendon_num[t] != 2) return bad("only two-joint fixed tendons are supported");
+        d0 = m->wrap_dofid[m->tendon_adr[t]] - base; d1 = m->wrap_dofid[m->tendon_adr[t] + 1] - base;
+        c0 = gear * m->wrap_coef[m->tendon_adr[t]]; c1 = gear * m->wrap_coef[m->tendon_adr[t] + 1];
+        if (d1 < 0 || d1 >= RP_NL) return bad("actuator does not belong to its hand");
+      }
+      if (d0 < 0 || d0 >= RP_NL) return bad("actuator does not belong to its hand (hand actuators must be contiguous)");
+      d.act_dof0[h][ai] = d0; d.act_dof1[h][ai] = d1; d.act_coef0[h][ai] = c0; d.act_coef1[h][ai] = c1;
+      d.act_gain[h][ai] = m->actuator_gainprm[a];
+      for (int c = 0; c < 3; c++) d.act_bias[h][ai][c] = m->actuator_biasprm[3 * a + c];
+      d.act_ctrllimited[h][ai] = m->actuator_ctrllimited[a]; d.act_forcelimited[h][ai] = m->actuator_forcelimited[a];
+      for (int c = 0; c < 2; c++) { d.act_ctrlrange[h][ai][c] = m->actuator_ctrlrange[2 * a + c]; d.act_forcerange[h][ai][c] = m->actuator_forcerange[2 * a + c]; }
+      if (d.dof_act[h][d0] >= 0 || (d1 >= 0 && d.dof_act[h][d1] >= 0)) return bad("more than one actuator on a dof");
+      d.dof_act[h][d0] = ai; d.dof_act_coef[h][d0] = c0;
+      if (d1 >= 0) { d.dof_act[h][d1] = ai; d.dof_act_coef[h][d1] = c1; }
+    }
+    // colliding primitives
+    int ng = 0;
+    for (int g = 0; g < m->ngeom; g++) {
+      if (m->geom_hand[g] != h || !m->geom_collide[g]) continue;
+      if (ng >= RP_NGH) return bad("too many colliding hand geoms");
+      int b = m->geom_bodyid[g];
+      int l = m->body_dofadr[b] + m->body_dofnum[b] - 1 - base;
+      if (m->geom_type[g] != 2 && m->geom_type[g] != 3) return bad("only sphere/capsule hand colliders are supported");
+      d.geom_link[h][ng] = l; d.geom_type[h][ng] = m->geom_type[g]; d.geom_order[h][ng] = order++;
+      double R[9];
+      quat_to_mat(m->geom_quat + 4 * g, R);
+      for (int c = 0; c < 3; c++) { d.geom_pos[h][ng][c] = m->geom_pos[3 * g + c]; d.geom_axis[h][ng][c] = R[3 * c + 2]; }
+      d.geom_size[h][ng][0] = m->geom_size[3 * g]; d.geom_size[h][ng][1] = m->geom_size[3 * g + 1];
+      copy_gp(d.geom_gp[h][ng], m, g);
+      ng++;
+    }
+    d.ngeom[h] = ng;
+    if (m->nsite != 2 * RP_NSITE) return bad("expected 5 fingertip sites per hand");
+    for (int s = 0; s < RP_NSITE; s++) {
+      int si = h * RP_NSITE + s, b = m->site_bodyid[si];
+      d.site_link[h][s] = m->body_dofadr[b] + m->body_dofnum[b] - 1 - base;
+      for (int c = 0; c < 3; c++) d.site_pos[h][s][c] = m->site_pos[3 * si + c];
+    }
+    if (m->nobsdof != RP_NL) return bad("hand_obs_dofid must list 26 dofs per hand");
+    for (int l = 0; l < RP_NL; l++) d.obs_dof[h][l] = m->hand_obs_dofid[h * RP_NL + l] - base;
+  }
+  d.nhandgeom_total = order;
+  if (order > 64) return bad("too many hand geoms for the contact sort key");
+  // ---------------- task
+  d.T = task->n_steps; d.lookahead = task->n_steps_lookahead;
+  d.wrong_press_termination = task->wrong_press_termination;
+  d.disable_fingering_reward = task->disable_fingering_reward;
+  d.disable_forearm_reward = task->disable_forearm_reward;
+  d.reward_type = task->reward_type;
+  d.energy_coef = task->energy_penalty_coef;
+  if (task->kind == 0) {
+    if (m->nhand != 2) return bad("piano_with_shadow_hands needs two hands");
+    d.obs_dim = RP_NK + 1 + 2 * RP_NL + (d.lookahead + 1) * RP_GOAL_DIM + (d.disable_fingering_reward ? 0 : 10);
+  } else {
+    if (nkey_act != RP_NK) return bad("self_actuated_piano needs key actuators");
+    d.obs_dim = RP_NK + 1 + (d.lookahead + 1) * RP_GOAL_DIM;
+  }
+  d.act_dim = m->nu + 1;
+  if (d.T <= 0) return bad("empty song");
+  M->goal.assign(task->goal, task->goal + (size_t)d.T * RP_GOAL_DIM);
+  M->fingering.assign(task->fingering, task->fingering + (size_t)d.T * RP_NK);
+  M->nv = m->nv; M->nu = m->nu; M->nhand = m->nhand; M->obs_dim = d.obs_dim; M->act_dim = d.act_dim;
+  return M;
+}
+
+extern "C" void rp_model_destroy(rp_model* m) { delete m; }
+extern "C" int rp_obs_dim(const rp_model* m) { return m->obs_dim; }
+extern "C" int rp_action_dim(const rp_model* m) { return m->act_dim; }
+extern "C" int rp_reward_terms(const rp_model* m) { return m->dm.task_kind == 0 ? 5 : 1; }
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t n) {
+  cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (n ? n : 1));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, sizeof(T) * (n ? n : 1));
+  return e;
+}
+
+extern "C" rp_batch* rp_batch_create(const rp_model* model, int nenv, int device, void* cuda_stream) {
+  if (!model || nenv <= 0) { fail("bad arguments"); return nullptr; }
+  if (device < 0) { fail("device < 0: this library has no CPU path"); return nullptr; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) { fail("CUDA device not available"); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { fail("cudaSetDevice failed"); return nullptr; }
+  rp_batch* b = new rp_batch();
+  memset(b, 0, sizeof(*b));
+  b->model = model; b->nenv = nenv; b->device = device; b->stream = (cudaStream_t)cuda_stream;
+  b->iterations = -1; b->tolerance = -1.0;
+  size_t N = nenv, nv = model->nv, nu = model->nu;
+  cudaError_t e = cudaSuccess;
+  auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+  chk(cudaMalloc((void**)&b->d_dm, sizeof(RpDevModel)));
+  chk(cudaMemcpy(b->d_dm, &model->dm, sizeof(RpDevModel), cudaMemcpyHostToDevice));
+  chk(cudaMalloc((void**)&b->d_goal, model->goal.size()));
+  chk(cudaMemcpy(b->d_goal, model->goal.data(), model->goal.size(), cudaMemcpyHostToDevice));
+  chk(cudaMalloc((void**)&b->d_fingering, model->fingering.size()));
+  chk(cudaMemcpy(b->d_fingering, model->fingering.data(), model->fingering.size(), cudaMemcpyHostToDevice));
+  chk(dalloc(&b->qpos, N * nv)); chk(dalloc(&b->qvel, N * nv)); chk(dalloc(&b->qacc_ws, N * nv));
+  chk(dalloc(&b->ctrl, N * nu)); chk(dalloc(&b->sustain, N)); chk(dalloc(&b->act_force, N * nu));
+  chk(dalloc(&b->site_xpos, N * 30)); chk(dalloc(&b->t_idx, N)); chk(dalloc(&b->step_type_state, N));
+  chk(dalloc(&b->diag, N * 3)); chk(dalloc(&b->activation, N * RP_NK));
+  size_t out_doubles = N * (model->obs_dim + 2 + 5) + (N + 7) / 8 + 8;
+  chk(cudaMallocHost((void**)&b->h_action, sizeof(double) * N * model->act_dim));
+  chk(cudaMallocHost((void**)&b->h_out, sizeof(double) * out_doubles));
+  chk(dalloc(&b->d_action, N * model->act_dim));
+  chk(dalloc(&b->d_out, out_doubles));
+  if (e != cudaSuccess) { fail(std::string("allocation failed: ") + cudaGetErrorString(e)); delete b; return nullptr; }
+  // step_type_state starts as MID so the first rp_step without rp_reset still steps
+  std::vector<int32_t> mid(N, RP_STEP_MID_);
+  cudaMemcpy(b->step_type_state, mid.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice);
+  return b;
+}
+
+extern "C" int rp_batch_destroy(rp_batch* b) {
+  if (!b) return 0;
+  cudaSetDevice(b->device);
+  cudaFree(b->d_dm); cudaFree(b->d_goal); cudaFree(b->d_fingering);
+  cudaFree(b->qpos); cudaFree(b->qvel); cudaFree(b->qacc_ws); cudaFree(b->ctrl); cudaFree(b->sustain);
+  cudaFree(b->act_force); cudaFree(b->site_xpos); cudaFree(b->t_idx); cudaFree(b->step_type_state);
+  cudaFree(b->diag); cudaFree(b->activation); cudaFree(b->dbg); cudaFree(b->d_action); cudaFree(b->d_out);
+  cudaFreeHost(b->h_action); cudaFreeHost(b->h_out);
+  delete b;
+  return 0;
+}
+
+extern "C" int rp_set_option(rp_batch* b, int iterations, double tolerance) {
+  b->iterations = iterations; b->tolerance = tolerance;
+  return 0;
+}
+
+static RpKernelArgs base_args(rp_batch* b, int mode) {
+  RpKernelArgs a;
+  memset(&a, 0, sizeof(a));
+  a.dm = b->d_dm; a.nenv = b->nenv; a.mode = mode; a.nsub = b->model->dm.nsub;
+  a.iterations = b->iterations; a.tolerance = b->tolerance;
+  a.qpos = b->qpos; a.qvel = b->qvel; a.qacc_ws = b->qacc_ws; a.ctrl = b->ctrl;
+  a.t_idx = b->t_idx; a.step_type_state = b->step_type_state; a.sustain = b->sustain;
+  a.goal = b->d_goal; a.fingering = b->d_fingering;
+  a.diag = b->diag; a.act_force = b->act_force; a.site_xpos = b->site_xpos; a.activation = b->activation;
+  a.dbg = b->dbg;
+  return a;
+}
+static int launch(rp_batch* b, const RpKernelArgs& a) {
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(rp_launch_step(a, b->model->nhand, b->stream));
+  b->launches++;
+  return 0;
+}
+
+extern "C" int rp_reset(rp_batch* b, const uint8_t* mask_dev, double* obs_dev) {
+  RpKernelArgs a = base_args(b, RP_MODE_RESET);
+  a.reset_mask = mask_dev; a.obs = obs_dev;
+  return launch(b, a);
+}
+
+extern "C" int rp_step(rp_batch* b, const double* action_dev, double* obs_dev, double* reward_dev,
+                       double* discount_dev, uint8_t* step_type_dev, double* reward_terms_dev) {
+  if (!action_dev) return fail("action is required");
+  RpKernelArgs a = base_args(b, RP_MODE_STEP);
+  a.action = action_dev; a.obs = obs_dev; a.reward = reward_dev; a.discount = discount_dev;
+  a.step_type = step_type_dev; a.reward_terms = reward_terms_dev;
+  return launch(b, a);
+}
+
+extern "C" int rp_step_host(rp_batch* b, const double* action, double* obs, double* reward, double* discount,
+                            uint8_t* step_type, double* reward_terms) {
+  const rp_model* M = b->model;
+  size_t N = b->nenv, od = M->obs_dim, ad = M->act_dim;
+  CUDA_OK(cudaSetDevice(b->device));
+  memcpy(b->h_action, action, sizeof(double) * N * ad);
+  CUDA_OK(cudaMemcpyAsync(b->d_action, b->h_action, sizeof(double) * N * ad, cudaMemcpyHostToDevice, b->stream));
+  double* d_obs = b->d_out;
+  double* d_rew = d_obs + N * od;
+  double* d_dis = d_rew + N;
+  double* d_terms = d_dis + N;
+  uint8_t* d_st = (uint8_t*)(d_terms + N * 5);
+  if (rp_step(b, b->d_action, d_obs, d_rew, d_dis, d_st, d_terms)) return 1;
+  size_t bytes = sizeof(double) * (N * od + 2 * N + 5 * N) + N;
+  CUDA_OK(cudaMemcpyAsync(b->h_out, b->d_out, bytes, cudaMemcpyDeviceToHost, b->stream));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  if (obs) memcpy(obs, b->h_out, sizeof(double) * N * od);
+  if (reward) memcpy(reward, b->h_out + N * od, sizeof(double) * N);
+  if (discount) memcpy(discount, b->h_out + N * od + N, sizeof(double) * N);
+  if (reward_terms) memcpy(reward_terms, b->h_out + N * od + 2 * N, sizeof(double) * N * 5);
+  if (step_type) memcpy(step_type, (uint8_t*)(b->h_out + N * od + 7 * N), N);
+  return 0;
+}
+
+extern "C" int rp_physics_step(rp_batch* b, const double* ctrl_dev, int nsub) {
+  RpKernelArgs a = base_args(b, RP_MODE_PHYSICS);
+  a.ctrl_in = ctrl_dev; a.nsub = nsub;
+  return launch(b, a);
+}
+
+extern "C" int rp_get_state(rp_batch* b, double* qpos, double* qvel, double* qacc_ws, int32_t* t_idx) {
+  size_t N = b->nenv, nv = b->model->nv;
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  if (qpos) CUDA_OK(cudaMemcpy(qpos, b->qpos, sizeof(double) * N * nv, cudaMemcpyDeviceToHost));
+  if (qvel) CUDA_OK(cudaMemcpy(qvel, b->qvel, sizeof(double) * N * nv, cudaMemcpyDeviceToHost));
+  if (qacc_ws) CUDA_OK(cudaMemcpy(qacc_ws, b->qacc_ws, sizeof(double) * N * nv, cudaMemcpyDeviceToHost));
+  if (t_idx) CUDA_OK(cudaMemcpy(t_idx, b->t_idx, sizeof(int32_t) * N, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int rp_set_state(rp_batch* b, const double* qpos, const double* qvel, const double* qacc_ws, const int32_t* t_idx) {
+  size_t N = b->nenv, nv = b->model->nv;
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  if (qpos) CUDA_OK(cudaMemcpy(b->qpos, qpos, sizeof(double) * N * nv, cudaMemcpyHostToDevice));
+  if (qvel) CUDA_OK(cudaMemcpy(b->qvel, qvel, sizeof(double) * N * nv, cudaMemcpyHostToDevice));
+  if (qacc_ws) CUDA_OK(cudaMemcpy(b->qacc_ws, qacc_ws, sizeof(double) * N * nv, cudaMemcpyHostToDevice));
+  if (t_idx) CUDA_OK(cudaMemcpy(b->t_idx, t_idx, sizeof(int32_t) * N, cudaMemcpyHostToDevice));
+  return 0;
+}
+extern "C" int rp_get_diag(rp_batch* b, int32_t* ncon, int32_t* niter, int32_t* flags) {
+  size_t N = b->nenv;
+  std::vector<int32_t> tmp(N * 3);
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  CUDA_OK(cudaMemcpy(tmp.data(), b->diag, sizeof(int32_t) * N * 3, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < N; i++) {
+    if (ncon) ncon[i] = tmp[3 * i];
+    if (niter) niter[i] = tmp[3 * i + 1];
+    if (flags) flags[i] = tmp[3 * i + 2];
+  }
+  return 0;
+}
+extern "C" int rp_get_aux(rp_batch* b, double* actuator_force, double* site_xpos, uint8_t* activation) {
+  size_t N = b->nenv;
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  if (actuator_force) CUDA_OK(cudaMemcpy(actuator_force, b->act_force, sizeof(double) * N * b->model->nu, cudaMemcpyDeviceToHost));
+  if (site_xpos) CUDA_OK(cudaMemcpy(site_xpos, b->site_xpos, sizeof(double) * N * 30, cudaMemcpyDeviceToHost));
+  if (activation) CUDA_OK(cudaMemcpy(activation, b->activation, N * RP_NK, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int64_t rp_launch_count(const rp_batch* b) { return b->launches; }
+
+// Debug hooks (not part of the public header): stage dump of substep 0 for every env.
+extern "C" int rp_debug_enable(rp_batch* b, int on) {
+  CUDA_OK(cudaSetDevice(b->device));
+  if (on && !b->dbg) CUDA_OK(dalloc(&b->dbg, (size_t)b->nenv * RP_DBG_STRIDE));
+  if (!on && b->dbg) { cudaFree(b->dbg); b->dbg = nullptr; }
+  return 0;
+}
+extern "C" int rp_debug_read(rp_batch* b, double* out) {
+  if (!b->dbg) return fail("debug dump not enabled");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  CUDA_OK(cudaMemcpy(out, b->dbg, sizeof(double) * (size_t)b->nenv * RP_DBG_STRIDE, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int rp_debug_stride(void) { return RP_DBG_STRIDE; }
+extern "C" int rp_smem_bytes(void) { return (int)rp_kernel_smem_bytes(); }

@@ -1,0 +1,49 @@
+// rp_kernels.h — launch interface between the C-ABI host code and the step kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "rp_model.h"
+
+enum { RP_MODE_STEP = 0, RP_MODE_RESET = 1, RP_MODE_PHYSICS = 2 };
+enum { RP_STEP_FIRST_ = 0, RP_STEP_MID_ = 1, RP_STEP_LAST_ = 2 };
+#define RP_GOAL_DIM_ 89
+
+// debug dump layout (doubles per env), filled for substep 0 when RpKernelArgs::dbg != nullptr
+#define RP_DBG_QACC_SMOOTH 0
+#define RP_DBG_QACC 160
+#define RP_DBG_QFRC_C 320
+#define RP_DBG_BIAS 480
+#define RP_DBG_SCALARS 640
+#define RP_DBG_CONTACTS 656   // 24 x 16
+#define RP_DBG_M 1040         // 26 x 26 (hand 0)
+#define RP_DBG_MINV 1716      // 26 x 26 (hand 0)
+#define RP_DBG_STRIDE 2400
+
+struct RpKernelArgs {
+  const RpDevModel* dm;
+  int nenv, mode, nsub, iterations;
+  double tolerance;
+  // state, env-major: [N][nv], [N][nu]
+  double *qpos, *qvel, *qacc_ws, *ctrl;
+  int32_t *t_idx, *step_type_state;
+  double* sustain;
+  // inputs
+  const double* action;      // [N][act_dim]      (STEP)
+  const double* ctrl_in;     // [N][nu]           (PHYSICS, optional)
+  const uint8_t* reset_mask; // [N]               (RESET, optional)
+  const uint8_t* goal;       // [T][89]
+  const int8_t* fingering;   // [T][88]
+  // outputs (optional)
+  double *obs, *reward, *discount, *reward_terms;
+  uint8_t* step_type;
+  int32_t* diag;             // [N][3] ncon, niter, flags
+  double* act_force;         // [N][nu]
+  double* site_xpos;         // [N][10][3]
+  uint8_t* activation;       // [N][88]
+  double* dbg;
+};
+
+size_t rp_kernel_smem_bytes();
+cudaError_t rp_launch_step(const RpKernelArgs& a, int nhand, cudaStream_t stream);

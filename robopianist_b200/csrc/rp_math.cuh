@@ -1,0 +1,319 @@
+// rp_math.cuh — scalar building blocks of the step kernel (host+device so they can be unit-tested
+// on the CPU against the oracle: tests/test_hd_math.py builds csrc/hd_harness.cpp with g++).
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define RP_HD __host__ __device__ __forceinline__
+#else
+#define RP_HD inline
+#endif
+
+#define RP_MINVAL 1e-15
+#define RP_MINIMP 0.0001
+#define RP_MAXIMP 0.9999
+
+namespace rp {
+
+RP_HD double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+RP_HD void cross3(double* r, const double* a, const double* b) {
+  double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+RP_HD void quat_mul(double* r, const double* a, const double* b) {
+  double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  double x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  double y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  double z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+RP_HD void quat_normalize(double* q) {
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < RP_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  double inv = 1.0 / n;
+  q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+}
+RP_HD void quat2mat(double* m, const double* q) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+RP_HD void mat_vec(double* r, const double* m, const double* v) {
+  double x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
+  double y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2];
+  double z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+RP_HD void matT_vec(double* r, const double* m, const double* v) {
+  double x = m[0] * v[0] + m[3] * v[1] + m[6] * v[2];
+  double y = m[1] * v[0] + m[4] * v[1] + m[7] * v[2];
+  double z = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+// spatial algebra at the world origin: motion V=[w;v], force F=[n;f], inertia I={m,h[3],Ixx,Iyy,Izz,Ixy,Ixz,Iyz}
+RP_HD void inertia_mul(double* F, const double* I, const double* V) {
+  const double *w = V, *v = V + 3, *h = I + 1;
+  double Iw0 = I[4] * w[0] + I[7] * w[1] + I[8] * w[2];
+  double Iw1 = I[7] * w[0] + I[5] * w[1] + I[9] * w[2];
+  double Iw2 = I[8] * w[0] + I[9] * w[1] + I[6] * w[2];
+  double hxv[3], wxh[3];
+  cross3(hxv, h, v);
+  cross3(wxh, w, h);
+  F[0] = Iw0 + hxv[0]; F[1] = Iw1 + hxv[1]; F[2] = Iw2 + hxv[2];
+  F[3] = I[0] * v[0] + wxh[0]; F[4] = I[0] * v[1] + wxh[1]; F[5] = I[0] * v[2] + wxh[2];
+}
+RP_HD void cross_motion(double* r, const double* V, const double* S) {
+  double a[3], b[3], c[3];
+  cross3(a, V, S);
+  cross3(b, V, S + 3);
+  cross3(c, V + 3, S);
+  r[0] = a[0]; r[1] = a[1]; r[2] = a[2];
+  r[3] = b[0] + c[0]; r[4] = b[1] + c[1]; r[5] = b[2] + c[2];
+}
+RP_HD void cross_force(double* r, const double* V, const double* F) {
+  double a[3], b[3], c[3];
+  cross3(a, V, F);
+  cross3(b, V + 3, F + 3);
+  cross3(c, V, F + 3);
+  r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2];
+  r[3] = c[0]; r[4] = c[1]; r[5] = c[2];
+}
+RP_HD double dot6(const double* a, const double* b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+// body inertia {mass, principal inertia di} with COM c (world) and inertial orientation R (world) -> at origin
+RP_HD void body_inertia_world(double* out, double mass, const double* di, const double* R, const double* c) {
+  double I00 = R[0] * di[0] * R[0] + R[1] * di[1] * R[1] + R[2] * di[2] * R[2];
+  double I11 = R[3] * di[0] * R[3] + R[4] * di[1] * R[4] + R[5] * di[2] * R[5];
+  double I22 = R[6] * di[0] * R[6] + R[7] * di[1] * R[7] + R[8] * di[2] * R[8];
+  double I01 = R[0] * di[0] * R[3] + R[1] * di[1] * R[4] + R[2] * di[2] * R[5];
+  double I02 = R[0] * di[0] * R[6] + R[1] * di[1] * R[7] + R[2] * di[2] * R[8];
+  double I12 = R[3] * di[0] * R[6] + R[4] * di[1] * R[7] + R[5] * di[2] * R[8];
+  double cc = dot3(c, c);
+  out[0] = mass;
+  out[1] = mass * c[0]; out[2] = mass * c[1]; out[3] = mass * c[2];
+  out[4] = I00 + mass * (cc - c[0] * c[0]);
+  out[5] = I11 + mass * (cc - c[1] * c[1]);
+  out[6] = I22 + mass * (cc - c[2] * c[2]);
+  out[7] = I01 - mass * c[0] * c[1];
+  out[8] = I02 - mass * c[0] * c[2];
+  out[9] = I12 - mass * c[1] * c[2];
+}
+
+// solimp -> impedance d(r) (MuJoCo getimpedance), with the usual clamps
+RP_HD double impedance(const double* solimp, double pos, double margin) {
+  double d0 = fmin(fmax(solimp[0], RP_MINIMP), RP_MAXIMP), d1 = fmin(fmax(solimp[1], RP_MINIMP), RP_MAXIMP);
+  double width = fmax(solimp[2], 0.0), mid = fmin(fmax(solimp[3], RP_MINIMP), RP_MAXIMP), power = fmax(solimp[4], 1.0);
+  if (d0 == d1 || width <= RP_MINVAL) return 0.5 * (d0 + d1);
+  double x = fabs((pos - margin) / width);
+  if (x >= 1) return d1;
+  if (x <= 0) return d0;
+  double y;
+  if (power == 1) y = x;
+  else if (power == 2) y = (x <= mid) ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);
+  else if (x <= mid) y = pow(x, power) / pow(mid, power - 1);
+  else y = 1 - pow(1 - x, power) / pow(1 - mid, power - 1);
+  return d0 + y * (d1 - d0);
+}
+// solref (+dmax, timestep) -> stiffness K and damping B of the reference acceleration
+RP_HD void ref_KB(const double* solref, double dmax_in, double timestep, double* K, double* B) {
+  double tc = solref[0], dr = solref[1];
+  double dmax = fmin(fmax(dmax_in, RP_MINIMP), RP_MAXIMP);
+  if (tc > 0 && tc < 2 * timestep) tc = 2 * timestep;  // refsafe
+  if (tc > 0) {
+    *K = 1.0 / fmax(RP_MINVAL, dmax * dmax * tc * tc * dr * dr);
+    *B = 2.0 / fmax(RP_MINVAL, dmax * tc);
+  } else {
+    *K = -tc / fmax(RP_MINVAL, dmax * dmax);
+    *B = -dr / fmax(RP_MINVAL, dmax);
+  }
+}
+
+// sphere (centre c in box frame, radius r) vs box half sizes s. Returns signed distance; n = unit
+// normal (box frame) from the sphere towards the box; p = point mid-way between the surfaces.
+RP_HD double sphere_box(const double* c, double r, const double* s, double* n, double* p) {
+  double cl[3], dl[3];
+  bool inside = true;
+  for (int k = 0; k < 3; k++) {
+    cl[k] = c[k] < -s[k] ? -s[k] : (c[k] > s[k] ? s[k] : c[k]);
+    dl[k] = c[k] - cl[k];
+    if (dl[k] != 0) inside = false;
+  }
+  double dist;
+  if (!inside) {
+    double len = sqrt(dot3(dl, dl));
+    dist = len - r;
+    for (int k = 0; k < 3; k++) n[k] = -dl[k] / len;
+    for (int k = 0; k < 3; k++) p[k] = cl[k] - n[k] * 0.5 * dist;
+  } else {
+    int best = 0;
+    double bd = 1e300;
+    for (int k = 0; k < 3; k++) {
+      double dk = s[k] - fabs(c[k]);
+      if (dk < bd) { bd = dk; best = k; }
+    }
+    double sg = c[best] >= 0 ? 1.0 : -1.0;
+    n[0] = n[1] = n[2] = 0;
+    for (int k = 0; k < 3; k++) { if (k == best) n[k] = -sg; p[k] = c[k]; }
+    dist = -bd - r;
+    for (int k = 0; k < 3; k++) if (k == best) p[k] = sg * s[k];
+    for (int k = 0; k < 3; k++) p[k] -= n[k] * 0.5 * dist;
+  }
+  return dist;
+}
+RP_HD double point_box_d2(const double* c, const double* s) {
+  double d2 = 0;
+  for (int k = 0; k < 3; k++) {
+    double e = fabs(c[k]) - s[k];
+    if (e > 0) d2 += e * e;
+  }
+  return d2;
+}
+// t in [0,1] minimising dist(a + t (b-a), box): convex piecewise quadratic, breakpoints where a
+// coordinate crosses a face plane; ties keep the smallest t.
+RP_HD double segment_box_closest_t(const double* a, const double* b, const double* s) {
+  double bp[8];
+  int nbp = 0;
+  bp[nbp++] = 0; bp[nbp++] = 1;
+  double dir[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+  for (int k = 0; k < 3; k++) {
+    if (fabs(dir[k]) < RP_MINVAL) continue;
+    double t1 = (-s[k] - a[k]) / dir[k], t2 = (s[k] - a[k]) / dir[k];
+    if (t1 > 0 && t1 < 1) bp[nbp++] = t1;
+    if (t2 > 0 && t2 < 1) bp[nbp++] = t2;
+  }
+  for (int i = 1; i < nbp; i++) {
+    double v = bp[i];
+    int j = i - 1;
+    while (j >= 0 && bp[j] > v) { bp[j + 1] = bp[j]; j--; }
+    bp[j + 1] = v;
+  }
+  double best_t = 0, best_d = 1e300;
+  for (int i = 0; i + 1 < nbp; i++) {
+    double t0 = bp[i], t1 = bp[i + 1];
+    if (t1 - t0 < 1e-14) continue;
+    double tm = 0.5 * (t0 + t1), qa = 0, qb = 0;
+    for (int k = 0; k < 3; k++) {
+      double pm = a[k] + tm * dir[k];
+      if (pm > s[k]) { qa += dir[k] * dir[k]; qb += 2 * dir[k] * (a[k] - s[k]); }
+      else if (pm < -s[k]) { qa += dir[k] * dir[k]; qb += 2 * dir[k] * (a[k] + s[k]); }
+    }
+    double tc = t0;
+    if (qa > RP_MINVAL) { tc = -qb / (2 * qa); tc = tc < t0 ? t0 : (tc > t1 ? t1 : tc); }
+    double cand[3] = {t0, tc, t1};
+    for (int c = 0; c < 3; c++) {
+      double p[3] = {a[0] + cand[c] * dir[0], a[1] + cand[c] * dir[1], a[2] + cand[c] * dir[2]};
+      double d2 = point_box_d2(p, s);
+      if (d2 < best_d - 1e-18) { best_d = d2; best_t = cand[c]; }
+    }
+  }
+  return best_t;
+}
+// mju_makeFrame: frame[0:3] unit normal -> frame[3:6], frame[6:9] tangents
+RP_HD void make_frame(double* frame) {
+  double *x = frame, *y = frame + 3, *z = frame + 6;
+  y[0] = y[1] = y[2] = 0;
+  if (x[1] < 0.5 && x[1] > -0.5) y[1] = 1; else y[2] = 1;
+  double t = dot3(x, y);
+  for (int k = 0; k < 3; k++) y[k] -= t * x[k];
+  double n = sqrt(dot3(y, y));
+  for (int k = 0; k < 3; k++) y[k] /= n;
+  cross3(z, x, y);
+}
+// mju_QCQP2
+RP_HD int qcqp2(double* res, const double* Ain, const double* bin, const double* d, double r) {
+  double b1 = bin[0] * d[0], b2 = bin[1] * d[1];
+  double A11 = Ain[0] * d[0] * d[0], A22 = Ain[3] * d[1] * d[1], A12 = Ain[1] * d[0] * d[1];
+  double la = 0, v1 = 0, v2 = 0;
+  for (int iter = 0; iter < 20; iter++) {
+    double det = (A11 + la) * (A22 + la) - A12 * A12;
+    if (det < 1e-10) { res[0] = 0; res[1] = 0; return 0; }
+    double detinv = 1 / det, P11 = (A22 + la) * detinv, P22 = (A11 + la) * detinv, P12 = -A12 * detinv;
+    v1 = -P11 * b1 - P12 * b2;
+    v2 = -P12 * b1 - P22 * b2;
+    double val = v1 * v1 + v2 * v2 - r * r;
+    if (val < 1e-10) break;
+    double deriv = -2 * (P11 * v1 * v1 + 2 * P12 * v1 * v2 + P22 * v2 * v2);
+    double delta = -val / deriv;
+    if (delta < 1e-10) break;
+    la += delta;
+  }
+  res[0] = v1 * d[0];
+  res[1] = v2 * d[1];
+  return la != 0;
+}
+// One PGS update of an elliptic condim-3 contact block.  A = 3x3 block of AR (row major, with R on
+// the diagonal), res = residual b + AR*f at the current force, f = force (in/out), mu = friction.
+// Returns the cost change (<= 0), reverting the update when it is positive.
+RP_HD double pgs_elliptic_update(const double* A, const double* res, double* f, double mu) {
+  double old[3] = {f[0], f[1], f[2]};
+  double fr[2] = {mu, mu};
+  if (f[0] < RP_MINVAL) {
+    f[0] -= res[0] / A[0];
+    if (f[0] < 0) f[0] = 0;
+    f[1] = f[2] = 0;
+  } else {
+    double v1[3];
+    for (int r = 0; r < 3; r++) v1[r] = A[3 * r] * old[0] + A[3 * r + 1] * old[1] + A[3 * r + 2] * old[2];
+    double denom = dot3(old, v1);
+    if (denom >= RP_MINVAL) {
+      double x = -dot3(old, res) / denom;
+      if (f[0] + x * old[0] < 0) x = -1.0;
+      for (int r = 0; r < 3; r++) f[r] += x * old[r];
+    }
+  }
+  if (f[0] >= RP_MINVAL) {
+    double Ac[4] = {A[4], A[5], A[7], A[8]}, bc[2], vv[2];
+    for (int r = 1; r < 3; r++) {
+      double t = res[r];
+      for (int s = 1; s < 3; s++) t -= A[3 * r + s] * old[s];
+      t += A[3 * r] * (f[0] - old[0]);
+      bc[r - 1] = t;
+    }
+    int flg = qcqp2(vv, Ac, bc, fr, f[0]);
+    if (flg) {
+      double s = vv[0] * vv[0] / (fr[0] * fr[0]) + vv[1] * vv[1] / (fr[1] * fr[1]);
+      s = sqrt(f[0] * f[0] / fmax(RP_MINVAL, s));
+      vv[0] *= s; vv[1] *= s;
+    }
+    f[1] = vv[0]; f[2] = vv[1];
+  }
+  double dl[3] = {f[0] - old[0], f[1] - old[1], f[2] - old[2]}, Ad[3];
+  for (int r = 0; r < 3; r++) Ad[r] = A[3 * r] * dl[0] + A[3 * r + 1] * dl[1] + A[3 * r + 2] * dl[2];
+  double change = 0.5 * dot3(dl, Ad) + dot3(dl, res);
+  if (change > 1e-10) { f[0] = old[0]; f[1] = old[1]; f[2] = old[2]; change = 0; }
+  return change;
+}
+// primal map of an elliptic contact: jar (3) -> force (3)  (mj_constraintUpdate)
+RP_HD void elliptic_primal_force(const double* jar, const double* D, double mu, double* force) {
+  double U0 = jar[0] * mu, U1 = jar[1] * mu, U2 = jar[2] * mu;
+  double N = U0, T = sqrt(U1 * U1 + U2 * U2);
+  if ((N >= mu * T) || (T <= 0 && N >= 0)) {
+    force[0] = force[1] = force[2] = 0;
+  } else if ((mu * N + T <= 0) || (T <= 0 && N < 0)) {
+    for (int r = 0; r < 3; r++) force[r] = -D[r] * jar[r];
+  } else {
+    double Dm = D[0] / (mu * mu * (1 + mu * mu));
+    double NmT = N - mu * T;
+    force[0] = -Dm * NmT * mu;
+    force[1] = -force[0] / T * U1 * mu;
+    force[2] = -force[0] / T * U2 * mu;
+  }
+}
+// geom-pair parameter mixing (mj_contactParam)
+RP_HD void mix_params(const double* solref1, const double* solimp1, const double* fr1, double solmix1, int prio1,
+                      const double* solref2, const double* solimp2, const double* fr2, double solmix2, int prio2,
+                      double* solref, double* solimp, double* mu) {
+  double mix;
+  if (prio1 != prio2) mix = prio1 > prio2 ? 1.0 : 0.0;
+  else if (solmix1 >= RP_MINVAL && solmix2 >= RP_MINVAL) mix = solmix1 / (solmix1 + solmix2);
+  else if (solmix1 < RP_MINVAL && solmix2 < RP_MINVAL) mix = 0.5;
+  else mix = solmix1 < RP_MINVAL ? 0.0 : 1.0;
+  if (solref1[0] > 0 && solref2[0] > 0) for (int k = 0; k < 2; k++) solref[k] = mix * solref1[k] + (1 - mix) * solref2[k];
+  else for (int k = 0; k < 2; k++) solref[k] = fmin(solref1[k], solref2[k]);
+  for (int k = 0; k < 5; k++) solimp[k] = mix * solimp1[k] + (1 - mix) * solimp2[k];
+  *mu = prio1 == prio2 ? fmax(fr1[0], fr2[0]) : (prio1 > prio2 ? fr1[0] : fr2[0]);
+}
+
+}  // namespace rp

@@ -1,0 +1,179 @@
+"""ctypes binding of libroboplay.so (the C-ABI in include/roboplay.h).
+
+The library is built in-tree by ``robopianist_b200/csrc/Makefile`` (``__graft_entry__.build()``).
+There is no fallback: a missing library or a machine without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import cabi
+
+_LIB = None
+LIB_PATH = Path(__file__).resolve().parent / "libroboplay.so"
+
+EXPORTS = [
+    "rp_last_error", "rp_version", "rp_model_create", "rp_model_destroy", "rp_obs_dim", "rp_action_dim",
+    "rp_reward_terms", "rp_batch_create", "rp_batch_destroy", "rp_set_option", "rp_reset", "rp_step",
+    "rp_step_host", "rp_physics_step", "rp_get_state", "rp_set_state", "rp_get_diag", "rp_get_aux",
+    "rp_launch_count",
+]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not LIB_PATH.exists():
+            raise NativeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU / PyTorch fallback for the step kernel)")
+        L = C.CDLL(str(LIB_PATH))
+        vp, ip, dp, u8 = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_uint8)
+        L.rp_last_error.restype = C.c_char_p
+        L.rp_model_create.restype = vp
+        L.rp_model_create.argtypes = [C.POINTER(cabi.RpFlatModel), C.POINTER(cabi.RpTask)]
+        L.rp_model_destroy.argtypes = [vp]
+        for fn in ("rp_obs_dim", "rp_action_dim", "rp_reward_terms"):
+            getattr(L, fn).argtypes = [vp]
+        L.rp_batch_create.restype = vp
+        L.rp_batch_create.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.rp_batch_destroy.argtypes = [vp]
+        L.rp_set_option.argtypes = [vp, C.c_int, C.c_double]
+        L.rp_reset.argtypes = [vp, vp, vp]
+        L.rp_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.rp_step_host.argtypes = [vp, dp, dp, dp, dp, u8, dp]
+        L.rp_physics_step.argtypes = [vp, vp, C.c_int]
+        L.rp_get_state.argtypes = [vp, dp, dp, dp, ip]
+        L.rp_set_state.argtypes = [vp, dp, dp, dp, ip]
+        L.rp_get_diag.argtypes = [vp, ip, ip, ip]
+        L.rp_get_aux.argtypes = [vp, dp, dp, u8]
+        L.rp_launch_count.restype = C.c_int64
+        L.rp_launch_count.argtypes = [vp]
+        L.rp_debug_enable.argtypes = [vp, C.c_int]
+        L.rp_debug_read.argtypes = [vp, dp]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise NativeError(lib().rp_last_error().decode())
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Model:
+    """Host-side compiled model + task tables (rp_model)."""
+
+    def __init__(self, flat_model, goal, fingering, kind=0, iterations=None, tolerance=None, **task_kw):
+        L = lib()
+        s, self._keep = cabi.pack_model(flat_model, iterations, tolerance)
+        t, keep2 = cabi.pack_task(kind, goal, fingering, **task_kw)
+        self._keep += keep2
+        self.ptr = L.rp_model_create(C.byref(s), C.byref(t))
+        if not self.ptr:
+            raise NativeError(L.rp_last_error().decode())
+        self.flat = flat_model
+        self.nv, self.nu = flat_model.meta["nv"], flat_model.meta["nu"]
+        self.obs_dim, self.act_dim = L.rp_obs_dim(self.ptr), L.rp_action_dim(self.ptr)
+        self.n_steps = int(goal.shape[0])
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().rp_model_destroy(self.ptr)
+        except Exception:
+            pass
+
+
+class Batch:
+    """Device-resident batch of N environments (rp_batch). Pointers are raw ints / torch data_ptr()."""
+
+    def __init__(self, model: Model, nenv: int, device: int = 0, stream: int = 0):
+        L = lib()
+        self.model, self.nenv, self.device = model, int(nenv), int(device)
+        self.ptr = L.rp_batch_create(model.ptr, nenv, device, C.c_void_p(stream))
+        if not self.ptr:
+            raise NativeError(L.rp_last_error().decode())
+
+    def close(self):
+        if self.ptr:
+            lib().rp_batch_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, iterations=-1, tolerance=-1.0):
+        _check(lib().rp_set_option(self.ptr, iterations, tolerance))
+
+    def reset(self, mask_ptr=None, obs_ptr=None):
+        _check(lib().rp_reset(self.ptr, mask_ptr, obs_ptr))
+
+    def step(self, action_ptr, obs_ptr, reward_ptr, discount_ptr, step_type_ptr, terms_ptr=None):
+        _check(lib().rp_step(self.ptr, action_ptr, obs_ptr, reward_ptr, discount_ptr, step_type_ptr, terms_ptr))
+
+    def step_host(self, action: np.ndarray):
+        N, m = self.nenv, self.model
+        action = np.ascontiguousarray(action, np.float64).reshape(N, m.act_dim)
+        obs = np.empty((N, m.obs_dim)); rew = np.empty(N); dis = np.empty(N)
+        st = np.empty(N, np.uint8); terms = np.empty((N, 5))
+        _check(lib().rp_step_host(self.ptr, _dp(action), _dp(obs), _dp(rew), _dp(dis),
+                                  st.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(terms)))
+        return obs, rew, dis, st, terms
+
+    def physics_step(self, ctrl_ptr=None, nsub=1):
+        _check(lib().rp_physics_step(self.ptr, ctrl_ptr, nsub))
+
+    def get_state(self):
+        N, nv = self.nenv, self.model.nv
+        q = np.empty((N, nv)); v = np.empty((N, nv)); w = np.empty((N, nv)); t = np.empty(N, np.int32)
+        _check(lib().rp_get_state(self.ptr, _dp(q), _dp(v), _dp(w), t.ctypes.data_as(C.POINTER(C.c_int32))))
+        return q, v, w, t
+
+    def set_state(self, qpos=None, qvel=None, qacc_warmstart=None, t_idx=None):
+        def prep(a):
+            return None if a is None else np.ascontiguousarray(a, np.float64)
+        q, v, w = prep(qpos), prep(qvel), prep(qacc_warmstart)
+        t = None if t_idx is None else np.ascontiguousarray(t_idx, np.int32)
+        _check(lib().rp_set_state(self.ptr, _dp(q), _dp(v), _dp(w),
+                                  None if t is None else t.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def get_diag(self):
+        N = self.nenv
+        a, b, c = (np.empty(N, np.int32) for _ in range(3))
+        ip = C.POINTER(C.c_int32)
+        _check(lib().rp_get_diag(self.ptr, a.ctypes.data_as(ip), b.ctypes.data_as(ip), c.ctypes.data_as(ip)))
+        return dict(ncon=a, niter=b, flags=c)
+
+    def get_aux(self):
+        N = self.nenv
+        f = np.empty((N, self.model.nu)); s = np.empty((N, 10, 3)); act = np.empty((N, 88), np.uint8)
+        _check(lib().rp_get_aux(self.ptr, _dp(f), _dp(s), act.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return dict(actuator_force=f, site_xpos=s, activation=act)
+
+    @property
+    def launches(self):
+        return int(lib().rp_launch_count(self.ptr))
+
+    # debug stage dump (substep 0 of the next launches)
+    def debug_enable(self, on=True):
+        _check(lib().rp_debug_enable(self.ptr, int(on)))
+
+    def debug_read(self):
+        stride = lib().rp_debug_stride()
+        out = np.empty((self.nenv, stride))
+        _check(lib().rp_debug_read(self.ptr, _dp(out)))
+        return out

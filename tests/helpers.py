@@ -1,0 +1,31 @@
+"""Shared builders for the tests (scene, song tables, oracle / native handles)."""
+from pathlib import Path
+
+import numpy as np
+
+from robopianist_b200.music import library, trajectory
+from robopianist_b200.scene import cache
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def song_tables(name="TwinkleTwinkleRousseau", trim_silence=True, dt=0.05):
+    seq = library.load(name)
+    if trim_silence:
+        seq = seq.trim_silence()
+    traj = trajectory.NoteTrajectory.from_seq(seq, dt)
+    return traj.goal_table(), traj.fingering_table()
+
+
+def twinkle_actions():
+    return np.load(GOLDEN / "twinkle_ctrl.npz")["action"]
+
+
+def make_native(task="piano_with_shadow_hands", song="TwinkleTwinkleRousseau", gravity_compensation=True,
+                nenv=1, lookahead=1, **task_kw):
+    from robopianist_b200 import native
+    fm = cache.load_scene(task, gravity_compensation=gravity_compensation)
+    goal, fing = song_tables(song)
+    kind = 0 if task == "piano_with_shadow_hands" else 1
+    model = native.Model(fm, goal, fing, kind=kind, n_steps_lookahead=lookahead, **task_kw)
+    return fm, model, native.Batch(model, nenv)
