@@ -940,6 +940,7 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
         double fold[3] = {f[0], f[1], f[2]};
         double change = rp::pgs_elliptic_update(A, res, f, cn.mu);
         double df[3] = {f[0] - fold[0], f[1] - fold[1], f[2] - fold[2]};
+        __syncwarp();
         if (lane == 0) {
           improvement -= change;
           cn.f[0] = f[0]; cn.f[1] = f[1]; cn.f[2] = f[2];
