@@ -1,0 +1,164 @@
+"""CPU restatement of the per-step task logic around the oracle physics — TEST INFRASTRUCTURE ONLY.
+
+Follows, line by line, the reference's Python:
+  composer.Environment.step order: before_step -> n_sub x (physics.step,
+  Piano.after_substep) -> after_step -> observables -> reward -> termination;
+  robopianist/suite/tasks/piano_with_shadow_hands.py:176-220 (before/after_step, termination),
+  :251-331 (rewards), :371-412 (goal / fingering state), robopianist/models/piano/piano.py:178-192
+  (key state), robopianist/suite/tasks/self_actuated_piano.py:38-57,143-243,
+  dm_control.utils.rewards.tolerance (gaussian sigmoid, value_at_margin=0.1).
+PARITY UNPINNED for the physics underneath (see oracle.c).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import oracle as O
+
+KEY_THRESHOLD = 0.00872665
+SUSTAIN_THRESHOLD = 0.5
+FIRST, MID, LAST = 0, 1, 2
+
+
+def tolerance(x, bounds, margin):
+    x = np.asarray(x, dtype=np.float64)
+    lo, hi = bounds
+    in_bounds = np.logical_and(lo <= x, x <= hi)
+    d = np.where(x < lo, lo - x, x - hi) / margin
+    scale = np.sqrt(-2 * np.log(0.1))
+    return np.where(in_bounds, 1.0, np.exp(-0.5 * (d * scale) ** 2))
+
+
+class RefEnv:
+    """One environment: oracle physics + the reference's task logic (dm_env semantics)."""
+
+    def __init__(self, fm, goal, fingering, kind=0, n_steps_lookahead=1, wrong_press_termination=False,
+                 disable_fingering_reward=False, disable_forearm_reward=False, energy_penalty_coef=5e-3,
+                 reward_type=0, maxcon=24, iterations=None, tolerance_=None):
+        self.fm, self.kind = fm, kind
+        self.goal = np.asarray(goal, np.float64)
+        self.fingering = np.asarray(fingering)
+        self.T, self.L = goal.shape[0], n_steps_lookahead
+        self.wrong_press_termination = wrong_press_termination
+        self.disable_fingering_reward = disable_fingering_reward
+        self.disable_forearm_reward = disable_forearm_reward
+        self.energy_coef, self.reward_type = energy_penalty_coef, reward_type
+        self.om = O.OracleModel(fm, iterations, tolerance_)
+        self.om.set_option(maxcon=maxcon)
+        self.d = O.OracleData(self.om)
+        self.qmax = fm.key_qmax
+        self.nu = fm.meta["nu"]
+        self._need_reset = True
+        self.reward_terms = {}
+
+    # ---------------------------------------------------------------- helpers
+    def _update_key_state(self):
+        d = self.d
+        if self.kind == 1:
+            mid = 0.5 * (self.fm.actuator_ctrlrange[:, 0] + self.fm.actuator_ctrlrange[:, 1])
+            self.activation = d.ctrl >= mid
+        else:
+            self.state = np.clip(d.qpos[:88], 0.0, self.qmax)
+            self.normalized = self.state / self.qmax
+            self.activation = np.abs(self.state - self.qmax) <= KEY_THRESHOLD
+        self.sustain_activation = self.sustain_state >= SUSTAIN_THRESHOLD
+
+    def _update_goal_state(self):
+        if self.t_idx == self.T:
+            return
+        g = np.zeros((self.L + 1, 89))
+        for i, t in enumerate(range(self.t_idx, min(self.t_idx + self.L + 1, self.T))):
+            g[i] = self.goal[t]
+        self.goal_state = g
+        f = self.fingering[self.t_idx]
+        keys = np.flatnonzero(self.goal[self.t_idx, :88])
+        self.rh_keys = [(k, int(f[k])) for k in keys if 0 <= f[k] < 5]
+        self.lh_keys = [(k, int(f[k]) - 5) for k in keys if f[k] >= 5]
+        fs = np.zeros((2, 5))
+        for k, fi in self.rh_keys:
+            fs[0, fi] = 1
+        for k, fi in self.lh_keys:
+            fs[1, fi] = 1
+        self.fingering_state = fs
+
+    def _observation(self):
+        self._update_goal_state()
+        d, fm = self.d, self.fm
+        if self.kind == 0:
+            parts = [self.normalized, [self.sustain_state], d.qpos[fm.hand_obs_dofid[0]], d.qpos[fm.hand_obs_dofid[1]],
+                     self.goal_state.ravel()]
+            if not self.disable_fingering_reward:
+                parts.append(self.fingering_state.ravel())
+        else:
+            parts = [self.activation.astype(np.float64), [float(self.sustain_activation)], self.goal_state.ravel()]
+        return np.concatenate([np.asarray(p, np.float64).ravel() for p in parts])
+
+    # ---------------------------------------------------------------- dm_env API
+    def reset(self):
+        self.d.reset()
+        self.t_idx = 0
+        self.sustain_state = 0.0
+        self._update_key_state()
+        self._need_reset = False
+        self.last_actuator_force = np.zeros(self.nu)
+        return FIRST, None, None, self._observation()
+
+    def step(self, action):
+        if self._need_reset:
+            return self.reset()
+        d, fm = self.d, self.fm
+        action = np.asarray(action, np.float64)
+        self.sustain_state = float(action[-1])
+        d.control_step(action[:-1])  # nsub x (mj_step2; mj_step1): legacy_step=True
+        self._update_key_state()
+        # after_step
+        self.t_idx += 1
+        should_terminate = (self.t_idx - 1) == self.T - 1
+        goal_current = self.goal_state[0].copy()
+        rh_cur, lh_cur = list(self.rh_keys), list(self.lh_keys)
+        failure = bool(self.activation[np.flatnonzero(1 - goal_current[:-1])].any()) if self.kind == 0 else False
+        obs = self._observation()
+        # reward
+        if self.kind == 0:
+            on = np.flatnonzero(goal_current[:-1])
+            r_key = 0.0
+            if on.size > 0:
+                actual = self.state / self.qmax
+                r_key += 0.5 * tolerance(goal_current[:-1][on] - actual[on], (0, 0.05), 0.5).mean()
+            off = np.flatnonzero(1 - goal_current[:-1])
+            r_key += 0.5 * (1 - float(self.activation[off].any()))
+            r_sus = float(tolerance(goal_current[-1] - float(self.sustain_activation), (0, 0.05), 0.5))
+            # energy: actuatorfrc from the last mj_step2 (pre-integration), actuatorvel from the last mj_step1
+            power = np.abs(d.actuator_force) * np.abs(d.actuator_velocity)
+            r_en = -self.energy_coef * power[:22].sum() - self.energy_coef * power[22:].sum()
+            terms = dict(key_press_reward=r_key, sustain_reward=r_sus, energy_reward=r_en)
+            if not self.disable_fingering_reward:
+                dists = []
+                for hand, keys in ((0, rh_cur), (1, lh_cur)):
+                    for k, fi in keys:
+                        g = fm.key_geomid[k]
+                        kp = d.geom_xpos[g].copy()
+                        kp[2] += 0.5 * fm.geom_size[g, 2]
+                        kp[0] += 0.35 * fm.geom_size[g, 0]
+                        dists.append(np.linalg.norm(kp - d.site_xpos[hand * 5 + fi]))
+                terms["fingering_reward"] = float(tolerance(np.array(dists), (0, 0.01), 0.1).mean()) if dists else 0.0
+            if not self.disable_forearm_reward:
+                terms["forearm_reward"] = 0.5  # hands cannot touch each other with disable_hand_collisions=True
+            reward = sum(terms.values())
+        else:
+            pred = np.concatenate([self.activation.astype(np.float64), [float(self.sustain_activation)]])
+            if self.reward_type == 0:
+                reward = -np.sqrt(np.sum((pred - goal_current) ** 2))
+            else:
+                reward = np.sum(goal_current * np.log(pred + 1e-6) + (1 - goal_current) * np.log(1 - pred + 1e-6))
+            terms = dict(key_press_reward=reward)
+        self.reward_terms = terms
+        discount = 1.0
+        step_type = MID
+        if should_terminate:
+            step_type = LAST
+        elif self.kind == 0 and self.wrong_press_termination and failure:
+            discount, step_type = 0.0, LAST
+        if step_type == LAST:
+            self._need_reset = True
+        return step_type, float(reward), discount, obs

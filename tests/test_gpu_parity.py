@@ -1,0 +1,139 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs,
+plus size-independent properties at the full 4096-env batch.  Tolerances: state within 1e-9 absolute
+per substep over 1000 substeps (north_star asks 1e-5 relative); rewards / observations 1e-9."""
+import numpy as np
+import pytest
+
+import helpers
+from oracle import oracle as O
+from oracle import task_ref
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _dev(a):
+    return torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+
+
+def test_native_library_is_loaded():
+    from robopianist_b200 import native
+    assert native.LIB_PATH.exists()
+    native.lib()
+
+
+def test_self_actuated_piano_trajectory():
+    fm, model, batch = helpers.make_native("self_actuated_piano", nenv=3, lookahead=0, gravity_compensation=False)
+    od = O.OracleData(O.OracleModel(fm))
+    od.reset()
+    rng = np.random.default_rng(1)
+    nv, nu = fm.meta["nv"], fm.meta["nu"]
+    batch.set_state(np.zeros((3, nv)), np.zeros((3, nv)), np.zeros((3, nv)))
+    od.qpos[:] = 0; od.qvel[:] = 0; od.qacc_warmstart[:] = 0
+    worst = 0.0
+    for t in range(400):
+        if t % 10 == 0:
+            ctrl = rng.uniform(0, 1, nu) * fm.actuator_ctrlrange[:, 1] * (rng.random(nu) < 0.3)
+            ct = _dev(np.tile(ctrl, (3, 1)))
+        batch.physics_step(ct.data_ptr(), 1)
+        od.mj_step(ctrl)
+        q, v, _, _ = batch.get_state()
+        worst = max(worst, np.abs(q[0] - od.qpos).max(), np.abs(v[0] - od.qvel).max() * 1e-2)
+        assert (q[0] == q[2]).all()
+    assert worst < 1e-11
+    batch.close()
+
+
+def test_hands_1000_substeps_match_oracle():
+    fm, model, batch = helpers.make_native("piano_with_shadow_hands", nenv=2)
+    om = O.OracleModel(fm); om.set_option(maxcon=24)
+    od = O.OracleData(om); od.reset()
+    nv = fm.meta["nv"]
+    acts = helpers.twinkle_actions()
+    batch.set_state(np.zeros((2, nv)), np.zeros((2, nv)), np.zeros((2, nv)))
+    od.qpos[:] = 0; od.qvel[:] = 0; od.qacc_warmstart[:] = 0
+    worst_q = worst_rel = 0.0
+    contacts_seen = 0
+    for t in range(1000):
+        ctrl = acts[t // 10, :44]
+        if t % 10 == 0:
+            ct = _dev(np.tile(ctrl, (2, 1)))
+        batch.physics_step(ct.data_ptr(), 1)
+        od.mj_step(ctrl)
+        q, v, _, _ = batch.get_state()
+        worst_q = max(worst_q, np.abs(q[0] - od.qpos).max())
+        worst_rel = max(worst_rel, (np.abs(v[0] - od.qvel) / (1e-3 + np.abs(od.qvel))).max())
+        contacts_seen += od.ncon
+        if t % 100 == 99:
+            dg = batch.get_diag()
+            assert dg["ncon"][0] == od.ncon and dg["niter"][0] == od.solver_niter and dg["flags"][0] == 0
+    assert contacts_seen > 500      # the rollout really exercises contacts
+    assert worst_q < 1e-9 and worst_rel < 1e-5
+    batch.close()
+
+
+@pytest.mark.parametrize("song,lookahead", [("TwinkleTwinkleRousseau", 1), ("CMajorScaleTwoHands", 3)])
+def test_task_layer_matches_reference_logic(song, lookahead):
+    """Full rp_step (ctrl write, 10 substeps, key state, 5 reward terms, obs, termination, auto-reset)."""
+    fm, model, batch = helpers.make_native("piano_with_shadow_hands", song=song, nenv=2, lookahead=lookahead)
+    goal, fing = helpers.song_tables(song)
+    ref = task_ref.RefEnv(fm, goal, fing, n_steps_lookahead=lookahead)
+    N = 2
+    obs = torch.empty((N, model.obs_dim), dtype=torch.float64, device="cuda")
+    rew = torch.empty(N, dtype=torch.float64, device="cuda"); dis = torch.empty_like(rew)
+    st = torch.empty(N, dtype=torch.uint8, device="cuda"); terms = torch.empty((N, 5), dtype=torch.float64, device="cuda")
+    batch.reset(None, obs.data_ptr())
+    rst, _, _, robs = ref.reset()
+    torch.cuda.synchronize()
+    assert np.abs(obs[0].cpu().numpy() - robs).max() < 1e-12
+    acts = helpers.twinkle_actions()
+    T = goal.shape[0]
+    for t in range(T + 3):
+        a = acts[t % 158]
+        batch.step(_dev(np.tile(a, (N, 1))).data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr(), terms.data_ptr())
+        rst, rrew, rdis, robs = ref.step(a)
+        torch.cuda.synchronize()
+        assert int(st[0]) == rst, (t, int(st[0]), rst)
+        assert np.abs(obs[0].cpu().numpy() - robs).max() < 1e-9, t
+        if rst != task_ref.FIRST:
+            assert abs(rew[0].item() - rrew) < 1e-9 and dis[0].item() == rdis, (t, rew[0].item(), rrew)
+            tr = list(ref.reward_terms.values())
+            assert np.abs(terms[0].cpu().numpy()[:len(tr)] - np.array(tr)).max() < 1e-9
+    batch.close()
+
+
+def test_full_batch_properties():
+    """4096 envs: identical inputs -> bitwise identical outputs across envs and across runs; noisy envs diverge;
+    episodes end after exactly T steps and auto-reset."""
+    N = 4096
+    acts = helpers.twinkle_actions()
+    finals = []
+    for run in range(2):
+        fm, model, batch = helpers.make_native("piano_with_shadow_hands", nenv=N)
+        obs = torch.empty((N, model.obs_dim), dtype=torch.float64, device="cuda")
+        rew = torch.empty(N, dtype=torch.float64, device="cuda"); dis = torch.empty_like(rew)
+        st = torch.empty(N, dtype=torch.uint8, device="cuda")
+        batch.reset(None, obs.data_ptr())
+        rng = np.random.default_rng(7)
+        for t in range(12):
+            a = np.tile(acts[t], (N, 1))
+            a[N // 2:, :44] += rng.normal(0, 0.02, (N - N // 2, 44))
+            batch.step(_dev(a).data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
+        q, v, _, tix = batch.get_state()
+        finals.append(q.copy())
+        assert (q[: N // 2] == q[0]).all() and (tix == 12).all()
+        assert np.abs(q[N // 2:] - q[0]).max() > 1e-6
+        assert np.isfinite(q).all() and (batch.get_diag()["flags"] == 0).all()
+        batch.close()
+    assert (finals[0] == finals[1]).all()
+
+
+def test_e2e_host_call_and_launch_count():
+    fm, model, batch = helpers.make_native("piano_with_shadow_hands", nenv=64)
+    acts = helpers.twinkle_actions()
+    batch.reset()
+    n0 = batch.launches
+    obs, rew, dis, st, terms = batch.step_host(np.tile(acts[0], (64, 1)))
+    assert batch.launches == n0 + 1 and obs.shape == (64, 329) and np.isfinite(rew).all() and (st == 1).all()
+    assert np.allclose(terms.sum(axis=1), rew)
+    batch.close()

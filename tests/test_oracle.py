@@ -1,0 +1,114 @@
+"""CPU oracle pinned against what can be pinned without MuJoCo: an independent numpy restatement
+of kinematics / inertia (finite differences for the bias force), closed-form key statics, the
+reference's threshold/structural tests, and committed golden trajectories (regression)."""
+import numpy as np
+import pytest
+
+import helpers
+import np_ref
+from oracle import oracle as O
+from oracle import task_ref
+from robopianist_b200.scene import cache
+
+
+@pytest.fixture(scope="module")
+def hands():
+    fm = cache.load_scene(gravity_compensation=True)
+    om = O.OracleModel(fm)
+    om.set_option(maxcon=24)
+    return fm, om
+
+
+def test_mass_matrix_and_bias_vs_numpy(hands):
+    fm, om = hands
+    d = O.OracleData(om)
+    rng = np.random.default_rng(0)
+    lo, hi = fm.jnt_range[:, 0], fm.jnt_range[:, 1]
+    q = lo + rng.random(140) * (hi - lo)
+    dofs = list(range(88, 100)) + [0]
+    v = np.zeros(140); v[dofs] = rng.normal(size=len(dofs))
+    d.qpos[:] = q; d.qvel[:] = v
+    for fn in ("orc_kinematics", "orc_crb", "orc_velocity"):
+        d.call(fn)
+    assert np.abs(np_ref.mass_matrix(fm, q) - d.M).max() < 1e-12
+    fm0 = cache.load_scene(gravity_compensation=False)
+    d0 = O.OracleData(O.OracleModel(fm0))
+    d0.qpos[:] = q; d0.qvel[:] = v
+    for fn in ("orc_kinematics", "orc_crb", "orc_velocity"):
+        d0.call(fn)
+    b = np_ref.bias_fd(fm0, q, v, dofs)
+    assert np.abs(b[dofs] - d0.qfrc_bias[dofs]).max() < 1e-6
+
+
+def test_key_rests_on_lower_limit(hands):
+    fm, om = hands
+    d = O.OracleData(om)
+    d.reset()
+    for _ in range(400):
+        d.mj_step(np.zeros(44))
+    # spring (-1 deg reference) beats gravity: keys sit slightly below 0 on the soft limit, at rest
+    assert (d.qpos[:88] < 0).all() and (d.qpos[:88] > -2e-3).all() and np.abs(d.qvel[:88]).max() < 1e-6
+
+
+def test_wrong_press_terminates_in_one_step():
+    # piano_with_shadow_hands_test.py:228-242: qfrc_applied = 3 on every key -> LAST, discount 0 after one step
+    fm = cache.load_scene()
+    goal, fing = helpers.song_tables("CMajorScaleTwoHands", trim_silence=False)
+    env = task_ref.RefEnv(fm, goal, fing, wrong_press_termination=True)
+    env.reset()
+    env.d.qfrc_applied[:88] = 3.0
+    st, rew, disc, obs = env.step(np.zeros(45))
+    assert st == task_ref.LAST and disc == 0.0
+
+
+def test_episode_length_and_goal_observable():
+    # piano_with_shadow_hands_test.py:119-192: a T-step song ends after exactly T steps; goal obs = roll slice
+    fm = cache.load_scene()
+    goal, fing = helpers.song_tables("CMajorChordProgressionTwoHands", trim_silence=False)
+    goal, fing = goal[:6], fing[:6]
+    env = task_ref.RefEnv(fm, goal, fing, n_steps_lookahead=2)
+    st, r, dsc, obs = env.reset()
+    assert st == task_ref.FIRST and r is None and obs.shape == (88 + 1 + 52 + 3 * 89 + 10,)
+    for t in range(6):
+        st, r, dsc, obs = env.step(np.zeros(45))
+        g = obs[141:141 + 3 * 89].reshape(3, 89)
+        if t < 5:
+            assert st == task_ref.MID
+            for i in range(3):
+                exp = goal[t + 1 + i] if t + 1 + i < 6 else np.zeros(89)
+                assert (g[i] == exp).all()
+    assert st == task_ref.LAST and dsc == 1.0
+
+
+def test_tolerance_values():
+    assert task_ref.tolerance(0.02, (0, 0.05), 0.5) == 1.0
+    assert np.isclose(task_ref.tolerance(0.55, (0, 0.05), 0.5), 0.1)   # value_at_margin
+    assert np.isclose(task_ref.tolerance(-0.5, (0, 0.05), 0.5), 0.1)
+
+
+def test_action_replay_presses_the_goal_keys(hands):
+    """The reference's recorded policy actions (trained on real MuJoCo) played open loop through the
+    oracle still press most goal keys: an external anchor for the restated physics."""
+    fm, om = hands
+    goal, fing = helpers.song_tables()
+    env = task_ref.RefEnv(fm, goal, fing)
+    env.reset()
+    acts = helpers.twinkle_actions()
+    hit = tot = 0
+    for t in range(158):
+        g = goal[t, :88].astype(bool)
+        st, r, dsc, obs = env.step(acts[t])
+        hit += (env.activation & g).sum(); tot += g.sum()
+    assert st == task_ref.LAST and hit / tot > 0.7
+
+
+def test_golden_trajectory_regression(hands):
+    fm, om = hands
+    gold = np.load(helpers.GOLDEN / "oracle_twinkle_traj.npz")
+    d = O.OracleData(om)
+    d.reset()
+    acts = helpers.twinkle_actions()
+    for t in range(60):
+        d.control_step(acts[t, :44])
+        if t in (9, 29, 59):
+            assert np.abs(d.qpos - gold[f"qpos_{t}"]).max() < 1e-9
