@@ -27,7 +27,12 @@ struct Contact {  // lives in shared memory
   double A[9];         // 3x3 block of AR (R on the diagonal)
   double R[3], b[3], f[3], aref[3];
   double mu, invMk;
-  int hand, link, key, pad;  // key = -1: piano base (static)
+  int hand, link, key, dep;  // key = -1: piano base (static)
+  signed char chain[16];     // dof (lane) at depth d of the hand chain
+};
+struct CKey {  // limit row of a key that is coupled to a hand through a contact
+  double J, R, b, AR, ARi, f, invM;
+  int key, active;
 };
 struct RawContact {  // narrowphase output before sorting
   double dist, pos[3], n[3];
@@ -36,13 +41,19 @@ struct RawContact {  // narrowphase output before sorting
 };
 
 struct Smem {
-  double Minv[RP_NHMAX][NL][NL];
+  double Minv[RP_NHMAX][NL][32];  // rows padded to 32 columns (zeros) so every lane can read its column
   double S[RP_NHMAX][NL][6];
   double qk[NK], vk[NK], vak[NK];
-  double wbuf[RP_NHMAX][NL];
-  double colk[RP_NHMAX][NL];
+  double wbuf[RP_NHMAX][32];
+  double colk[RP_NHMAX][32];
+  double colk2[RP_NHMAX][32];
   double actf[RP_NHMAX][RP_NAH];
   double vh[RP_NHMAX][NL];  // hand joint velocities (for chain walks)
+  double kfrc[NK], kqs[NK], kfc[NK];  // per key: qfrc_smooth, qacc_smooth, constraint force J^T f
+  double stash[RP_NHMAX][NL][2];      // qfrc_smooth, qacc_smooth of the hand dofs (parked during PGS)
+  CKey ck[MAXCON];                    // limit rows of keys that also carry contacts
+  signed char keyslot[NK];            // index into ck[] (-1: key not in contact)
+  int nck, pad2;
   union {
     double acc[RP_NHMAX][NL][16];  // upward accumulation scratch: F (6) + composite inertia (10)
     struct {
@@ -83,6 +94,40 @@ struct KeyRow {       // active limit row of a key (at most one side can be acti
 
 }  // namespace
 
+// In-place inverse of the NH symmetric positive definite 26x26 matrices held in sm.Minv (rows padded
+// to 32): symmetric sweep operator, each lane keeps its own column in registers, column k is
+// exchanged through shared memory once per step (double buffered, one __syncwarp per step).
+// After 26 sweeps the registers hold -A^-1.  Branch-free; padded lanes mirror column 0.
+template <int NH>
+__device__ __forceinline__ void sweep_inverse(Smem& sm, int lane, double (&col)[NH > 0 ? NH : 1][NL]) {
+  const int lc = lane < NL ? lane : 0;
+#pragma unroll
+  for (int h = 0; h < NH; h++) {
+#pragma unroll
+    for (int i = 0; i < NL; i++) col[h][i] = sm.Minv[h][i][lc];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < NL; k++) {
+    double (*buf)[32] = (k & 1) ? sm.colk2 : sm.colk;
+#pragma unroll
+    for (int h = 0; h < NH; h++) buf[h][lane] = col[h][k];  // A[lane][k] == A[k][lane]
+    __syncwarp();
+    const bool isk = lc == k;
+#pragma unroll
+    for (int h = 0; h < NH; h++) {
+      const double dinv = 1.0 / buf[h][k];
+      const double t = buf[h][lc] * dinv;  // A[k][j] / d
+#pragma unroll
+      for (int i = 0; i < NL; i++) {
+        const double ci = buf[h][i];
+        const double upd = isk ? ci * dinv : col[h][i] - ci * t;
+        col[h][i] = (i == k) ? (isk ? -dinv : t) : upd;
+      }
+    }
+  }
+}
+
 // The kernel proper is large; it is written as one function so that lane-owned state stays in
 // registers across the stages of a substep.
 template <int NH>
@@ -90,7 +135,8 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const RpDevModel* __restrict__ dm = a.dm;
-  const int lane = threadIdx.x;
+  int lane;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // opaque: keeps the compiler from re-reading S2R in loops
   const int env = blockIdx.x;
   if (env >= a.nenv) return;
   const int nvtot = NK + NH * NL;
@@ -157,6 +203,9 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
     ldep[h] = hl ? dm->link_depth[h][lane] : -1;
     ljt[h] = hl ? dm->link_jtype[h][lane] : 0;
   }
+  int lsub[NH > 0 ? NH : 1], ldc[NH > 0 ? NH : 1];  // subtree size, depth clamped to >= 0
+#pragma unroll
+  for (int h = 0; h < NH; h++) { lsub[h] = hl ? dm->link_subtree[h][lane] : 0; ldc[h] = ldep[h] > 0 ? ldep[h] : 0; }
   const double hstep = dm->h;
   const double g3[3] = {dm->gravity[0], dm->gravity[1], dm->gravity[2]};
   const int nsub = (a.mode == RP_MODE_RESET || do_reset) ? 0 : a.nsub;
@@ -168,6 +217,12 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
 
   // link world poses (kept for the task epilogue)
   double xp[NH > 0 ? NH : 1][3], xq[NH > 0 ? NH : 1][4];
+#ifdef RP_PROFILE
+  long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#define TICK(i) { long long tn = clock64(); tacc[i] += tn - tlast; tlast = tn; }
+#else
+#define TICK(i)
+#endif
 
   // =============================================================================================
   for (int sub = 0; sub <= nsub; sub++) {
@@ -222,6 +277,7 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
         }
       }
     }
+    TICK(0)
     if (last_pass) break;
 
     // ------------------------------------------------------------------ publish S, velocities
@@ -322,7 +378,7 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
             if (d == ldep[h]) Mrow[h][d] += dm->link_armature[h][lane];
           }
         }
-        for (int j = 0; j < NL; j++) sm.Minv[h][lane][j] = 0;
+        for (int j = 0; j < 32; j++) sm.Minv[h][lane][j] = 0;
       }
     }
     __syncwarp();
@@ -344,36 +400,25 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
       double* dbg = a.dbg + (size_t)env * RP_DBG_STRIDE;
       for (int i = 0; i < NL; i++) if (hl) dbg[RP_DBG_M + i * NL + lane] = sm.Minv[0][i][lane];
     }
-    // ---------------------------------------------------------------- invert M (Gauss-Jordan)
+    TICK(1)
+    // ---------------------------------------------------------------- invert M (symmetric sweep)
     if (NH > 0) {
-      for (int k = 0; k < NL; k++) {
+      double col[NH > 0 ? NH : 1][NL];
+      sweep_inverse<NH>(sm, lane, col);
+      __syncwarp();
 #pragma unroll
-        for (int h = 0; h < NH; h++) if (hl) sm.colk[h][lane] = sm.Minv[h][lane][k];
-        __syncwarp();
+      for (int h = 0; h < NH; h++) {
 #pragma unroll
-        for (int h = 0; h < NH; h++) {
-          if (hl) {
-            double p = 1.0 / sm.colk[h][k];
-            if (lane != k) {
-              double akj = sm.Minv[h][k][lane] * p;
-              for (int i = 0; i < NL; i++)
-                if (i != k) sm.Minv[h][i][lane] -= sm.colk[h][i] * akj;
-              sm.Minv[h][k][lane] = akj;
-            } else {
-              for (int i = 0; i < NL; i++)
-                if (i != k) sm.Minv[h][i][k] = -sm.colk[h][i] * p;
-              sm.Minv[h][k][k] = p;
-            }
-          }
-        }
-        __syncwarp();
+        for (int i = 0; i < NL; i++) sm.Minv[h][i][lane] = hl ? -col[h][i] : 0.0;
       }
+      __syncwarp();
     }
     if (a.dbg && sub == 0 && NH > 0) {
       double* dbg = a.dbg + (size_t)env * RP_DBG_STRIDE;
       for (int i = 0; i < NL; i++) if (hl) dbg[RP_DBG_MINV + i * NL + lane] = sm.Minv[0][i][lane];
     }
 
+    TICK(2)
     // ------------------------------------------------------------------ actuation (lane = actuator)
 #pragma unroll
     for (int h = 0; h < NH; h++) {
@@ -443,6 +488,9 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
         kM[s] = dm->key_M[k];
         ks_qfrc[s] = passive - bias + actq;
         ks_qacc[s] = ks_qfrc[s] / kM[s];
+        sm.kfrc[k] = ks_qfrc[s];
+        sm.kqs[k] = ks_qacc[s];
+        sm.keyslot[k] = -1;
         double lo = dm->key_range[k][0], hi = dm->key_range[k][1];
         double dlo = qk[s] - lo, dhi = hi - qk[s];
         double J = 0, pos = 0;
@@ -500,6 +548,7 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
       lm_mask[h] = __ballot_sync(FULL, lm_on);
     }
 
+    TICK(3)
     // ------------------------------------------------------------------ collision (lane = hand geom)
     __syncwarp();
     if (lane == 0) { sm.nraw = 0; sm.ncon = 0; sm.overflow = 0; }
@@ -514,43 +563,51 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
         for (int k = 0; k < 3; k++) lp[k] = shfl(xp[h][k], gl);
 #pragma unroll
         for (int k = 0; k < 4; k++) lq[k] = shfl(xq[h][k], gl);
+        double gc[3] = {0, 0, 0}, gax[3] = {0, 0, 1}, rad = 0, half = 0, gmargin = 0, rb = 0;
+        int i0 = 0, i1 = -1, ncand = 0, gtype = 2, gorder = 0;
         if (isg) {
-          double xm[9], gc[3], gax[3], tmp[3];
+          double xm[9], tmp[3];
           rp::quat2mat(xm, lq);
+          gtype = dm->geom_type[h][lane];
+          gorder = dm->geom_order[h][lane];
           double gpos[3] = {dm->geom_pos[h][lane][0], dm->geom_pos[h][lane][1], dm->geom_pos[h][lane][2]};
           double gaxl[3] = {dm->geom_axis[h][lane][0], dm->geom_axis[h][lane][1], dm->geom_axis[h][lane][2]};
           rp::mat_vec(tmp, xm, gpos);
           for (int k = 0; k < 3; k++) gc[k] = lp[k] + tmp[k];
           rp::mat_vec(gax, xm, gaxl);
-          double rad = dm->geom_size[h][lane][0], half = dm->geom_type[h][lane] == 3 ? dm->geom_size[h][lane][1] : 0.0;
-          double gmargin = dm->geom_gp[h][lane].margin;
-          double rb = rad + half;
+          rad = dm->geom_size[h][lane][0];
+          half = gtype == 3 ? dm->geom_size[h][lane][1] : 0.0;
+          gmargin = dm->geom_gp[h][lane].margin;
+          rb = rad + half;
           // candidate piano boxes: base + keys whose y-extent overlaps
-          int i0 = (int)floor((gc[1] - rb - 0.02 - dm->lattice_y0) / dm->lattice_pitch);
-          int i1 = (int)ceil((gc[1] + rb + 0.02 - dm->lattice_y0) / dm->lattice_pitch);
+          i0 = (int)floor((gc[1] - rb - 0.02 - dm->lattice_y0) / dm->lattice_pitch);
+          i1 = (int)ceil((gc[1] + rb + 0.02 - dm->lattice_y0) / dm->lattice_pitch);
           i0 = max(i0, 0); i1 = min(i1, 51);
-          int ncand = (i1 >= i0) ? 2 * (i1 - i0 + 1) + 2 : 0;
-          for (int ci = -1; ci < ncand; ci++) {
-            int key;
-            if (ci < 0) { if (!dm->has_base) continue; key = -1; }
+          ncand = (i1 >= i0) ? 2 * (i1 - i0 + 1) + 1 : 0;
+        }
+        // structured, warp-uniform trip count (no continue/break: keeps the warp reconvergent)
+        const int ncand_max = __reduce_max_sync(FULL, isg ? ncand : 0);
+        for (int ci = -1; ci < ncand_max; ci++) {
+          // candidate -> piano box: ci = -1 base; 2k / 2k+1 = white / following black of slot i0+k;
+          // last = the black key before the first slot
+          int key = -2;
+          if (isg && ci < ncand) {
+            if (ci < 0) key = dm->has_base ? -1 : -2;
+            else if (ci == ncand - 1) key = i0 > 0 ? dm->black_after[i0 - 1] : -1, key = key < 0 ? -2 : key;
             else {
               int slot = i0 + (ci >> 1);
-              if (ci == ncand - 2 || ci == ncand - 1) {  // trailing: black key before the first slot
-                if (ci == ncand - 1) continue;
-                key = i0 > 0 ? dm->black_after[i0 - 1] : -1;
-                if (key < 0) continue;
-              } else {
-                key = (ci & 1) ? dm->black_after[slot] : dm->white_of_slot[slot];
-                if (key < 0) continue;
-              }
+              key = (ci & 1) ? dm->black_after[slot] : dm->white_of_slot[slot];
+              key = key < 0 ? -2 : key;
             }
+          }
+          if (key > -2) {
             // box pose
             double bpos[3], bhalf[3], R[9];
-            double margin, gapv;
+            double margin;
             if (key < 0) {
               for (int k = 0; k < 3; k++) { bpos[k] = dm->base_pos[k]; bhalf[k] = dm->base_half[k]; }
               R[0] = R[4] = R[8] = 1; R[1] = R[2] = R[3] = R[5] = R[6] = R[7] = 0;
-              margin = fmax(gmargin, dm->base_gp.margin); gapv = fmax(dm->geom_gp[h][lane].gap, dm->base_gp.gap);
+              margin = fmax(gmargin, dm->base_gp.margin);
             } else {
               double ax[3] = {dm->key_axis[key][0], dm->key_axis[key][1], dm->key_axis[key][2]};
               double sn, cs;
@@ -564,44 +621,49 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
               double jp[3] = {dm->key_jpos[key][0], dm->key_jpos[key][1], dm->key_jpos[key][2]}, rj[3];
               rp::mat_vec(rj, R, jp);
               for (int k = 0; k < 3; k++) { bpos[k] = dm->key_pos[key][k] + jp[k] - rj[k]; bhalf[k] = dm->key_half[key][k]; }
-              margin = fmax(gmargin, dm->key_gp[key].margin); gapv = fmax(dm->geom_gp[h][lane].gap, dm->key_gp[key].gap);
+              margin = fmax(gmargin, dm->key_gp[key].margin);
             }
-            (void)gapv;
             double rel[3] = {gc[0] - bpos[0], gc[1] - bpos[1], gc[2] - bpos[2]}, c[3];
             rp::matT_vec(c, R, rel);
             double bound = rb + margin;
-            if (rp::point_box_d2(c, bhalf) > bound * bound) continue;
-            // narrowphase: sphere, or capsule end points + interior closest point
-            int ntest = 1;
-            double pts[3][3];
-            if (dm->geom_type[h][lane] == 2) {
-              for (int k = 0; k < 3; k++) pts[0][k] = c[k];
-            } else {
-              double ax[3];
-              rp::matT_vec(ax, R, gax);
-              for (int k = 0; k < 3; k++) { pts[0][k] = c[k] - half * ax[k]; pts[1][k] = c[k] + half * ax[k]; }
-              ntest = 2;
-              double t = rp::segment_box_closest_t(pts[0], pts[1], bhalf);
-              if (t > 1e-9 && t < 1 - 1e-9) {
-                for (int k = 0; k < 3; k++) pts[2][k] = pts[0][k] + t * (pts[1][k] - pts[0][k]);
-                ntest = 3;
+            if (rp::point_box_d2(c, bhalf) <= bound * bound) {
+              // narrowphase: sphere, or capsule end points + interior closest point
+              int ntest = 1;
+              double pts[3][3];
+              if (gtype == 2) {
+                for (int k = 0; k < 3; k++) { pts[0][k] = c[k]; pts[1][k] = c[k]; pts[2][k] = c[k]; }
+              } else {
+                double ax[3];
+                rp::matT_vec(ax, R, gax);
+                for (int k = 0; k < 3; k++) { pts[0][k] = c[k] - half * ax[k]; pts[1][k] = c[k] + half * ax[k]; pts[2][k] = c[k]; }
+                ntest = 2;
+                double t = rp::segment_box_closest_t(pts[0], pts[1], bhalf);
+                if (t > 1e-9 && t < 1 - 1e-9) {
+                  for (int k = 0; k < 3; k++) pts[2][k] = pts[0][k] + t * (pts[1][k] - pts[0][k]);
+                  ntest = 3;
+                }
               }
-            }
-            for (int ti = 0; ti < ntest; ti++) {
-              double n[3], p[3];
-              double dist = rp::sphere_box(pts[ti], rad, bhalf, n, p);
-              if (!(dist < margin)) continue;
-              int slot = atomicAdd(&sm.nraw, 1);
-              if (slot >= MAXCON) { sm.overflow = 1; continue; }
-              RawContact& rc = sm.u.c.raw[slot];
-              double nw[3], pw[3];
-              rp::mat_vec(nw, R, n);
-              rp::mat_vec(pw, R, p);
-              rc.dist = dist;
-              for (int k = 0; k < 3; k++) { rc.n[k] = nw[k]; rc.pos[k] = bpos[k] + pw[k]; }
-              rc.hand = h; rc.geom = lane; rc.key = key; rc.sub = ti;
-              // MuJoCo order: piano geom (base, then keys) major, hand geom (model order) minor
-              rc.sortkey = (unsigned)(((key + 1) * 64 + dm->geom_order[h][lane]) * 4 + ti);
+#pragma unroll
+              for (int ti = 0; ti < 3; ti++) {
+                double n[3], p[3];
+                double dist = rp::sphere_box(pts[ti], rad, bhalf, n, p);
+                if (ti < ntest && dist < margin) {
+                  int slot = atomicAdd(&sm.nraw, 1);
+                  if (slot < MAXCON) {
+                    RawContact& rc = sm.u.c.raw[slot];
+                    double nw[3], pw[3];
+                    rp::mat_vec(nw, R, n);
+                    rp::mat_vec(pw, R, p);
+                    rc.dist = dist;
+                    for (int k = 0; k < 3; k++) { rc.n[k] = nw[k]; rc.pos[k] = bpos[k] + pw[k]; }
+                    rc.hand = h; rc.geom = lane; rc.key = key; rc.sub = ti;
+                    // MuJoCo order: piano geom (base, then keys) major, hand geom (model order) minor
+                    rc.sortkey = (unsigned)(((key + 1) * 64 + gorder) * 4 + ti);
+                  } else {
+                    sm.overflow = 1;
+                  }
+                }
+              }
             }
           }
         }
@@ -609,6 +671,7 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
       }
     }
     __syncwarp();
+    TICK(4)
     int nraw = min(sm.nraw, MAXCON);
     if (sm.nraw > MAXCON) flags |= 1;
     // NOTE: on overflow the kept subset depends on atomic order; the flag marks the env invalid.
@@ -649,6 +712,8 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
       cn.mu = mu;
       // Jacobian: rows = frame directions, body2 (key) minus body1 (hand link)
       int dep = dm->link_depth[h][link];
+      cn.dep = dep;
+      for (int d = 0; d < 16; d++) cn.chain[d] = (signed char)(d <= dep ? dm->link_anc[h][link][d] : 0);
       for (int r = 0; r < 3; r++) {
         const double* dir = c_frame + 3 * r;
         for (int d = 0; d < MAXD; d++) {
@@ -734,6 +799,24 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
     }
     __syncwarp();
 
+    TICK(5)
+    // =============================================================== coupled keys
+    // keys touched by a contact get their limit row solved inside the Gauss-Seidel sweep; all other
+    // key rows are independent 1x1 problems that are finished in closed form below.
+    {
+      bool firstc = false;
+      int mykey = -1;
+      if (lane < ncon) {
+        mykey = sm.u.c.con[lane].key;
+        firstc = mykey >= 0 && (lane == 0 || sm.u.c.con[lane - 1].key != mykey);
+      }
+      unsigned fmask = __ballot_sync(FULL, firstc);
+      if (firstc) sm.keyslot[mykey] = (signed char)__popc(fmask & ((1u << lane) - 1u));
+      if (lane == 0) sm.nck = __popc(fmask);
+    }
+    __syncwarp();
+    const int nck = sm.nck;
+
     // =============================================================== warm start
     // forces from qacc_warmstart through the primal map; kept only if the dual cost is negative
 #pragma unroll
@@ -774,7 +857,8 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
     }
     __syncwarp();
     // va = Minv J^T f ; cost = 0.5 f'(J va) + 0.5 sum R f^2 + f'b
-    double va[NH > 0 ? NH : 1], vakr[3];
+    double va[NH > 0 ? NH : 1];
+    double improvement0 = 0;  // contribution of the closed-form key rows to the first sweep
     {
       double cost = 0;
       double wq[NH > 0 ? NH : 1];
@@ -803,13 +887,13 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
         if (k < NK) {
           wqk[s] = krow[s].J * krow[s].f;
           cost += 0.5 * krow[s].R * krow[s].f * krow[s].f + krow[s].f * krow[s].b;
-          for (int c = 0; c < ncon; c++) {
-            const Contact& cn = sm.u.c.con[c];
-            if (cn.key == k) wqk[s] += cn.Jk[0] * cn.f[0] + cn.Jk[1] * cn.f[1] + cn.Jk[2] * cn.f[2];
-          }
-          vakr[s] = wqk[s] / kM[s];
-          cost += 0.5 * wqk[s] * vakr[s];
-        } else vakr[s] = 0;
+          if (sm.keyslot[k] >= 0)
+            for (int c = 0; c < ncon; c++) {
+              const Contact& cn = sm.u.c.con[c];
+              if (cn.key == k) wqk[s] += cn.Jk[0] * cn.f[0] + cn.Jk[1] * cn.f[1] + cn.Jk[2] * cn.f[2];
+            }
+          cost += 0.5 * wqk[s] * wqk[s] / kM[s];
+        }
       }
       if (lane < ncon) {
         const Contact& cn = sm.u.c.con[lane];
@@ -824,151 +908,189 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
         cost += 0.5 * wq[h] * s2;
       }
       cost = warp_sum(cost);
-      if (cost > 0) {
+      const bool keep = !(cost > 0);
+      if (!keep) {
 #pragma unroll
         for (int h = 0; h < NH; h++) { fr_f[h] = 0; lm_f[h] = 0; va[h] = 0; }
-#pragma unroll
-        for (int s = 0; s < 3; s++) { krow[s].f = 0; vakr[s] = 0; }
         if (lane < ncon) { Contact& cn = sm.u.c.con[lane]; cn.f[0] = cn.f[1] = cn.f[2] = 0; }
       }
       if (a.dbg && sub == 0 && lane == 0) a.dbg[(size_t)env * RP_DBG_STRIDE + RP_DBG_SCALARS + 3] = cost;
-    }
-    __syncwarp();
+      // key rows: uncoupled ones are solved exactly now (one Gauss-Seidel update of a 1x1 system is
+      // its solution); coupled ones move to the ck[] list with their warm-start force
 #pragma unroll
-    for (int s = 0; s < 3; s++) { int k = lane + 32 * s; if (k < NK) sm.vak[k] = vakr[s]; }
+      for (int s = 0; s < 3; s++) {
+        int k = lane + 32 * s;
+        if (k < NK) {
+          double f = keep ? krow[s].f : 0.0;
+          int slot = sm.keyslot[k];
+          if (slot < 0) {
+            if (krow[s].active) {
+              double res = krow[s].b + krow[s].AR * f;
+              double fn = f - res * krow[s].ARinv;
+              if (fn < 0) fn = 0;
+              double dl = fn - f;
+              improvement0 -= 0.5 * dl * dl * krow[s].AR + dl * res;
+              f = fn;
+            }
+            sm.kfc[k] = krow[s].J * f;
+            sm.vak[k] = krow[s].J * f / kM[s];
+          } else {
+            CKey& ck = sm.ck[slot];
+            ck.key = k; ck.active = krow[s].active;
+            ck.J = krow[s].J; ck.R = krow[s].R; ck.b = krow[s].b; ck.AR = krow[s].AR; ck.ARi = krow[s].ARinv;
+            ck.f = f; ck.invM = 1.0 / kM[s];
+            sm.vak[k] = (keep ? wqk[s] : 0.0) / kM[s];
+          }
+        }
+      }
+    }
+    // park what is only needed after the sweep
+#pragma unroll
+    for (int h = 0; h < NH; h++) if (hl) { sm.stash[h][lane][0] = qfrc_smooth[h]; sm.stash[h][lane][1] = qacc_smooth[h]; }
     __syncwarp();
 
+    TICK(6)
     // =============================================================== PGS
+    // Row order inside a sweep follows MuJoCo: friction-loss dofs, joint limits (keys, then hand
+    // joints), contacts.  Rows that do not interact (the two hands, untouched keys) are advanced
+    // together.  1-D rows: the candidate update is evaluated by every lane for its own row (no
+    // divergence) and only lane i's result is committed at step i.
     int iter = 0;
     const int maxiter = a.iterations > 0 ? a.iterations : dm->iterations;
     const double tol = a.tolerance >= 0 ? a.tolerance : dm->tol;
     const unsigned anyrow_fr = (NH > 0 ? fr_mask[0] : 0u) | (NH > 1 ? fr_mask[NH > 1 ? 1 : 0] : 0u);
     const unsigned anyrow_lm = (NH > 0 ? lm_mask[0] : 0u) | (NH > 1 ? lm_mask[NH > 1 ? 1 : 0] : 0u);
+    double fr_ARi[NH > 0 ? NH : 1], fr_base[NH > 0 ? NH : 1], lm_ARi[NH > 0 ? NH : 1], lm_base[NH > 0 ? NH : 1];
+#pragma unroll
+    for (int h = 0; h < NH; h++) {
+      fr_ARi[h] = 1.0 / fr_AR[h]; lm_ARi[h] = 1.0 / lm_AR[h];
+      fr_base[h] = fr_b[h] + fr_R[h] * fr_f[h];
+      lm_base[h] = lm_b[h] + lm_R[h] * lm_f[h];
+      if (!(hl && (fr_mask[h] >> lane & 1))) fr_loss[h] = 0;  // inactive rows clamp to zero
+      if (!(hl && (lm_mask[h] >> lane & 1))) { lm_J[h] = 0; lm_ARi[h] = 0; lm_base[h] = 0; }
+    }
     while (iter < maxiter) {
-      double improvement = 0;
-      // ---- friction-loss rows, dof order, both hands in lock-step
+      double improvement = iter == 0 ? improvement0 : 0.0;
+      // ---- friction-loss rows, dof order, both hands in lock-step (branch-free, hands interleaved)
       if (NH > 0) {
         for (int i = 0; i < NL; i++) {
-          if (!(anyrow_fr >> i & 1)) continue;
-          double delta[NH > 0 ? NH : 1];
+          const bool mine = lane == i;
+          double res[NH > 0 ? NH : 1], fn[NH > 0 ? NH : 1], dl[NH > 0 ? NH : 1], dbc[NH > 0 ? NH : 1], mrow[NH > 0 ? NH : 1];
 #pragma unroll
           for (int h = 0; h < NH; h++) {
-            double dl = 0;
-            if (lane == i && (fr_mask[h] >> i & 1)) {
-              double res = fr_b[h] + fr_R[h] * fr_f[h] + va[h];
-              double fo = fr_f[h], fn = fo - res / fr_AR[h];
-              fn = fmin(fmax(fn, -fr_loss[h]), fr_loss[h]);
-              dl = fn - fo;
-              double change = 0.5 * dl * dl * fr_AR[h] + dl * res;
-              if (change > 1e-10) { dl = 0; change = 0; fn = fo; }
-              fr_f[h] = fn;
-              improvement -= change;
-            }
-            delta[h] = shfl(dl, i);
+            mrow[h] = sm.Minv[h][i][lane];
+            res[h] = fr_base[h] + va[h];
+            double x = fr_f[h] - res[h] * fr_ARi[h];
+            double lo = -fr_loss[h], fx = x;   // two independent selects: stays predicated
+            fx = x < lo ? lo : fx;
+            fx = x > fr_loss[h] ? fr_loss[h] : fx;
+            fn[h] = fx;
+            dl[h] = fn[h] - fr_f[h];
           }
 #pragma unroll
-          for (int h = 0; h < NH; h++) if (hl) va[h] += sm.Minv[h][i][lane] * delta[h];
+          for (int h = 0; h < NH; h++) dbc[h] = shfl(dl[h], i);
+#pragma unroll
+          for (int h = 0; h < NH; h++) {
+            va[h] += mrow[h] * dbc[h];
+            improvement -= mine ? dl[h] * (0.5 * dl[h] * fr_AR[h] + res[h]) : 0.0;
+            fr_f[h] = mine ? fn[h] : fr_f[h];
+            fr_base[h] = mine ? fr_b[h] + fr_R[h] * fn[h] : fr_base[h];
+          }
         }
       }
-      // ---- key limit rows (mutually independent: lane-parallel)
-#pragma unroll
-      for (int s = 0; s < 3; s++) {
-        if (krow[s].active) {
-          int k = lane + 32 * s;
-          double vak = sm.vak[k];
-          double res = krow[s].b + krow[s].R * krow[s].f + krow[s].J * vak;
-          double fo = krow[s].f, fn = fo - res * krow[s].ARinv;
-          if (fn < 0) fn = 0;
-          double dl = fn - fo;
-          double change = 0.5 * dl * dl * krow[s].AR + dl * res;
-          if (change > 1e-10) { dl = 0; change = 0; fn = fo; }
-          krow[s].f = fn;
-          improvement -= change;
-          sm.vak[k] = vak + krow[s].J * dl / kM[s];
-        }
+      TICK(9)
+      // ---- limit rows of keys that carry contacts (uniform scalar work, values in shared memory)
+      for (int c = 0; c < nck; c++) {
+        CKey& ck = sm.ck[c];
+        double vak = sm.vak[ck.key], f = ck.f;
+        double res = ck.b + ck.R * f + ck.J * vak;
+        double fn = f - res * ck.ARi;
+        fn = (fn < 0 || !ck.active) ? 0.0 : fn;
+        double dl = fn - f;
+        __syncwarp();
+        improvement -= lane == 0 ? dl * (0.5 * dl * ck.AR + res) : 0.0;
+        ck.f = fn;                                    // every lane stores the same value
+        sm.vak[ck.key] = vak + ck.J * dl * ck.invM;
+        __syncwarp();
       }
       // ---- hand limit rows
       if (NH > 0) {
-        for (int i = 0; i < NL; i++) {
-          if (!(anyrow_lm >> i & 1)) continue;
-          double delta[NH > 0 ? NH : 1];
+        for (int i = 0; i < NL; i++) if (anyrow_lm >> i & 1) {
+          const bool mine = lane == i;
 #pragma unroll
           for (int h = 0; h < NH; h++) {
-            double dl = 0;
-            if (lane == i && (lm_mask[h] >> i & 1)) {
-              double res = lm_b[h] + lm_R[h] * lm_f[h] + lm_J[h] * va[h];
-              double fo = lm_f[h], fn = fo - res / lm_AR[h];
-              if (fn < 0) fn = 0;
-              dl = fn - fo;
-              double change = 0.5 * dl * dl * lm_AR[h] + dl * res;
-              if (change > 1e-10) { dl = 0; change = 0; fn = fo; }
-              lm_f[h] = fn;
-              improvement -= change;
-              dl *= lm_J[h];
-            }
-            delta[h] = shfl(dl, i);
+            double res = lm_base[h] + lm_J[h] * va[h];
+            double x = lm_f[h] - res * lm_ARi[h];
+            double fn = x < 0 ? 0.0 : x;
+            double dl = fn - lm_f[h];
+            double dbc = shfl(lm_J[h] * dl, i);
+            improvement -= mine ? dl * (0.5 * dl * lm_AR[h] + res) : 0.0;
+            lm_f[h] = mine ? fn : lm_f[h];
+            lm_base[h] = mine ? lm_b[h] + lm_R[h] * fn : lm_base[h];
+            va[h] += sm.Minv[h][i][lane] * dbc;
           }
-#pragma unroll
-          for (int h = 0; h < NH; h++) if (hl) va[h] += sm.Minv[h][i][lane] * delta[h];
         }
       }
-      __syncwarp();
+      TICK(10)
       // ---- contacts, sorted order
       for (int c = 0; c < ncon; c++) {
         Contact& cn = sm.u.c.con[c];
-        const int h = cn.hand, link = cn.link, key = cn.key;
-        double part[3] = {0, 0, 0};
-        double vsel = (NH > 1 && h == 1) ? va[NH > 1 ? 1 : 0] : va[0];
-        bool anc = hl && lane <= link && link < lane + dm->link_subtree[h][lane];
-        int dme = (NH > 1 && h == 1) ? ldep[NH > 1 ? 1 : 0] : ldep[0];
-        if (anc) {
+        const int h = cn.hand, link = cn.link, key = cn.key, dep = cn.dep;
+        const bool h1 = NH > 1 && h == 1;
+        const double vsel = h1 ? va[NH > 1 ? 1 : 0] : va[0];
+        const int mysub = h1 ? lsub[NH > 1 ? 1 : 0] : lsub[0];
+        const int dme = h1 ? ldc[NH > 1 ? 1 : 0] : ldc[0];
+        const bool anc = lane <= link && link < lane + mysub;
+        const double j0 = anc ? cn.Jc[0][dme] : 0.0, j1 = anc ? cn.Jc[1][dme] : 0.0, j2 = anc ? cn.Jc[2][dme] : 0.0;
+        double part[3] = {j0 * vsel, j1 * vsel, j2 * vsel};
 #pragma unroll
-          for (int r = 0; r < 3; r++) part[r] = cn.Jc[r][dme] * vsel;
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int r = 0; r < 3; r++) part[r] += __shfl_xor_sync(FULL, part[r], o);
         }
         double res[3], f[3];
-#pragma unroll
-        for (int r = 0; r < 3; r++) part[r] = warp_sum(part[r]);
-        double vak = key >= 0 ? sm.vak[key] : 0.0;
+        const double vak = sm.vak[key >= 0 ? key : 0];
+        const double jkm = key >= 0 ? 1.0 : 0.0;
 #pragma unroll
         for (int r = 0; r < 3; r++) {
           f[r] = cn.f[r];
-          res[r] = cn.b[r] + cn.R[r] * f[r] + part[r] + cn.Jk[r] * vak;
+          res[r] = cn.b[r] + cn.R[r] * f[r] + part[r] + jkm * cn.Jk[r] * vak;
         }
         double A[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) A[k] = cn.A[k];
-        double fold[3] = {f[0], f[1], f[2]};
-        double change = rp::pgs_elliptic_update(A, res, f, cn.mu);
-        double df[3] = {f[0] - fold[0], f[1] - fold[1], f[2] - fold[2]};
+        const double fold[3] = {f[0], f[1], f[2]};
+        const double change = rp::pgs_elliptic_update(A, res, f, cn.mu);
+        const double df[3] = {f[0] - fold[0], f[1] - fold[1], f[2] - fold[2]};
         __syncwarp();
-        if (lane == 0) {
-          improvement -= change;
-          cn.f[0] = f[0]; cn.f[1] = f[1]; cn.f[2] = f[2];
-          if (key >= 0) sm.vak[key] = vak + (cn.Jk[0] * df[0] + cn.Jk[1] * df[1] + cn.Jk[2] * df[2]) * cn.invMk;
-        }
+        improvement -= lane == 0 ? change : 0.0;
+        cn.f[0] = f[0]; cn.f[1] = f[1]; cn.f[2] = f[2];  // identical on every lane
+        if (key >= 0) sm.vak[key] = vak + (cn.Jk[0] * df[0] + cn.Jk[1] * df[1] + cn.Jk[2] * df[2]) * cn.invMk;
         // hand side: w = Jc^T df on the chain, va += Minv[:,chain] w
-        double w = anc ? (cn.Jc[0][dme] * df[0] + cn.Jc[1][dme] * df[1] + cn.Jc[2][dme] * df[2]) : 0.0;
-        int dep = dm->link_depth[h][link];
+        const double w = j0 * df[0] + j1 * df[1] + j2 * df[2];
         double acc = 0;
         for (int d = 0; d <= dep; d++) {
-          int j = dm->link_anc[h][link][d];
-          double wj = shfl(w, j);
-          if (hl) acc += sm.Minv[h][j][lane] * wj;
+          const int j = cn.chain[d];
+          const double wj = shfl(w, j);
+          acc += sm.Minv[h][j][lane] * wj;
         }
-        if (NH > 1 && h == 1) va[NH > 1 ? 1 : 0] += acc; else va[0] += acc;
+        if (h1) va[NH > 1 ? 1 : 0] += acc; else va[0] += acc;
         __syncwarp();
       }
+      TICK(11)
       improvement = warp_sum(improvement) * dm->solver_scale;
       iter++;
       if (improvement < tol) break;
     }
     niter_last = iter;
 
+    TICK(7)
     // =============================================================== dual -> primal, Euler
     // qacc = qacc_smooth + va ; qfrc_constraint = J^T f
     double qacc[NH > 0 ? NH : 1], qfrc_c[NH > 0 ? NH : 1];
 #pragma unroll
     for (int h = 0; h < NH; h++) {
+      if (hl) { qfrc_smooth[h] = sm.stash[h][lane][0]; qacc_smooth[h] = sm.stash[h][lane][1]; }
       qacc[h] = qacc_smooth[h] + va[h];
       qfrc_c[h] = 0;
       if (hl) {
@@ -983,19 +1105,24 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
         }
       }
     }
-    double kq_acc[3], kq_frc[3];
+    // constraint force on coupled keys: limit row + contacts, accumulated in contact order
+    if (lane == 0) {
+      for (int c = 0; c < nck; c++) sm.kfc[sm.ck[c].key] = sm.ck[c].J * sm.ck[c].f;
+      for (int c = 0; c < ncon; c++) {
+        const Contact& cn = sm.u.c.con[c];
+        if (cn.key >= 0) sm.kfc[cn.key] += cn.Jk[0] * cn.f[0] + cn.Jk[1] * cn.f[1] + cn.Jk[2] * cn.f[2];
+      }
+    }
+    __syncwarp();
+    double kq_acc[3], kq_frc[3], kq_smooth[3];
 #pragma unroll
     for (int s = 0; s < 3; s++) {
       int k = lane + 32 * s;
-      kq_acc[s] = 0; kq_frc[s] = 0;
+      kq_acc[s] = 0; kq_frc[s] = 0; kq_smooth[s] = 0;
       if (k < NK) {
-        double fc = krow[s].J * krow[s].f;
-        for (int c = 0; c < ncon; c++) {
-          const Contact& cn = sm.u.c.con[c];
-          if (cn.key == k) fc += cn.Jk[0] * cn.f[0] + cn.Jk[1] * cn.f[1] + cn.Jk[2] * cn.f[2];
-        }
-        kq_frc[s] = fc;
-        kq_acc[s] = ks_qacc[s] + sm.vak[k];
+        kq_frc[s] = sm.kfc[k];
+        kq_smooth[s] = sm.kfrc[k];
+        kq_acc[s] = sm.kqs[k] + sm.vak[k];
       }
     }
     if (a.dbg && sub == 0) {
@@ -1003,7 +1130,7 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
 #pragma unroll
       for (int s = 0; s < 3; s++) {
         int k = lane + 32 * s;
-        if (k < NK) { dbg[RP_DBG_QACC_SMOOTH + k] = ks_qacc[s]; dbg[RP_DBG_QACC + k] = kq_acc[s]; dbg[RP_DBG_QFRC_C + k] = kq_frc[s]; dbg[RP_DBG_BIAS + k] = 0; }
+        if (k < NK) { dbg[RP_DBG_QACC_SMOOTH + k] = sm.kqs[k]; dbg[RP_DBG_QACC + k] = kq_acc[s]; dbg[RP_DBG_QFRC_C + k] = kq_frc[s]; dbg[RP_DBG_BIAS + k] = 0; }
       }
 #pragma unroll
       for (int h = 0; h < NH; h++) if (hl) {
@@ -1028,8 +1155,7 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
 #pragma unroll
       for (int h = 0; h < NH; h++) {
         if (hl) {
-          for (int j = 0; j < NL; j++) sm.Minv[h][lane][j] = 0;
-          sm.wbuf[h][lane] = qfrc_smooth[h] + qfrc_c[h];
+          for (int j = 0; j < 32; j++) sm.Minv[h][lane][j] = 0;
         }
       }
       __syncwarp();
@@ -1046,34 +1172,27 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
               sm.Minv[h][j][lane] = v;
             }
           }
+          sm.Minv[h][lane][NL] = qfrc_smooth[h] + qfrc_c[h];  // augmented column: right-hand side
         }
       }
       __syncwarp();
-      // Gauss-Jordan on [A | rhs]; lane NL carries the right-hand side column
-      for (int k = 0; k < NL; k++) {
-#pragma unroll
-        for (int h = 0; h < NH; h++) if (hl) sm.colk[h][lane] = sm.Minv[h][lane][k];
-        __syncwarp();
+      // a = (M + h*D)^-1 rhs : sweep-invert in registers, then one row-times-vector per lane
+      {
+        double col[NH > 0 ? NH : 1][NL];
+        sweep_inverse<NH>(sm, lane, col);
 #pragma unroll
         for (int h = 0; h < NH; h++) {
-          double p = 1.0 / sm.colk[h][k];
-          if (hl && lane > k) {
-            double akj = sm.Minv[h][k][lane] * p;
-            for (int i = 0; i < NL; i++)
-              if (i != k) sm.Minv[h][i][lane] -= sm.colk[h][i] * akj;
-            sm.Minv[h][k][lane] = akj;
-          } else if (lane == NL) {
-            double akj = sm.wbuf[h][k] * p;
-            for (int i = 0; i < NL; i++)
-              if (i != k) sm.wbuf[h][i] -= sm.colk[h][i] * akj;
-            sm.wbuf[h][k] = akj;
-          }
+          double acc = 0;
+#pragma unroll
+          for (int i = 0; i < NL; i++) acc -= col[h][i] * sm.Minv[h][i][NL];  // rhs sits in the padded column NL
+          sm.wbuf[h][lane] = acc;
         }
         __syncwarp();
       }
 #pragma unroll
       for (int h = 0; h < NH; h++) aeul[h] = hl ? sm.wbuf[h][lane] : 0.0;
     }
+    TICK(8)
     // integrate
 #pragma unroll
     for (int h = 0; h < NH; h++) {
@@ -1087,7 +1206,7 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
     for (int s = 0; s < 3; s++) {
       int k = lane + 32 * s;
       if (k < NK) {
-        double ae = (ks_qfrc[s] + kq_frc[s]) / (kM[s] + hstep * dm->key_damping[k]);
+        double ae = (kq_smooth[s] + kq_frc[s]) / (dm->key_M[k] + hstep * dm->key_damping[k]);
         vk[s] += hstep * ae;
         qk[s] += hstep * vk[s];
         wk[s] = kq_acc[s];
@@ -1118,6 +1237,9 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
       }
     }
   }
+#ifdef RP_PROFILE
+  if (a.dbg && lane == 0) for (int i = 0; i < 12; i++) a.dbg[(size_t)env * RP_DBG_STRIDE + RP_DBG_SCALARS + 4 + i] = (double)tacc[i];
+#endif
   if (a.mode == RP_MODE_PHYSICS) return;
 
   // =============================================================================================

@@ -15,6 +15,22 @@
 
 namespace rp {
 
+// 1/x: on the device MUFU.RCP64H seed + two Newton steps (about 1 ulp, no special-case slow path;
+// the callers guard against zero/denormal denominators); plain division on the host.
+RP_HD double rcp(double x) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+
 RP_HD double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 RP_HD void cross3(double* r, const double* a, const double* b) {
   double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
@@ -178,10 +194,11 @@ RP_HD double segment_box_closest_t(const double* a, const double* b, const doubl
   bp[nbp++] = 0; bp[nbp++] = 1;
   double dir[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
   for (int k = 0; k < 3; k++) {
-    if (fabs(dir[k]) < RP_MINVAL) continue;
-    double t1 = (-s[k] - a[k]) / dir[k], t2 = (s[k] - a[k]) / dir[k];
-    if (t1 > 0 && t1 < 1) bp[nbp++] = t1;
-    if (t2 > 0 && t2 < 1) bp[nbp++] = t2;
+    if (fabs(dir[k]) >= RP_MINVAL) {
+      double t1 = (-s[k] - a[k]) / dir[k], t2 = (s[k] - a[k]) / dir[k];
+      if (t1 > 0 && t1 < 1) bp[nbp++] = t1;
+      if (t2 > 0 && t2 < 1) bp[nbp++] = t2;
+    }
   }
   for (int i = 1; i < nbp; i++) {
     double v = bp[i];
@@ -192,7 +209,7 @@ RP_HD double segment_box_closest_t(const double* a, const double* b, const doubl
   double best_t = 0, best_d = 1e300;
   for (int i = 0; i + 1 < nbp; i++) {
     double t0 = bp[i], t1 = bp[i + 1];
-    if (t1 - t0 < 1e-14) continue;
+    if (t1 - t0 >= 1e-14) {
     double tm = 0.5 * (t0 + t1), qa = 0, qb = 0;
     for (int k = 0; k < 3; k++) {
       double pm = a[k] + tm * dir[k];
@@ -206,6 +223,7 @@ RP_HD double segment_box_closest_t(const double* a, const double* b, const doubl
       double p[3] = {a[0] + cand[c] * dir[0], a[1] + cand[c] * dir[1], a[2] + cand[c] * dir[2]};
       double d2 = point_box_d2(p, s);
       if (d2 < best_d - 1e-18) { best_d = d2; best_t = cand[c]; }
+    }
     }
   }
   return best_t;
@@ -229,13 +247,13 @@ RP_HD int qcqp2(double* res, const double* Ain, const double* bin, const double*
   for (int iter = 0; iter < 20; iter++) {
     double det = (A11 + la) * (A22 + la) - A12 * A12;
     if (det < 1e-10) { res[0] = 0; res[1] = 0; return 0; }
-    double detinv = 1 / det, P11 = (A22 + la) * detinv, P22 = (A11 + la) * detinv, P12 = -A12 * detinv;
+    double detinv = rcp(det), P11 = (A22 + la) * detinv, P22 = (A11 + la) * detinv, P12 = -A12 * detinv;
     v1 = -P11 * b1 - P12 * b2;
     v2 = -P12 * b1 - P22 * b2;
     double val = v1 * v1 + v2 * v2 - r * r;
     if (val < 1e-10) break;
     double deriv = -2 * (P11 * v1 * v1 + 2 * P12 * v1 * v2 + P22 * v2 * v2);
-    double delta = -val / deriv;
+    double delta = -val * rcp(deriv);
     if (delta < 1e-10) break;
     la += delta;
   }
@@ -250,7 +268,7 @@ RP_HD double pgs_elliptic_update(const double* A, const double* res, double* f, 
   double old[3] = {f[0], f[1], f[2]};
   double fr[2] = {mu, mu};
   if (f[0] < RP_MINVAL) {
-    f[0] -= res[0] / A[0];
+    f[0] -= res[0] * rcp(A[0]);
     if (f[0] < 0) f[0] = 0;
     f[1] = f[2] = 0;
   } else {
@@ -258,7 +276,7 @@ RP_HD double pgs_elliptic_update(const double* A, const double* res, double* f, 
     for (int r = 0; r < 3; r++) v1[r] = A[3 * r] * old[0] + A[3 * r + 1] * old[1] + A[3 * r + 2] * old[2];
     double denom = dot3(old, v1);
     if (denom >= RP_MINVAL) {
-      double x = -dot3(old, res) / denom;
+      double x = -dot3(old, res) * rcp(denom);
       if (f[0] + x * old[0] < 0) x = -1.0;
       for (int r = 0; r < 3; r++) f[r] += x * old[r];
     }
@@ -273,8 +291,9 @@ RP_HD double pgs_elliptic_update(const double* A, const double* res, double* f, 
     }
     int flg = qcqp2(vv, Ac, bc, fr, f[0]);
     if (flg) {
-      double s = vv[0] * vv[0] / (fr[0] * fr[0]) + vv[1] * vv[1] / (fr[1] * fr[1]);
-      s = sqrt(f[0] * f[0] / fmax(RP_MINVAL, s));
+      double imu2 = rcp(fr[0] * fr[0]);
+      double s = vv[0] * vv[0] * imu2 + vv[1] * vv[1] * imu2;
+      s = sqrt(f[0] * f[0] * rcp(fmax(RP_MINVAL, s)));
       vv[0] *= s; vv[1] *= s;
     }
     f[1] = vv[0]; f[2] = vv[1];
