@@ -1,0 +1,65 @@
+"""RoboPianist suite over the B200 step kernel — mirror of ``robopianist.suite`` (suite/__init__.py).
+
+``load()`` keeps the reference signature (suite/__init__.py:50-59) and adds keyword-only
+``num_envs`` / ``device`` / solver overrides.  ``num_envs=1`` returns a ``dm_env``-shaped
+``PianoEnv``; ``num_envs>1`` returns a ``BatchedPianoEnv`` working on CUDA tensors.
+
+The PIG-dataset names (``REPERTOIRE_150`` / ``ETUDE_12``) need the PIG ``.proto`` files the reference
+downloads separately (cli.py:231-288); they are not distributable, so those lists are empty here and
+only the programmatic debug songs (music/library.py) are registered.  Any ``.mid`` file can be passed
+through ``midi_file``.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Any, Mapping, Optional
+
+from ..music import library
+from .env import BatchedPianoEnv, PianoEnv, StepType, TimeStep  # noqa: F401
+
+REPERTOIRE_150: list = []
+ETUDE_12: list = []
+_DEBUG_BASE_NAME = "RoboPianist-debug-{}-v0"
+DEBUG = [_DEBUG_BASE_NAME.format(name) for name in library.MIDI_NAME_TO_CALLABLE]
+_DEBUG_DICT = dict(zip(DEBUG, library.MIDI_NAME_TO_CALLABLE))
+ALL = REPERTOIRE_150 + ETUDE_12 + DEBUG
+_ALL_DICT = dict(_DEBUG_DICT)
+
+
+def load(
+    environment_name: str,
+    midi_file: Optional[Path] = None,
+    seed: Optional[int] = None,
+    stretch: float = 1.0,
+    shift: int = 0,
+    recompile_physics: bool = False,
+    legacy_step: bool = True,
+    task_kwargs: Optional[Mapping[str, Any]] = None,
+    *,
+    num_envs: int = 1,
+    device: int = 0,
+    iterations: Optional[int] = None,
+    tolerance: Optional[float] = None,
+):
+    """Loads a RoboPianist environment backed by the CUDA rollout.
+
+    ``seed`` is accepted for signature compatibility: the environment itself draws no random numbers
+    (qpos0 start, no augmentations).  ``recompile_physics`` is meaningless here (the scene is
+    flattened once).  ``legacy_step=False`` is rejected: the kernel implements the reference's
+    default legacy ordering (mj_step2 + mj_step1; SURVEY.md §2 table, `Physics.step`).
+    """
+    if not legacy_step:
+        raise NotImplementedError("only legacy_step=True (the reference default) is implemented")
+    del seed, recompile_physics
+    if midi_file is not None:
+        midi = library.load(midi_file, stretch=stretch, shift=shift)
+    else:
+        if environment_name not in ALL:
+            raise ValueError(f"Unknown environment {environment_name}. Available environments: {ALL}")
+        midi = library.load(_ALL_DICT[environment_name], stretch=stretch, shift=shift)
+    batched = BatchedPianoEnv(midi, num_envs=num_envs, device=device, iterations=iterations,
+                              tolerance=tolerance, **dict(task_kwargs or {}))
+    return PianoEnv(batched) if num_envs == 1 else batched
+
+
+__all__ = ["ALL", "DEBUG", "ETUDE_12", "REPERTOIRE_150", "load", "BatchedPianoEnv", "PianoEnv", "StepType", "TimeStep"]

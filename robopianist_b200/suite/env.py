@@ -1,0 +1,312 @@
+"""Environment surface over the CUDA step kernel.
+
+Mirrors, for the one path this repository replaces, what the reference hands back from
+``robopianist.suite.load`` (suite/__init__.py:50-93): a ``dm_env.Environment``-shaped object whose
+``reset()`` / ``step(action)`` return ``TimeStep(step_type, reward, discount, observation)``
+(composer.Environment semantics), plus the batched form a learner on the same
+GPU wants: ``BatchedPianoEnv.step(actions[N, 45]) -> (obs[N, 329], reward[N], discount[N],
+step_type[N])`` as CUDA tensors, one kernel launch per control step.
+
+``dm_env`` is not installable here, so ``TimeStep`` / ``StepType`` / ``BoundedArray`` are restated
+with the same field names and meaning.  There is no CPU path: constructing an environment without
+the native library or without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import collections
+import enum
+from typing import Any, Mapping, NamedTuple, Optional
+
+import numpy as np
+
+from .. import native
+from ..music import trajectory
+from ..scene import cache
+
+_TASK_KWARGS = dict(
+    n_steps_lookahead=1, n_seconds_lookahead=None, trim_silence=False, wrong_press_termination=False,
+    initial_buffer_time=0.0, disable_fingering_reward=False, disable_forearm_reward=False,
+    disable_colorization=False, disable_hand_collisions=False, augmentations=None,
+    energy_penalty_coef=5e-3, randomize_hand_positions=False,
+    # PianoTask kwargs (tasks/base.py:96-107)
+    gravity_compensation=False, change_color_on_activation=False, primitive_fingertip_collisions=False,
+    reduced_action_space=False, attachment_yaw=0.0, forearm_dofs=("forearm_tx", "forearm_ty"),
+    physics_timestep=0.005, control_timestep=0.05,
+)
+
+
+class StepType(enum.IntEnum):
+    FIRST = 0
+    MID = 1
+    LAST = 2
+
+
+class TimeStep(NamedTuple):
+    step_type: Any
+    reward: Any
+    discount: Any
+    observation: Any
+
+    def first(self) -> bool:
+        return self.step_type == StepType.FIRST
+
+    def mid(self) -> bool:
+        return self.step_type == StepType.MID
+
+    def last(self) -> bool:
+        return self.step_type == StepType.LAST
+
+
+class Array:
+    def __init__(self, shape, dtype, name=None):
+        self.shape, self.dtype, self.name = tuple(shape), np.dtype(dtype), name
+
+    def validate(self, value):
+        value = np.asarray(value)
+        if value.shape != self.shape:
+            raise ValueError(f"Expected shape {self.shape} but found {value.shape}")
+        return value
+
+    def __repr__(self):
+        return f"Array(shape={self.shape}, dtype={self.dtype}, name={self.name!r})"
+
+
+class BoundedArray(Array):
+    def __init__(self, shape, dtype, minimum, maximum, name=None):
+        super().__init__(shape, dtype, name)
+        self.minimum = np.asarray(minimum, dtype=dtype)
+        self.maximum = np.asarray(maximum, dtype=dtype)
+
+
+def _unsupported(kw: Mapping[str, Any]):
+    """Reference kwargs this path does not implement must fail loudly, not be ignored."""
+    if kw["augmentations"]:
+        raise NotImplementedError("augmentations (variations.py) are host-side per-reset MIDI edits: out of scope")
+    if kw["randomize_hand_positions"]:
+        raise NotImplementedError("randomize_hand_positions is not implemented")
+    if kw["reduced_action_space"]:
+        raise NotImplementedError("reduced_action_space is not implemented")
+    if kw["attachment_yaw"] != 0.0:
+        raise NotImplementedError("attachment_yaw != 0 is not implemented")
+    if not kw["primitive_fingertip_collisions"]:
+        raise NotImplementedError(
+            "mesh fingertip colliders need a convex-mesh narrowphase (SURVEY.md §8(f) row 1); pass "
+            "task_kwargs=dict(primitive_fingertip_collisions=True) — the north_star configuration")
+    if not kw["disable_hand_collisions"]:
+        raise NotImplementedError(
+            "hand-hand contacts are not implemented (SURVEY.md §8(f) row 1); pass "
+            "task_kwargs=dict(disable_hand_collisions=True)")
+
+
+class BatchedPianoEnv:
+    """N independent PianoWithShadowHands (or SelfActuatedPiano) environments on one GPU.
+
+    All tensors are float64 CUDA tensors owned by this object and overwritten by the next call.
+    Episodes auto-reset with dm_env semantics: the step after LAST returns FIRST (reward 0,
+    discount 1) and ignores its action.
+    """
+
+    def __init__(self, midi, num_envs: int = 1, device: int = 0, task: str = "piano_with_shadow_hands",
+                 iterations: Optional[int] = None, tolerance: Optional[float] = None,
+                 reward_type: int = 0, **task_kwargs):
+        import torch
+
+        unknown = set(task_kwargs) - set(_TASK_KWARGS)
+        if unknown:
+            raise TypeError(f"unexpected task kwargs {sorted(unknown)}")
+        kw = dict(_TASK_KWARGS, **task_kwargs)
+        hands = task == "piano_with_shadow_hands"
+        if hands:
+            _unsupported(kw)
+        if not torch.cuda.is_available():
+            raise native.NativeError("BatchedPianoEnv needs a CUDA device (there is no CPU path)")
+        self.torch = torch
+        self.task_name = task
+        self.control_timestep = float(kw["control_timestep"])
+        if kw["trim_silence"]:
+            midi = midi.trim_silence()
+        self.midi = midi
+        L = int(kw["n_steps_lookahead"])
+        if kw["n_seconds_lookahead"] is not None:  # piano_with_shadow_hands.py:103-106
+            L = int(np.ceil(kw["n_seconds_lookahead"] / self.control_timestep))
+        traj = trajectory.NoteTrajectory.from_seq(midi, self.control_timestep)
+        if kw["initial_buffer_time"]:
+            traj = traj.add_initial_buffer_time(kw["initial_buffer_time"])
+        self.trajectory = traj
+        self._notes, self._sustains = traj.notes, traj.sustains
+        goal, fing = traj.goal_table(), traj.fingering_table()
+        self.goal_table, self.fingering_table = goal, fing
+        self.n_steps_lookahead = L
+        has_fingering = bool((fing >= 0).any())
+        self.disable_fingering_reward = bool(kw["disable_fingering_reward"]) or not has_fingering
+        if hands and not kw["disable_fingering_reward"] and not has_fingering:
+            raise NotImplementedError(
+                "songs without fingering use the optimal-transport fingering reward "
+                "(piano_with_shadow_hands.py:333-369): not implemented; pass disable_fingering_reward=True")
+        self.disable_forearm_reward = bool(kw["disable_forearm_reward"])
+        self.flat = cache.load_scene(task, gravity_compensation=bool(kw["gravity_compensation"]),
+                                     physics_timestep=float(kw["physics_timestep"]),
+                                     control_timestep=self.control_timestep,
+                                     forearm_dofs=tuple(kw["forearm_dofs"]))
+        self.model = native.Model(
+            self.flat, goal, fing, kind=0 if hands else 1, iterations=iterations, tolerance=tolerance,
+            n_steps_lookahead=L, wrong_press_termination=bool(kw["wrong_press_termination"]),
+            disable_fingering_reward=self.disable_fingering_reward,
+            disable_forearm_reward=bool(kw["disable_forearm_reward"]),
+            energy_penalty_coef=float(kw["energy_penalty_coef"]), reward_type=reward_type)
+        self.num_envs, self.device = int(num_envs), torch.device("cuda", device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self.batch = native.Batch(self.model, self.num_envs, device=device, stream=stream)
+        N, dev = self.num_envs, self.device
+        self.obs = torch.empty((N, self.model.obs_dim), dtype=torch.float64, device=dev)
+        self.reward = torch.empty(N, dtype=torch.float64, device=dev)
+        self.discount = torch.empty(N, dtype=torch.float64, device=dev)
+        self.step_type = torch.empty(N, dtype=torch.uint8, device=dev)
+        self.reward_terms = torch.empty((N, 5), dtype=torch.float64, device=dev)
+        self._hands = hands
+        self.obs_slices = self._obs_layout()
+
+    # ------------------------------------------------------------------ specs
+    def _obs_layout(self):
+        L, nl = self.n_steps_lookahead, 26
+        out, off = collections.OrderedDict(), 0
+
+        def add(name, n):
+            nonlocal off
+            out[name] = slice(off, off + n)
+            off += n
+
+        if self._hands:
+            add("piano/state", 88); add("piano/sustain_state", 1)
+            add("rh_shadow_hand/joints_pos", nl); add("lh_shadow_hand/joints_pos", nl)
+            add("goal", (L + 1) * 89)
+            if not self.disable_fingering_reward:
+                add("fingering", 10)
+        else:
+            add("piano/activation", 88); add("piano/sustain_activation", 1)
+            add("goal", (L + 1) * 89)
+        assert off == self.model.obs_dim, (off, self.model.obs_dim)
+        return out
+
+    def action_spec(self) -> BoundedArray:
+        cr = self.flat.actuator_ctrlrange
+        lo, hi = np.append(cr[:, 0], 0.0), np.append(cr[:, 1], 1.0)
+        names = "\t".join(list(self.flat.meta["actuator_names"]) + ["sustain"])
+        return BoundedArray((self.model.act_dim,), np.float64, lo, hi, name=names)
+
+    def observation_spec(self):
+        return collections.OrderedDict((k, Array((s.stop - s.start,), np.float64, k)) for k, s in self.obs_slices.items())
+
+    # ------------------------------------------------------------------ stepping
+    def reset(self, mask=None):
+        """FIRST observation for all envs (mask: uint8 CUDA tensor selecting the envs to reset)."""
+        self.batch.reset(None if mask is None else mask.data_ptr(), self.obs.data_ptr())
+        if mask is None:
+            self.reward.zero_(); self.discount.fill_(1.0); self.step_type.fill_(int(StepType.FIRST))
+        return self.obs, self.reward, self.discount, self.step_type
+
+    def step(self, actions):
+        """actions: float64 CUDA tensor [N, act_dim] (contiguous). One launch; asynchronous."""
+        t = self.torch
+        if not (isinstance(actions, t.Tensor) and actions.is_cuda and actions.dtype == t.float64
+                and actions.is_contiguous() and tuple(actions.shape) == (self.num_envs, self.model.act_dim)):
+            raise ValueError(f"actions must be a contiguous float64 CUDA tensor of shape {(self.num_envs, self.model.act_dim)}")
+        self.batch.step(actions.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(), self.discount.data_ptr(),
+                        self.step_type.data_ptr(), self.reward_terms.data_ptr())
+        return self.obs, self.reward, self.discount, self.step_type
+
+    def step_host(self, actions: np.ndarray):
+        """Host buffers in and out (pinned staging + copies inside the library): the e2e call."""
+        return self.batch.step_host(actions)
+
+    def get_state(self):
+        return self.batch.get_state()
+
+    def set_state(self, *a, **k):
+        return self.batch.set_state(*a, **k)
+
+    def close(self):
+        self.batch.close()
+
+
+class _Piano:
+    """`env.task.piano` attributes read by the reference's wrappers (wrappers/evaluation.py:70-73)."""
+
+    def __init__(self, env):
+        self._env = env
+
+    @property
+    def activation(self):
+        return self._env._batched.batch.get_aux()["activation"][0].astype(bool)
+
+    @property
+    def sustain_activation(self):
+        return np.array([self._env._sustain >= 0.5])
+
+
+class _RewardFn:
+    def __init__(self):
+        self.reward_terms = {}
+
+
+class _Task:
+    """`env.task` facade: `_notes`, `_sustains`, `piano`, `reward_fn.reward_terms`, `control_timestep`."""
+
+    def __init__(self, env):
+        b = env._batched
+        self._notes, self._sustains = b._notes, b._sustains
+        self.piano = _Piano(env)
+        self.reward_fn = _RewardFn()
+        self.control_timestep = b.control_timestep
+        self.midi = b.midi
+
+
+_TERM_NAMES = ("key_press_reward", "sustain_reward", "energy_reward", "fingering_reward", "forearm_reward")
+
+
+class PianoEnv:
+    """One environment with the ``dm_env.Environment`` call surface (reset / step / specs)."""
+
+    def __init__(self, batched: BatchedPianoEnv):
+        assert batched.num_envs == 1
+        self._batched = batched
+        self._sustain = 0.0
+        self.task = _Task(self)
+        self._reset_next = True
+
+    def action_spec(self):
+        return self._batched.action_spec()
+
+    def observation_spec(self):
+        return self._batched.observation_spec()
+
+    def _obs_dict(self, obs_row):
+        return collections.OrderedDict((k, obs_row[s].copy()) for k, s in self._batched.obs_slices.items())
+
+    def reset(self) -> TimeStep:
+        b = self._batched
+        b.reset()
+        b.torch.cuda.synchronize(b.device)
+        self._reset_next = False
+        self._sustain = 0.0
+        return TimeStep(StepType.FIRST, None, None, self._obs_dict(b.obs[0].cpu().numpy()))
+
+    def step(self, action) -> TimeStep:
+        if self._reset_next:
+            return self.reset()
+        b = self._batched
+        action = self.action_spec().validate(np.asarray(action, np.float64))
+        obs, rew, dis, st, terms = b.step_host(action[None])
+        self._sustain = float(action[-1])
+        names = _TERM_NAMES if b._hands else ("key_press_reward",)
+        enabled = [n for n in names if not (n == "fingering_reward" and b.disable_fingering_reward)
+                   and not (n == "forearm_reward" and b.disable_forearm_reward)]
+        self.task.reward_fn.reward_terms = {n: float(terms[0][names.index(n)]) for n in enabled}
+        step_type = StepType(int(st[0]))
+        if step_type == StepType.LAST:
+            self._reset_next = True
+        return TimeStep(step_type, float(rew[0]), float(dis[0]), self._obs_dict(obs[0]))
+
+    def close(self):
+        self._batched.close()

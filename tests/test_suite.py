@@ -1,0 +1,161 @@
+"""Suite surface: mirrors the reference's structural tests
+(robopianist/suite/suite_test.py:27-56, suite/tasks/piano_with_shadow_hands_test.py:74-272) against
+the CUDA-backed environment.  CPU part: registry, kwargs and loud failures; GPU part: the dm_env
+behaviour itself."""
+import numpy as np
+import pytest
+
+from robopianist_b200 import suite
+from robopianist_b200.music import trajectory
+from robopianist_b200.music.sequence import NoteSeq
+
+KW = dict(primitive_fingertip_collisions=True, disable_hand_collisions=True)
+
+
+def _test_midi(dt=0.01):
+    """C6 for 2 dt (right index), then G5 for 1 dt (left thumb) — piano_with_shadow_hands_test.py:28-50."""
+    seq = NoteSeq()
+    seq.add(84, 0.0, 2 * dt, 80, 1)
+    seq.add(79, 2 * dt, 3 * dt, 80, 5)
+    seq.total_time = 3 * dt
+    return seq
+
+
+def _env(control_timestep=0.01, **kw):
+    from robopianist_b200.suite.env import BatchedPianoEnv, PianoEnv
+    kw = dict(KW, control_timestep=control_timestep, n_steps_lookahead=0, **kw)
+    return PianoEnv(BatchedPianoEnv(_test_midi(control_timestep), num_envs=1, **kw))
+
+
+# ------------------------------------------------------------------------------------ CPU
+def test_registry_and_unknown_name():
+    assert "RoboPianist-debug-TwinkleTwinkleRousseau-v0" in suite.DEBUG and set(suite.DEBUG) <= set(suite.ALL)
+    with pytest.raises(ValueError):
+        suite.load("RoboPianist-debug-NoSuchSong-v0")
+
+
+def test_unsupported_kwargs_fail_loudly():
+    name = suite.DEBUG[0]
+    with pytest.raises(NotImplementedError):
+        suite.load(name)  # reference default = mesh fingertips: not implemented, must not be silently replaced
+    with pytest.raises(NotImplementedError):
+        suite.load(name, task_kwargs=dict(primitive_fingertip_collisions=True))  # hand-hand contacts
+    with pytest.raises(TypeError):
+        suite.load(name, task_kwargs=dict(KW, no_such_kwarg=1))
+    with pytest.raises(NotImplementedError):
+        suite.load(name, legacy_step=False, task_kwargs=KW)
+
+
+# ------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_all_debug_envs_load_and_step():
+    """suite_test.py:27-56: every debug env loads, FIRST has no reward/discount, obs matches the spec."""
+    rng = np.random.default_rng(12345)
+    for name in suite.DEBUG:
+        midi_has_fingering = name not in ()
+        env = suite.load(name, seed=12345, task_kwargs=dict(KW))
+        spec = env.action_spec()
+        assert spec.shape == (45,) and np.isfinite(spec.minimum).all() and np.isfinite(spec.maximum).all()
+        ts = env.reset()
+        assert ts.first() and ts.reward is None and ts.discount is None
+        ospec = env.observation_spec()
+        for _ in range(10):
+            ts = env.step(rng.uniform(spec.minimum, spec.maximum))
+            assert list(ts.observation) == list(ospec)
+            for k, v in ts.observation.items():
+                assert v.shape == ospec[k].shape and np.isfinite(v).all()
+            assert np.isfinite(ts.reward)
+        env.close()
+
+
+@pytest.mark.gpu
+def test_observables_and_action_layout():
+    env = _env()
+    keys = list(env.observation_spec())
+    assert keys == ["piano/state", "piano/sustain_state", "rh_shadow_hand/joints_pos", "lh_shadow_hand/joints_pos",
+                    "goal", "fingering"]
+    names = env.action_spec().name.split("\t")
+    assert len(names) == 45 and names[-1] == "sustain"
+    assert all(n.startswith("rh_shadow_hand/") for n in names[:22]) and all(n.startswith("lh_shadow_hand/") for n in names[22:44])
+    env.close()
+
+
+@pytest.mark.gpu
+def test_termination_and_discount():
+    env = _env()
+    zero = np.zeros(45)
+    env.reset()
+    for _ in range(3):
+        ts = env.step(zero)
+        assert ts.mid() and ts.discount == 1.0
+    ts = env.step(zero)
+    assert ts.last() and ts.discount == 1.0
+    assert env.step(zero).first()  # dm_env: the step after LAST resets
+    env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ct,secs", [(0.01, 0), (0.01, 0.1), (0.05, 0.01), (0.05, 1)])
+def test_n_seconds_lookahead(ct, secs):
+    env = _env(control_timestep=ct, n_seconds_lookahead=secs)
+    assert env._batched.n_steps_lookahead == int(np.ceil(secs / ct))
+    env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L", [0, 1, 2, 5])
+def test_goal_and_fingering_observables(L):
+    from robopianist_b200.suite.env import BatchedPianoEnv, PianoEnv
+    env = PianoEnv(BatchedPianoEnv(_test_midi(), num_envs=1, control_timestep=0.01, n_steps_lookahead=L, **KW))
+    traj = trajectory.NoteTrajectory.from_seq(_test_midi(), 0.01)
+    notes, sustains = traj.notes, traj.sustains
+    assert len(notes) == 4
+    ts = env.reset()
+    for i in range(len(notes)):
+        expected = np.zeros((L + 1, 89))
+        for j, t in enumerate(range(i, min(i + L + 1, len(notes)))):
+            expected[j, [n.key for n in notes[t]]] = 1.0
+            expected[j, -1] = sustains[t]
+        np.testing.assert_array_equal(ts.observation["goal"], expected.ravel())
+        fing = np.zeros((2, 5))
+        idx = [n.fingering for n in notes[i]]
+        fing[0, [f for f in idx if f < 5]] = 1.0
+        fing[1, [f - 5 for f in idx if f >= 5]] = 1.0
+        np.testing.assert_array_equal(ts.observation["fingering"], fing.ravel())
+        ts = env.step(np.zeros(45))
+    env.close()
+
+
+@pytest.mark.gpu
+def test_failure_termination():
+    """piano_with_shadow_hands_test.py:228-242 pushes every key down with qfrc_applied; the C-ABI has no
+    applied-force input, so the same end state (all keys at their upper limit) is set directly."""
+    env = _env(wrong_press_termination=True)
+    env.reset()
+    b = env._batched
+    q, v, w, _ = b.get_state()
+    q[0, :88] = b.flat.key_qmax
+    b.set_state(q, v, w)
+    ts = env.step(np.zeros(45))
+    assert ts.last() and ts.discount == 0.0
+    env.close()
+
+
+@pytest.mark.gpu
+def test_reward_terms_and_batched_surface():
+    import torch
+    env = suite.load("RoboPianist-debug-CMajorScaleTwoHands-v0", task_kwargs=dict(KW), num_envs=8)
+    obs, rew, dis, st = env.reset()
+    assert obs.shape == (8, 329) and obs.is_cuda and (st == 0).all()
+    a = torch.zeros((8, 45), dtype=torch.float64, device="cuda")
+    obs, rew, dis, st = env.step(a)
+    torch.cuda.synchronize()
+    assert (st == 1).all() and torch.allclose(env.reward_terms.sum(dim=1), rew)
+    with pytest.raises(ValueError):
+        env.step(a.float())
+    env.close()
+    one = suite.load("RoboPianist-debug-CMajorScaleTwoHands-v0", task_kwargs=dict(KW, disable_fingering_reward=True))
+    one.reset(); one.step(np.zeros(45))
+    assert "fingering_reward" not in one.task.reward_fn.reward_terms and "key_press_reward" in one.task.reward_fn.reward_terms
+    assert "fingering" not in one.observation_spec()
+    one.close()
