@@ -40,13 +40,15 @@ struct RawContact {  // narrowphase output before sorting
   unsigned sortkey, pad;
 };
 
+#define RS 27  // row stride of the hand matrices (odd: lane-per-row accesses are bank-conflict free)
 struct Smem {
-  double Minv[RP_NHMAX][NL][32];  // rows padded to 32 columns (zeros) so every lane can read its column
+  double A[RP_NHMAX][NL * RS];  // per hand: M, then -M^-1 (sweep), later -(M + h*D)^-1; symmetric, row-major
   double S[RP_NHMAX][NL][6];
   double qk[NK], vk[NK], vak[NK];
   double wbuf[RP_NHMAX][32];
-  double colk[RP_NHMAX][32];
-  double colk2[RP_NHMAX][32];
+  double Mrow[RP_NHMAX][NL][MAXD];   // mass-matrix entries M[link][ancestor at depth d] (kept for the Euler solve)
+  signed char anc[RP_NHMAX][NL][MAXD];  // ancestor-or-self at depth d (copy of the model table, for the sweep)
+  signed char dep[RP_NHMAX][32], sub[RP_NHMAX][32];  // link depth / subtree size
   double actf[RP_NHMAX][RP_NAH];
   double vh[RP_NHMAX][NL];  // hand joint velocities (for chain walks)
   double kfrc[NK], kqs[NK], kfc[NK];  // per key: qfrc_smooth, qacc_smooth, constraint force J^T f
@@ -94,38 +96,78 @@ struct KeyRow {       // active limit row of a key (at most one side can be acti
 
 }  // namespace
 
-// In-place inverse of the NH symmetric positive definite 26x26 matrices held in sm.Minv (rows padded
-// to 32): symmetric sweep operator, each lane keeps its own column in registers, column k is
-// exchanged through shared memory once per step (double buffered, one __syncwarp per step).
-// After 26 sweeps the registers hold -A^-1.  Branch-free; padded lanes mirror column 0.
+// In-place symmetric sweep of the NH hand matrices in sm.A: afterwards A = -M^-1 (callers fold the
+// sign into their multiply-adds).  Lane j owns row j (== column j; the sweep keeps the matrix
+// symmetric).  Pivots run leaves first (k = NL-1 .. 0): at that point row k is non-zero only at the
+// ancestors of k and inside its subtree, so a pivot touches depth_k + subtree_k rows instead of 26
+// (290 row updates per hand instead of 676), and the loops stay rolled: the code is a few hundred
+// bytes, not the 230 KB of a register-resident unrolled elimination (instruction-cache bound).
 template <int NH>
-__device__ __forceinline__ void sweep_inverse(Smem& sm, int lane, double (&col)[NH > 0 ? NH : 1][NL]) {
-  const int lc = lane < NL ? lane : 0;
-#pragma unroll
+__device__ __noinline__ void sweep_inverse(Smem& sm, int lane) {
+#pragma unroll 1
   for (int h = 0; h < NH; h++) {
-#pragma unroll
-    for (int i = 0; i < NL; i++) col[h][i] = sm.Minv[h][i][lc];
-  }
-  __syncwarp();
-#pragma unroll
-  for (int k = 0; k < NL; k++) {
-    double (*buf)[32] = (k & 1) ? sm.colk2 : sm.colk;
-#pragma unroll
-    for (int h = 0; h < NH; h++) buf[h][lane] = col[h][k];  // A[lane][k] == A[k][lane]
-    __syncwarp();
-    const bool isk = lc == k;
-#pragma unroll
-    for (int h = 0; h < NH; h++) {
-      const double dinv = 1.0 / buf[h][k];
-      const double t = buf[h][lc] * dinv;  // A[k][j] / d
-#pragma unroll
-      for (int i = 0; i < NL; i++) {
-        const double ci = buf[h][i];
-        const double upd = isk ? ci * dinv : col[h][i] - ci * t;
-        col[h][i] = (i == k) ? (isk ? -dinv : t) : upd;
+    double* A = sm.A[h];
+    double* myrow = A + (lane < NL ? lane : 0) * RS;
+#pragma unroll 1
+    for (int k = NL - 1; k >= 0; k--) {
+      const double* rowk = A + k * RS;
+      const double dinv = 1.0 / rowk[k];
+      const bool upd = lane < NL && lane != k;  // lane k's own row is rewritten after the updates
+      const double t = upd ? rowk[lane] * dinv : 0.0;
+      const int depk = sm.dep[h][k], endk = k + sm.sub[h][k];
+      if (upd) {
+        for (int d = 0; d < depk; d++) {
+          const int i = sm.anc[h][k][d];
+          myrow[i] -= rowk[i] * t;
+        }
+#pragma unroll 2
+        for (int i = k + 1; i < endk; i++) myrow[i] -= rowk[i] * t;
       }
+      __syncwarp();
+      if (upd) { myrow[k] = t; A[k * RS + lane] = t; }
+      if (lane == k) A[k * RS + k] = -dinv;
+      __syncwarp();
     }
   }
+}
+
+// lane == dof values of hand 0 / hand 1 -> half-warp mapping (both shuffles run on the full warp)
+__device__ __forceinline__ double to_new(double x0, double x1, int src, int hh) {
+  const double v0 = __shfl_sync(FULL, x0, src), v1 = __shfl_sync(FULL, x1, src);
+  return hh ? v1 : v0;
+}
+
+// Scalar constraint rows of the two hands in the half-warp mapping (see the PGS section).
+struct HandRows { double f[2], b[2], R[2], AR[2], ARi[2], J[2], lo[2], hi[2]; };
+
+// One Gauss-Seidel pass over the scalar rows `anyrow` (bit i: dof i has a row in either hand).
+// Ah: this lane's hand matrix (A = -M^-1), l0/l1: the dofs owned by the lane.  Returns the lane's
+// share of the cost improvement.  Every lane evaluates the candidate update of its own row; only
+// the owner of row i commits at step i and broadcasts J*delta inside its half-warp.
+__device__ __forceinline__ double gs_rows(const double* __restrict__ Ah, int lane, int l0, int l1, unsigned anyrow,
+                                          HandRows& r, double (&va)[2]) {
+  double impr = 0;
+  const int hb = lane & 16;
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const double base = r.b[s] + r.R[s] * r.f[s];  // f only changes at the lane's own commit
+    const int i0 = 16 * s, i1 = s ? NL : 16, own = s ? l1 : l0;
+#pragma unroll 1
+    for (int i = i0; i < i1; i++) {
+      if (!(anyrow >> i & 1)) continue;
+      const double m0 = Ah[i * RS + l0], m1 = Ah[i * RS + l1];
+      const double res = base + r.J[s] * va[s];
+      const double x = r.f[s] - res * r.ARi[s];
+      double fx = x < r.lo[s] ? r.lo[s] : x;
+      fx = x > r.hi[s] ? r.hi[s] : fx;
+      const double dl = fx - r.f[s];
+      const double dbc = __shfl_sync(FULL, r.J[s] * dl, hb | (i & 15));
+      va[0] -= m0 * dbc;
+      va[1] -= m1 * dbc;
+      if (own == i) { impr -= dl * (0.5 * dl * r.AR[s] + res); r.f[s] = fx; }
+    }
+  }
+  return impr;
 }
 
 // The kernel proper is large; it is written as one function so that lane-owned state stays in
@@ -215,6 +257,18 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
   double key_actforce[3] = {0, 0, 0};
   int niter_last = 0, ncon_last = 0, flags = 0;
 
+  // topology tables into shared memory (read in the inner loops of the sweep / contact rows)
+  if (NH > 0) {
+#pragma unroll
+    for (int h = 0; h < NH; h++) {
+      if (hl) {
+        for (int d = 0; d < MAXD; d++) sm.anc[h][lane][d] = (signed char)dm->link_anc[h][lane][d];
+      }
+      sm.dep[h][lane] = (signed char)ldep[h];
+      sm.sub[h][lane] = (signed char)lsub[h];
+    }
+    __syncwarp();
+  }
   // link world poses (kept for the task epilogue)
   double xp[NH > 0 ? NH : 1][3], xq[NH > 0 ? NH : 1][4];
 #ifdef RP_PROFILE
@@ -303,14 +357,14 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
     __syncwarp();
 
     // --------------------------------------------------- RNE forward (chain walk), inertia, F
-    double qfrc_bias[NH > 0 ? NH : 1], Mrow[NH > 0 ? NH : 1][MAXD];
+    double qfrc_bias[NH > 0 ? NH : 1];
 #pragma unroll
     for (int h = 0; h < NH; h++) {
       qfrc_bias[h] = 0;
       if (hl) {
         double V[6] = {0, 0, 0, 0, 0, 0}, A[6] = {0, 0, 0, 0, 0, 0};
         for (int d = 0; d <= ldep[h]; d++) {
-          int j = dm->link_anc[h][lane][d];
+          int j = sm.anc[h][lane][d];
           double Sj[6], Sd[6];
           for (int k = 0; k < 6; k++) Sj[k] = sm.S[h][j][k];
           double qd = sm.vh[h][j];
@@ -367,55 +421,44 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
         for (int k = 0; k < 10; k++) Ic[k] = sm.u.acc[h][lane][6 + k];
         qfrc_bias[h] = rp::dot6(Sown[h], F);
         rp::inertia_mul(fI, Ic, Sown[h]);
-#pragma unroll
-        for (int d = 0; d < MAXD; d++) {
-          Mrow[h][d] = 0;
-          if (d <= ldep[h]) {
-            int j = dm->link_anc[h][lane][d];
-            double Sj[6];
-            for (int k = 0; k < 6; k++) Sj[k] = sm.S[h][j][k];
-            Mrow[h][d] = rp::dot6(Sj, fI);
-            if (d == ldep[h]) Mrow[h][d] += dm->link_armature[h][lane];
-          }
+        for (int d = 0; d <= ldep[h]; d++) {
+          const int j = sm.anc[h][lane][d];
+          double Sj[6];
+          for (int k = 0; k < 6; k++) Sj[k] = sm.S[h][j][k];
+          double m = rp::dot6(Sj, fI);
+          if (d == ldep[h]) m += dm->link_armature[h][lane];
+          sm.Mrow[h][lane][d] = m;
         }
-        for (int j = 0; j < 32; j++) sm.Minv[h][lane][j] = 0;
       }
+    }
+    // scatter M into the dense symmetric work matrix
+    if (NH > 0) {
+      double* Aflat = &sm.A[0][0];
+      for (int idx = lane; idx < NH * NL * RS; idx += 32) Aflat[idx] = 0;
     }
     __syncwarp();
 #pragma unroll
     for (int h = 0; h < NH; h++) {
       if (hl) {
-#pragma unroll
-        for (int d = 0; d < MAXD; d++) {
-          if (d <= ldep[h]) {
-            int j = dm->link_anc[h][lane][d];
-            sm.Minv[h][lane][j] = Mrow[h][d];
-            sm.Minv[h][j][lane] = Mrow[h][d];
-          }
+        for (int d = 0; d <= ldep[h]; d++) {
+          const int j = sm.anc[h][lane][d];
+          const double m = sm.Mrow[h][lane][d];
+          sm.A[h][lane * RS + j] = m;
+          sm.A[h][j * RS + lane] = m;
         }
       }
     }
     __syncwarp();
     if (a.dbg && sub == 0 && NH > 0) {
       double* dbg = a.dbg + (size_t)env * RP_DBG_STRIDE;
-      for (int i = 0; i < NL; i++) if (hl) dbg[RP_DBG_M + i * NL + lane] = sm.Minv[0][i][lane];
+      for (int i = 0; i < NL; i++) if (hl) dbg[RP_DBG_M + i * NL + lane] = sm.A[0][i * RS + lane];
     }
     TICK(1)
-    // ---------------------------------------------------------------- invert M (symmetric sweep)
-    if (NH > 0) {
-      double col[NH > 0 ? NH : 1][NL];
-      sweep_inverse<NH>(sm, lane, col);
-      __syncwarp();
-#pragma unroll
-      for (int h = 0; h < NH; h++) {
-#pragma unroll
-        for (int i = 0; i < NL; i++) sm.Minv[h][i][lane] = hl ? -col[h][i] : 0.0;
-      }
-      __syncwarp();
-    }
+    // ---------------------------------------------------------------- invert M (symmetric sweep): A = -M^-1
+    if (NH > 0) sweep_inverse<NH>(sm, lane);
     if (a.dbg && sub == 0 && NH > 0) {
       double* dbg = a.dbg + (size_t)env * RP_DBG_STRIDE;
-      for (int i = 0; i < NL; i++) if (hl) dbg[RP_DBG_MINV + i * NL + lane] = sm.Minv[0][i][lane];
+      for (int i = 0; i < NL; i++) if (hl) dbg[RP_DBG_MINV + i * NL + lane] = -sm.A[0][i * RS + lane];
     }
 
     TICK(2)
@@ -456,7 +499,7 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
 #pragma unroll
     for (int h = 0; h < NH; h++) {
       double s = 0;
-      if (hl) for (int k = 0; k < NL; k++) s += sm.Minv[h][k][lane] * sm.wbuf[h][k];
+      if (hl) for (int k = 0; k < NL; k++) s -= sm.A[h][k * RS + lane] * sm.wbuf[h][k];
       qacc_smooth[h] = s;
     }
     __syncwarp();
@@ -519,7 +562,7 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
       lm_J[h] = 0; lm_R[h] = 1; lm_b[h] = 0; lm_AR[h] = 1; lm_f[h] = 0; lm_aref[h] = 0;
       bool fr_on = false, lm_on = false;
       if (hl) {
-        double mii = sm.Minv[h][lane][lane];
+        double mii = -sm.A[h][lane * RS + lane];
         fr_loss[h] = dm->link_frictionloss[h][lane];
         fr_on = fr_loss[h] > 0;
         if (fr_on) {
@@ -711,15 +754,15 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
       double margin = fmax(g1.margin, g2.margin), gap = fmax(g1.gap, g2.gap), incl = margin - gap;
       cn.mu = mu;
       // Jacobian: rows = frame directions, body2 (key) minus body1 (hand link)
-      int dep = dm->link_depth[h][link];
+      int dep = sm.dep[h][link];
       cn.dep = dep;
-      for (int d = 0; d < 16; d++) cn.chain[d] = (signed char)(d <= dep ? dm->link_anc[h][link][d] : 0);
+      for (int d = 0; d < 16; d++) cn.chain[d] = (signed char)(d <= dep ? sm.anc[h][link][d] : 0);
       for (int r = 0; r < 3; r++) {
         const double* dir = c_frame + 3 * r;
         for (int d = 0; d < MAXD; d++) {
           double v = 0;
           if (d <= dep) {
-            int j = dm->link_anc[h][link][d];
+            int j = sm.anc[h][link][d];
             const double* S = sm.S[h][j];
             double wxp[3];
             rp::cross3(wxp, S, c_pos);
@@ -753,7 +796,7 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
       double vel[3], jqs[3];
       for (int r = 0; r < 3; r++) {
         double sv = 0;
-        for (int d = 0; d <= dep; d++) sv += cn.Jc[r][d] * sm.vh[h][dm->link_anc[h][link][d]];
+        for (int d = 0; d <= dep; d++) sv += cn.Jc[r][d] * sm.vh[h][sm.anc[h][link][d]];
         if (c_key >= 0) sv += cn.Jk[r] * sm.vk[c_key];
         vel[r] = sv;
       }
@@ -765,9 +808,9 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
       double u[3][MAXD];
       for (int r = 0; r < 3; r++)
         for (int d = 0; d <= dep; d++) {
-          int jd = dm->link_anc[h][link][d];
+          int jd = sm.anc[h][link][d];
           double s2 = 0;
-          for (int e = 0; e <= dep; e++) s2 += sm.Minv[h][jd][dm->link_anc[h][link][e]] * cn.Jc[r][e];
+          for (int e = 0; e <= dep; e++) s2 -= sm.A[h][jd * RS + sm.anc[h][link][e]] * cn.Jc[r][e];
           u[r][d] = s2;
         }
       for (int r = 0; r < 3; r++)
@@ -789,10 +832,10 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
     __syncwarp();
     if (lane < ncon) {
       Contact& cn = sm.u.c.con[lane];
-      int h = cn.hand, link = cn.link, dep = dm->link_depth[h][link];
+      int h = cn.hand, link = cn.link, dep = sm.dep[h][link];
       for (int r = 0; r < 3; r++) {
         double s2 = 0;
-        for (int d = 0; d <= dep; d++) s2 += cn.Jc[r][d] * sm.wbuf[h][dm->link_anc[h][link][d]];
+        for (int d = 0; d <= dep; d++) s2 += cn.Jc[r][d] * sm.wbuf[h][sm.anc[h][link][d]];
         if (cn.key >= 0) s2 += cn.Jk[r] * sm.vak[cn.key];
         cn.b[r] = s2 - cn.aref[r];
       }
@@ -826,11 +869,11 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
     __syncwarp();
     if (lane < ncon) {
       Contact& cn = sm.u.c.con[lane];
-      int h = cn.hand, link = cn.link, dep = dm->link_depth[h][link];
+      int h = cn.hand, link = cn.link, dep = sm.dep[h][link];
       double jar[3], D[3];
       for (int r = 0; r < 3; r++) {
         double s2 = 0;
-        for (int d = 0; d <= dep; d++) s2 += cn.Jc[r][d] * sm.wbuf[h][dm->link_anc[h][link][d]];
+        for (int d = 0; d <= dep; d++) s2 += cn.Jc[r][d] * sm.wbuf[h][sm.anc[h][link][d]];
         if (cn.key >= 0) s2 += cn.Jk[r] * sm.vak[cn.key];
         jar[r] = s2 - cn.aref[r];
         D[r] = 1.0 / cn.R[r];
@@ -872,7 +915,7 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
             const Contact& cn = sm.u.c.con[c];
             if (cn.hand == h) {
               int link = cn.link;
-              bool anc = lane <= link && link < lane + dm->link_subtree[h][lane];
+              bool anc = lane <= link && link < lane + sm.sub[h][lane];
               if (anc) { int d = ldep[h]; wq[h] += cn.Jc[0][d] * cn.f[0] + cn.Jc[1][d] * cn.f[1] + cn.Jc[2][d] * cn.f[2]; }
             }
           }
@@ -903,7 +946,7 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
 #pragma unroll
       for (int h = 0; h < NH; h++) {
         double s2 = 0;
-        if (hl) for (int k = 0; k < NL; k++) s2 += sm.Minv[h][k][lane] * sm.wbuf[h][k];
+        if (hl) for (int k = 0; k < NL; k++) s2 -= sm.A[h][k * RS + lane] * sm.wbuf[h][k];
         va[h] = s2;
         cost += 0.5 * wq[h] * s2;
       }
@@ -953,51 +996,45 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
     // =============================================================== PGS
     // Row order inside a sweep follows MuJoCo: friction-loss dofs, joint limits (keys, then hand
     // joints), contacts.  Rows that do not interact (the two hands, untouched keys) are advanced
-    // together.  1-D rows: the candidate update is evaluated by every lane for its own row (no
-    // divergence) and only lane i's result is committed at step i.
+    // together.  Scalar hand rows (friction loss, limits) run in a half-warp-per-hand mapping: lanes
+    // 0-15 serve hand 0, lanes 16-31 hand 1, each lane owning dofs l and l+16 of its hand, so one
+    // instruction stream sweeps both hands (gs_rows).  Contacts still use lane == dof.
     int iter = 0;
     const int maxiter = a.iterations > 0 ? a.iterations : dm->iterations;
     const double tol = a.tolerance >= 0 ? a.tolerance : dm->tol;
     const unsigned anyrow_fr = (NH > 0 ? fr_mask[0] : 0u) | (NH > 1 ? fr_mask[NH > 1 ? 1 : 0] : 0u);
     const unsigned anyrow_lm = (NH > 0 ? lm_mask[0] : 0u) | (NH > 1 ? lm_mask[NH > 1 ? 1 : 0] : 0u);
-    double fr_ARi[NH > 0 ? NH : 1], fr_base[NH > 0 ? NH : 1], lm_ARi[NH > 0 ? NH : 1], lm_base[NH > 0 ? NH : 1];
+    const int hh = lane >> 4, l0 = lane & 15, l1 = (l0 + 16 < NL) ? l0 + 16 : l0;
+    const bool slot1 = l0 + 16 < NL;
+    HandRows FR, LM;
+    double van[2] = {0, 0};  // va in the half-warp mapping
+    if (NH > 1) {
+      const int H1 = NH > 1 ? 1 : 0;
+#define TO_NEW(x, s) to_new(x[0], x[H1], (s) ? l1 : l0, hh)
 #pragma unroll
-    for (int h = 0; h < NH; h++) {
-      fr_ARi[h] = 1.0 / fr_AR[h]; lm_ARi[h] = 1.0 / lm_AR[h];
-      fr_base[h] = fr_b[h] + fr_R[h] * fr_f[h];
-      lm_base[h] = lm_b[h] + lm_R[h] * lm_f[h];
-      if (!(hl && (fr_mask[h] >> lane & 1))) fr_loss[h] = 0;  // inactive rows clamp to zero
-      if (!(hl && (lm_mask[h] >> lane & 1))) { lm_J[h] = 0; lm_ARi[h] = 0; lm_base[h] = 0; }
+      for (int s = 0; s < 2; s++) {
+        const bool ok = s == 0 || slot1;
+        // all shuffles first (full warp), selects afterwards
+        const double fl = TO_NEW(fr_loss, s), far = TO_NEW(fr_AR, s), ff = TO_NEW(fr_f, s);
+        const double lar = TO_NEW(lm_AR, s), lf = TO_NEW(lm_f, s), lj = TO_NEW(lm_J, s), vv = TO_NEW(va, s);
+        FR.b[s] = TO_NEW(fr_b, s); FR.R[s] = TO_NEW(fr_R, s);
+        LM.b[s] = TO_NEW(lm_b, s); LM.R[s] = TO_NEW(lm_R, s);
+        const bool fon = ok && ((hh ? fr_mask[H1] : fr_mask[0]) >> (s ? l1 : l0) & 1);
+        const bool lon = ok && ((hh ? lm_mask[H1] : lm_mask[0]) >> (s ? l1 : l0) & 1);
+        FR.f[s] = ok ? ff : 0.0;
+        FR.AR[s] = far; FR.ARi[s] = fon ? 1.0 / far : 0.0; FR.J[s] = 1.0;
+        FR.hi[s] = fon ? fl : 0.0; FR.lo[s] = -FR.hi[s];
+        LM.f[s] = lon ? lf : 0.0;
+        LM.AR[s] = lar; LM.ARi[s] = lon ? 1.0 / lar : 0.0; LM.J[s] = lon ? lj : 0.0;
+        LM.lo[s] = 0.0; LM.hi[s] = lon ? __longlong_as_double(0x7ff0000000000000LL) : 0.0;
+        van[s] = ok ? vv : 0.0;
+      }
     }
+    const double* Ah = sm.A[NH > 1 ? hh : 0];
     while (iter < maxiter) {
       double improvement = iter == 0 ? improvement0 : 0.0;
-      // ---- friction-loss rows, dof order, both hands in lock-step (branch-free, hands interleaved)
-      if (NH > 0) {
-        for (int i = 0; i < NL; i++) {
-          const bool mine = lane == i;
-          double res[NH > 0 ? NH : 1], fn[NH > 0 ? NH : 1], dl[NH > 0 ? NH : 1], dbc[NH > 0 ? NH : 1], mrow[NH > 0 ? NH : 1];
-#pragma unroll
-          for (int h = 0; h < NH; h++) {
-            mrow[h] = sm.Minv[h][i][lane];
-            res[h] = fr_base[h] + va[h];
-            double x = fr_f[h] - res[h] * fr_ARi[h];
-            double lo = -fr_loss[h], fx = x;   // two independent selects: stays predicated
-            fx = x < lo ? lo : fx;
-            fx = x > fr_loss[h] ? fr_loss[h] : fx;
-            fn[h] = fx;
-            dl[h] = fn[h] - fr_f[h];
-          }
-#pragma unroll
-          for (int h = 0; h < NH; h++) dbc[h] = shfl(dl[h], i);
-#pragma unroll
-          for (int h = 0; h < NH; h++) {
-            va[h] += mrow[h] * dbc[h];
-            improvement -= mine ? dl[h] * (0.5 * dl[h] * fr_AR[h] + res[h]) : 0.0;
-            fr_f[h] = mine ? fn[h] : fr_f[h];
-            fr_base[h] = mine ? fr_b[h] + fr_R[h] * fn[h] : fr_base[h];
-          }
-        }
-      }
+      // ---- friction-loss rows, dof order
+      if (NH > 1) improvement += gs_rows(Ah, lane, l0, l1, anyrow_fr, FR, van);
       TICK(9)
       // ---- limit rows of keys that carry contacts (uniform scalar work, values in shared memory)
       for (int c = 0; c < nck; c++) {
@@ -1014,24 +1051,16 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
         __syncwarp();
       }
       // ---- hand limit rows
-      if (NH > 0) {
-        for (int i = 0; i < NL; i++) if (anyrow_lm >> i & 1) {
-          const bool mine = lane == i;
-#pragma unroll
-          for (int h = 0; h < NH; h++) {
-            double res = lm_base[h] + lm_J[h] * va[h];
-            double x = lm_f[h] - res * lm_ARi[h];
-            double fn = x < 0 ? 0.0 : x;
-            double dl = fn - lm_f[h];
-            double dbc = shfl(lm_J[h] * dl, i);
-            improvement -= mine ? dl * (0.5 * dl * lm_AR[h] + res) : 0.0;
-            lm_f[h] = mine ? fn : lm_f[h];
-            lm_base[h] = mine ? lm_b[h] + lm_R[h] * fn : lm_base[h];
-            va[h] += sm.Minv[h][i][lane] * dbc;
-          }
-        }
-      }
+      if (NH > 1 && anyrow_lm) improvement += gs_rows(Ah, lane, l0, l1, anyrow_lm, LM, van);
       TICK(10)
+      if (NH > 1 && ncon > 0) {
+        // half-warp mapping -> lane == dof for the contact rows
+        const int H1 = NH > 1 ? 1 : 0;
+        const double a0 = shfl(van[0], l0), a1 = shfl(van[1], l0);        // hand 0: dofs 0-15 / 16-31
+        const double b0 = shfl(van[0], 16 + l0), b1 = shfl(van[1], 16 + l0);
+        va[0] = lane < 16 ? a0 : a1;
+        va[H1] = lane < 16 ? b0 : b1;
+      }
       // ---- contacts, sorted order
       for (int c = 0; c < ncon; c++) {
         Contact& cn = sm.u.c.con[c];
@@ -1072,15 +1101,31 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
         for (int d = 0; d <= dep; d++) {
           const int j = cn.chain[d];
           const double wj = shfl(w, j);
-          acc += sm.Minv[h][j][lane] * wj;
+          acc -= sm.A[h][j * RS + lane] * wj;
         }
         if (h1) va[NH > 1 ? 1 : 0] += acc; else va[0] += acc;
         __syncwarp();
+      }
+      if (NH > 1 && ncon > 0) {
+        const int H1 = NH > 1 ? 1 : 0;
+#pragma unroll
+        for (int s = 0; s < 2; s++) { const double vv = TO_NEW(va, s); van[s] = (s == 0 || slot1) ? vv : 0.0; }
+        (void)H1;
       }
       TICK(11)
       improvement = warp_sum(improvement) * dm->solver_scale;
       iter++;
       if (improvement < tol) break;
+    }
+    if (NH > 1) {
+      // back to lane == dof
+      const int H1 = NH > 1 ? 1 : 0;
+#define TO_OLD(x, dst0, dst1) { const double a0_ = shfl(x[0], l0), a1_ = shfl(x[1], l0), b0_ = shfl(x[0], 16 + l0), b1_ = shfl(x[1], 16 + l0); \
+                               dst0 = lane < 16 ? a0_ : a1_; dst1 = lane < 16 ? b0_ : b1_; }
+      TO_OLD(van, va[0], va[H1]);
+      TO_OLD(FR.f, fr_f[0], fr_f[H1]);
+      TO_OLD(LM.f, lm_f[0], lm_f[H1]);
+      if (!hl) { va[0] = 0; va[H1] = 0; fr_f[0] = 0; fr_f[H1] = 0; lm_f[0] = 0; lm_f[H1] = 0; }
     }
     niter_last = iter;
 
@@ -1099,7 +1144,7 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
           const Contact& cn = sm.u.c.con[c];
           if (cn.hand == h) {
             int link = cn.link;
-            bool anc = lane <= link && link < lane + dm->link_subtree[h][lane];
+            bool anc = lane <= link && link < lane + sm.sub[h][lane];
             if (anc) { int d = ldep[h]; qfrc_c[h] += cn.Jc[0][d] * cn.f[0] + cn.Jc[1][d] * cn.f[1] + cn.Jc[2][d] * cn.f[2]; }
           }
         }
@@ -1152,45 +1197,32 @@ __global__ void __launch_bounds__(32) rp_step_kernel(RpKernelArgs a) {
     // Euler with implicit joint damping: (M + h*D) a = qfrc_smooth + qfrc_constraint
     double aeul[NH > 0 ? NH : 1];
     if (NH > 0) {
-#pragma unroll
-      for (int h = 0; h < NH; h++) {
-        if (hl) {
-          for (int j = 0; j < 32; j++) sm.Minv[h][lane][j] = 0;
-        }
-      }
+      double* Aflat = &sm.A[0][0];
+      for (int idx = lane; idx < NH * NL * RS; idx += 32) Aflat[idx] = 0;
       __syncwarp();
 #pragma unroll
       for (int h = 0; h < NH; h++) {
         if (hl) {
-#pragma unroll
-          for (int d = 0; d < MAXD; d++) {
-            if (d <= ldep[h]) {
-              int j = dm->link_anc[h][lane][d];
-              double v = Mrow[h][d];
-              if (d == ldep[h]) v += hstep * dm->link_damping[h][lane];
-              sm.Minv[h][lane][j] = v;
-              sm.Minv[h][j][lane] = v;
-            }
+          for (int d = 0; d <= ldep[h]; d++) {
+            const int j = sm.anc[h][lane][d];
+            double v = sm.Mrow[h][lane][d];
+            if (d == ldep[h]) v += hstep * dm->link_damping[h][lane];
+            sm.A[h][lane * RS + j] = v;
+            sm.A[h][j * RS + lane] = v;
           }
-          sm.Minv[h][lane][NL] = qfrc_smooth[h] + qfrc_c[h];  // augmented column: right-hand side
+          sm.wbuf[h][lane] = qfrc_smooth[h] + qfrc_c[h];  // right-hand side
         }
       }
       __syncwarp();
-      // a = (M + h*D)^-1 rhs : sweep-invert in registers, then one row-times-vector per lane
-      {
-        double col[NH > 0 ? NH : 1][NL];
-        sweep_inverse<NH>(sm, lane, col);
+      // a = (M + h*D)^-1 rhs: sweep (A = -inverse), then one row-times-vector per lane
+      sweep_inverse<NH>(sm, lane);
 #pragma unroll
-        for (int h = 0; h < NH; h++) {
-          double acc = 0;
-#pragma unroll
-          for (int i = 0; i < NL; i++) acc -= col[h][i] * sm.Minv[h][i][NL];  // rhs sits in the padded column NL
-          sm.wbuf[h][lane] = acc;
-        }
-        __syncwarp();
+      for (int h = 0; h < NH; h++) {
+        double acc = 0;
+        if (hl) for (int i = 0; i < NL; i++) acc -= sm.A[h][lane * RS + i] * sm.wbuf[h][i];
+        aeul[h] = acc;
       }
-#pragma unroll
-      for (int h = 0; h < NH; h++) aeul[h] = hl ? sm.wbuf[h][lane] : 0.0;
+      __syncwarp();
     }
     TICK(8)
     // integrate
