@@ -34,6 +34,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 ENVS_PER_GPU = 4096
+NCU_DRAM_BYTES_PER_LAUNCH = 45.6e6  # profiles/r01_ncu_p2.csv: dram__bytes_read.sum + dram__bytes_write.sum, 4096 envs
 SONG = "TwinkleTwinkleRousseau"
 METRIC = "env-steps/sec at 4096 envs/GPU (piano_with_shadow_hands, 10 substeps/step)"
 
@@ -217,14 +218,19 @@ def main():
     value = N * world * args.steps / (dev_ms * 1e-3)
     diag = batch.get_diag()
 
-    # ---- e2e: host actions in, host results out, every step, through rp_step_host
-    e2e_steps = max(3, min(args.steps, 10))
-    host_actions = actions_np
-    batch.step_host(host_actions[0])
+    # ---- e2e: the same step sequence again, through the host call (rp_step_staged: pageable numpy actions ->
+    # pinned staging -> device, launch, device -> pinned staging, read on the host), wall clock
+    batch.reset(None, obs.data_ptr())
+    for t in range(args.warmup):
+        one_step(t)
     barrier()
+    e2e_steps = args.steps
+    host_actions = actions_np
     w0 = time.perf_counter()
+    e2e_reward = 0.0
     for k in range(e2e_steps):
-        batch.step_host(host_actions[(k + 1) % pool])
+        _, rew_h, _, _, _ = batch.step_host(host_actions[(args.warmup + k) % pool], copy=False)
+        e2e_reward += float(rew_h.sum())  # each rank consumes its own shard on the host (no collective on this path)
     barrier()
     e2e_s = time.perf_counter() - w0
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -249,7 +255,8 @@ def main():
     kernel_ms = dev_ms / args.steps  # one launch per step (plus NCCL for N>1)
     achieved = N * abytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH if N == ENVS_PER_GPU else None, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/)",
+                "peak_source": "measured" if peaks else "fallback",
                 "algorithmic_bytes_per_env_step": abytes,
                 "note": "latency/ALU-bound fp64 Gauss-Seidel; see profiles/ for pipe utilisation"}
     line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,

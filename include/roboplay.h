@@ -122,6 +122,13 @@ int rp_step(rp_batch *, const double *action_dev, double *obs_dev, double *rewar
 int rp_step_host(rp_batch *, const double *action, double *obs, double *reward, double *discount,
                  uint8_t *step_type, double *reward_terms);
 
+/* Staged form of the same call: the caller writes actions into the pinned input buffer and reads the
+ * results from the pinned output buffer returned by rp_host_buffers (layout, in doubles: obs
+ * [N,obs_dim], reward [N], discount [N], reward_terms [N,5], then step_type as N bytes).  One H2D
+ * copy, one launch, one D2H copy, one stream synchronise; no pageable copies. */
+int rp_step_staged(rp_batch *);
+int rp_host_buffers(rp_batch *, double **action_pinned, double **out_pinned);
+
 /* Physics-only advance (mj_step x nsub with ctrl as given, no task logic); used by parity tests.
  * ctrl_dev [N,nu]. */
 int rp_physics_step(rp_batch *, const double *ctrl_dev, int nsub);

@@ -397,12 +397,13 @@ extern "C" int rp_step(rp_batch* b, const double* action_dev, double* obs_dev, d
   return launch(b, a);
 }
 
-extern "C" int rp_step_host(rp_batch* b, const double* action, double* obs, double* reward, double* discount,
-                            uint8_t* step_type, double* reward_terms) {
+// Staged form of the host call: actions are written by the caller into the pinned input buffer and
+// results are left in the pinned output buffer (rp_host_buffers), so a step costs one H2D copy, one
+// launch, one D2H copy and a stream synchronise — no pageable memcpy, no allocation.
+extern "C" int rp_step_staged(rp_batch* b) {
   const rp_model* M = b->model;
   size_t N = b->nenv, od = M->obs_dim, ad = M->act_dim;
   CUDA_OK(cudaSetDevice(b->device));
-  memcpy(b->h_action, action, sizeof(double) * N * ad);
   CUDA_OK(cudaMemcpyAsync(b->d_action, b->h_action, sizeof(double) * N * ad, cudaMemcpyHostToDevice, b->stream));
   double* d_obs = b->d_out;
   double* d_rew = d_obs + N * od;
@@ -413,6 +414,23 @@ extern "C" int rp_step_host(rp_batch* b, const double* action, double* obs, doub
   size_t bytes = sizeof(double) * (N * od + 2 * N + 5 * N) + N;
   CUDA_OK(cudaMemcpyAsync(b->h_out, b->d_out, bytes, cudaMemcpyDeviceToHost, b->stream));
   CUDA_OK(cudaStreamSynchronize(b->stream));
+  return 0;
+}
+
+// Pinned staging buffers of rp_step_staged / rp_step_host.  out layout (doubles): obs [N,obs_dim],
+// reward [N], discount [N], reward_terms [N,5], then step_type as N bytes.
+extern "C" int rp_host_buffers(rp_batch* b, double** action_pinned, double** out_pinned) {
+  if (action_pinned) *action_pinned = b->h_action;
+  if (out_pinned) *out_pinned = b->h_out;
+  return 0;
+}
+
+extern "C" int rp_step_host(rp_batch* b, const double* action, double* obs, double* reward, double* discount,
+                            uint8_t* step_type, double* reward_terms) {
+  const rp_model* M = b->model;
+  size_t N = b->nenv, od = M->obs_dim, ad = M->act_dim;
+  if (action != b->h_action) memcpy(b->h_action, action, sizeof(double) * N * ad);
+  if (rp_step_staged(b)) return 1;
   if (obs) memcpy(obs, b->h_out, sizeof(double) * N * od);
   if (reward) memcpy(reward, b->h_out + N * od, sizeof(double) * N);
   if (discount) memcpy(discount, b->h_out + N * od + N, sizeof(double) * N);

@@ -27,8 +27,20 @@
 #define MAXCON RP_MAXCON
 #define RS 27  // row stride of the hand matrices (odd: lane-per-row accesses are bank-conflict free)
 #define H1 (RP_NHMAX - 1)
+// tuning knobs (instruction-cache footprint of the PGS loop vs. per-row overhead)
+#ifndef RP_FR_UNROLL
+#define RP_FR_UNROLL 1  // rolled: the 25-instruction body stays in the L0 instruction cache (measured 27.7 -> 24.6 ms/step)
+#endif
+#ifndef RP_CH_UNROLL
+#define RP_CH_UNROLL 1
+#endif
+#ifndef RP_MINBLOCKS
+#define RP_MINBLOCKS 6
+#endif
 
 namespace {
+
+constexpr int kFrUnroll = RP_FR_UNROLL, kChUnroll = RP_CH_UNROLL;
 
 struct Contact {  // lives in shared memory
   double Jc[3][MAXD];  // hand-chain Jacobian entries by depth (already signed: body2 - body1)
@@ -52,14 +64,14 @@ struct RawContact {  // narrowphase output before sorting
 struct Smem {
   double A[RP_NHMAX][NL * RS];  // per hand: M, then -M^-1 (sweep), later -(M + h*D)^-1; symmetric, row-major
   double S[RP_NHMAX][NL][6];
-  double qk[NK], vk[NK], vak[NK];
+  double vk[NK], vak[NK];
   double ksn[NK], kcs[NK];            // sin / cos of the key angles of this substep
   double wbuf[RP_NHMAX][32];
   double wsb[RP_NHMAX][32];           // qacc_warmstart of the hand dofs (read by the contact rows)
   double actf[RP_NHMAX][RP_NAH];
   double vh[RP_NHMAX][NL];            // hand joint velocities (for chain walks)
-  double kfrc[NK], kqs[NK], kfc[NK];  // per key: qfrc_smooth, qacc_smooth, constraint force J^T f
-  double Mrow[RP_NHMAX][NL][MAXD];    // mass-matrix entries M[link][ancestor at depth d] (kept for the Euler solve)
+  double kfc[NK];                     // per key: constraint force J^T f (qacc_warmstart before the sweep)
+  double Mrow[RP_NHMAX][160];         // mass-matrix entries M[link][ancestor at depth d], packed by link (kept for the Euler solve)
   double ctrl[NK];                    // actuator controls of this control step
   double site[RP_NHMAX][RP_NSITE][3]; // fingertip sites (task epilogue)
   double red[2][RP_NHMAX][8];         // block reductions (double buffered)
@@ -73,10 +85,8 @@ struct Smem {
   int nck, shared_key;                // shared_key: some key carries contacts of both hands
   union {
     double acc[RP_NHMAX][NL][16];  // upward accumulation scratch: F (6) + composite inertia (10)
-    struct {
-      Contact con[MAXCON];
-      RawContact raw[MAXCON];
-    } c;
+    Contact con[MAXCON];           // constraint blocks of the contacts (sorted)
+    RawContact raw[MAXCON];        // narrowphase output; moved to registers before con[] is written
   } u;
   int ncon, nraw, overflow, pad;
 };
@@ -152,7 +162,7 @@ __device__ __noinline__ void sweep_inverse(double* A, const signed char* anc /*[
 // The kernel proper is large; it is written as one function so that lane-owned state stays in
 // registers across the stages of a substep.
 template <int NW>
-__global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKernelArgs a) {
+__global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_kernel(RpKernelArgs a) {
   constexpr bool HANDS = NW == 2;
   constexpr int KT = 32 * NW;               // threads per environment
   constexpr int KS = (NK + KT - 1) / KT;    // keys per thread
@@ -223,8 +233,17 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
   const int ldep = hl ? dm->link_depth[h][lane] : -1;
   const int ljt = hl ? dm->link_jtype[h][lane] : 0;
   const int lsub = hl ? dm->link_subtree[h][lane] : 0;
+  int flags_init_overflow = 0;
   const int ldc = ldep > 0 ? ldep : 0;
   const int maxd = HANDS ? dm->maxdepth[h] : 0;
+  int moff = 0;  // offset of this link's packed mass-matrix row: exclusive prefix sum of depth + 1
+  if (HANDS) {
+    int v = hl ? ldep + 1 : 0, incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+    moff = incl - v;
+    if (__shfl_sync(FULL, incl, 31) > 160) flags_init_overflow = 1;
+  }
   // topology tables into shared memory (read in the inner loops of the sweep / contact rows)
   if (HANDS) {
     if (hl) for (int d = 0; d < MAXD; d++) sm.anc[h][lane][d] = (signed char)dm->link_anc[h][lane][d];
@@ -238,7 +257,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
   double key_actforce[KS];
 #pragma unroll
   for (int s = 0; s < KS; s++) key_actforce[s] = 0;
-  int niter_last = 0, ncon_last = 0, flags = 0;
+  int niter_last = 0, ncon_last = 0, flags = flags_init_overflow ? 4 : 0;
   const int maxiter = a.iterations > 0 ? a.iterations : dm->iterations;
   const double tol = a.tolerance >= 0 ? a.tolerance : dm->tol;
 
@@ -299,7 +318,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
       if (k < NK) {
         double sn, cs;
         sincos(qk[s], &sn, &cs);
-        sm.qk[k] = qk[s]; sm.vk[k] = vk[s]; sm.ksn[k] = sn; sm.kcs[k] = cs;
+        sm.vk[k] = vk[s]; sm.ksn[k] = sn; sm.kcs[k] = cs;
       }
     }
     if (last_pass) break;
@@ -379,7 +398,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
         for (int k = 0; k < 6; k++) Sj[k] = sm.S[h][j][k];
         double m = rp::dot6(Sj, fI);
         if (d == ldep) m += dm->link_armature[h][lane];
-        sm.Mrow[h][lane][d] = m;
+        sm.Mrow[h][moff + d] = m;
       }
     }
     // scatter M into the dense symmetric work matrix
@@ -390,7 +409,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
       if (hl) {
         for (int d = 0; d <= ldep; d++) {
           const int j = sm.anc[h][lane][d];
-          const double m = sm.Mrow[h][lane][d];
+          const double m = sm.Mrow[h][moff + d];
           Aw[lane * RS + j] = m;
           Aw[j * RS + lane] = m;
         }
@@ -447,13 +466,13 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
       __syncwarp();
     }
     // ------------------------------------------------------------------ keys: smooth dynamics + limit rows
-    double ks_qacc[KS], kM[KS];
+    double ks_qacc[KS], ks_qfrc[KS], kM[KS];
     KeyRow krow[KS];
 #pragma unroll
     for (int s = 0; s < KS; s++) {
       const int k = tid + KT * s;
       krow[s].active = 0; krow[s].f = 0; krow[s].J = 0; krow[s].R = 0; krow[s].b = 0; krow[s].ARinv = 0; krow[s].AR = 1; krow[s].aref = 0;
-      ks_qacc[s] = 0; kM[s] = 1; key_actforce[s] = 0;
+      ks_qacc[s] = 0; ks_qfrc[s] = 0; kM[s] = 1; key_actforce[s] = 0;
       if (k < NK) {
         double ax[3] = {dm->key_axis[k][0], dm->key_axis[k][1], dm->key_axis[k][2]};
         double r0[3] = {dm->key_ipos[k][0] - dm->key_jpos[k][0], dm->key_ipos[k][1] - dm->key_jpos[k][1], dm->key_ipos[k][2] - dm->key_jpos[k][2]};
@@ -473,8 +492,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
         kM[s] = dm->key_M[k];
         const double kq = passive - bias + actq;
         ks_qacc[s] = kq / kM[s];
-        sm.kfrc[k] = kq;
-        sm.kqs[k] = ks_qacc[s];
+        ks_qfrc[s] = kq;
         sm.keyslot[k] = -1;
         const double lo = dm->key_range[k][0], hi = dm->key_range[k][1];
         const double dlo = qk[s] - lo, dhi = hi - qk[s];
@@ -625,7 +643,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
               if (ti < ntest && dist < margin) {
                 const int slot = atomicAdd(&sm.nraw, 1);
                 if (slot < MAXCON) {
-                  RawContact& rc = sm.u.c.raw[slot];
+                  RawContact& rc = sm.u.raw[slot];
                   double nw[3], pw[3];
                   rp::mat_vec(nw, R, n);
                   rp::mat_vec(pw, R, p);
@@ -658,15 +676,15 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
     if (HANDS && h == 0 && ncon > 0) {
       int myrank = -1;
       if (lane < nraw) {
-        const unsigned mykey = sm.u.c.raw[lane].sortkey;
+        const unsigned mykey = sm.u.raw[lane].sortkey;
         myrank = 0;
-        for (int j = 0; j < nraw; j++) myrank += (sm.u.c.raw[j].sortkey < mykey) ? 1 : 0;
+        for (int j = 0; j < nraw; j++) myrank += (sm.u.raw[j].sortkey < mykey) ? 1 : 0;
       }
-      // contact geometry is first moved to registers (raw[] aliases nothing in con[], both live in the union)
+      // contact geometry is first moved to registers: raw[] and con[] share the same shared memory
       double c_dist = 0, c_pos[3] = {0, 0, 0}, c_frame[9];
       int c_hand = 0, c_geom = 0, c_key = -1;
       if (lane < ncon) {
-        RawContact rc = sm.u.c.raw[lane];
+        RawContact rc = sm.u.raw[lane];
         c_dist = rc.dist;
         for (int k = 0; k < 3; k++) { c_pos[k] = rc.pos[k]; c_frame[k] = rc.n[k]; }
         const double nn = sqrt(rp::dot3(c_frame, c_frame));
@@ -676,7 +694,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
       }
       __syncwarp();
       if (lane < ncon) {
-        Contact& cn = sm.u.c.con[myrank];
+        Contact& cn = sm.u.con[myrank];
         const int ch = c_hand, link = dm->geom_link[ch][c_geom];
         cn.hand = ch; cn.link = link; cn.key = c_key;
         // mixed parameters
@@ -777,11 +795,11 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
         bool firstc = false, sharedc = false;
         int mykey = -1, myhand = -1;
         if (lane < ncon) {
-          mykey = sm.u.c.con[lane].key;
-          myhand = sm.u.c.con[lane].hand;
-          const bool samekey = lane > 0 && sm.u.c.con[lane - 1].key == mykey;
+          mykey = sm.u.con[lane].key;
+          myhand = sm.u.con[lane].hand;
+          const bool samekey = lane > 0 && sm.u.con[lane - 1].key == mykey;
           firstc = mykey >= 0 && !samekey;
-          sharedc = mykey >= 0 && samekey && sm.u.c.con[lane - 1].hand != myhand;
+          sharedc = mykey >= 0 && samekey && sm.u.con[lane - 1].hand != myhand;
         }
         const unsigned fmask = __ballot_sync(FULL, firstc);
         const unsigned smask = __ballot_sync(FULL, sharedc);
@@ -824,7 +842,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
         wq = fr_f + lm_J * lm_f;
         cost += 0.5 * fr_R * fr_f * fr_f + fr_f * fr_b + 0.5 * lm_R * lm_f * lm_f + lm_f * lm_b;
         for (int ci = 0; ci < nmine; ci++) {
-          const Contact& cn = sm.u.c.con[sm.hlist[h][ci]];
+          const Contact& cn = sm.u.con[sm.hlist[h][ci]];
           const int link = cn.link;
           if (lane <= link && link < lane + lsub) wq += cn.Jc[0][ldc] * cn.f[0] + cn.Jc[1][ldc] * cn.f[1] + cn.Jc[2][ldc] * cn.f[2];
         }
@@ -840,14 +858,14 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
           cost += 0.5 * krow[s].R * krow[s].f * krow[s].f + krow[s].f * krow[s].b;
           if (sm.keyslot[k] >= 0)
             for (int c = 0; c < ncon; c++) {
-              const Contact& cn = sm.u.c.con[c];
+              const Contact& cn = sm.u.con[c];
               if (cn.key == k) wqk[s] += cn.Jk[0] * cn.f[0] + cn.Jk[1] * cn.f[1] + cn.Jk[2] * cn.f[2];
             }
           cost += 0.5 * wqk[s] * wqk[s] / kM[s];
         }
       }
       if (HANDS && h == 0 && lane < ncon) {
-        const Contact& cn = sm.u.c.con[lane];
+        const Contact& cn = sm.u.con[lane];
         for (int r = 0; r < 3; r++) cost += 0.5 * cn.R[r] * cn.f[r] * cn.f[r] + cn.f[r] * cn.b[r];
       }
       __syncwarp();
@@ -866,7 +884,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
       const bool keep = !(cost > 0);
       if (!keep) {
         fr_f = 0; lm_f = 0; va = 0;
-        if (HANDS && h == 0 && lane < ncon) { Contact& cn = sm.u.c.con[lane]; cn.f[0] = cn.f[1] = cn.f[2] = 0; }
+        if (HANDS && h == 0 && lane < ncon) { Contact& cn = sm.u.con[lane]; cn.f[0] = cn.f[1] = cn.f[2] = 0; }
       }
       if (a.dbg && sub == 0 && tid == 0) a.dbg[(size_t)env * RP_DBG_STRIDE + RP_DBG_SCALARS + 3] = cost;
       // key rows: uncoupled ones are solved exactly now (one Gauss-Seidel update of a 1x1 system is
@@ -916,7 +934,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
           // ---- friction-loss rows, dof order: every lane evaluates the candidate update of its own
           // row; lane i commits at step i and broadcasts the force change
           const double fbase = fr_b + fr_R * fr_f;  // f only changes at the lane's own commit
-#pragma unroll
+#pragma unroll kFrUnroll
           for (int i = 0; i < NL; i++) {
             const double mrow = Ah[i * RS + lc];
             const double res = fbase + va;
@@ -964,7 +982,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
           const int ntrip = shared_key ? ncon : nmine;
           for (int ci = 0; ci < ntrip; ci++) {
             const int c = shared_key ? ci : sm.hlist[h][ci];
-            Contact& cn = sm.u.c.con[c];
+            Contact& cn = sm.u.con[c];
             if (!shared_key || cn.hand == h) {
               const int link = cn.link, key = cn.key, dep = cn.dep;
               const bool anc = lane <= link && link < lane + lsub;
@@ -992,16 +1010,19 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
               __syncwarp();
               improvement -= lane == 0 ? change : 0.0;
               cn.f[0] = f[0]; cn.f[1] = f[1]; cn.f[2] = f[2];  // identical on every lane
-              if (key >= 0) sm.vak[key] = vak + (cn.Jk[0] * df[0] + cn.Jk[1] * df[1] + cn.Jk[2] * df[2]) * cn.invMk;
-              // hand side: w = Jc^T df on the chain, va += Minv[:,chain] w
-              const double w = j0 * df[0] + j1 * df[1] + j2 * df[2];
-              double acc = 0;
-              for (int d = 0; d <= dep; d++) {
-                const int j = cn.chain[d];
-                const double wj = shfl(w, j);
-                acc -= Ah[j * RS + lc] * wj;
+              if (df[0] != 0.0 || df[1] != 0.0 || df[2] != 0.0) {  // warp-uniform; an unchanged force moves nothing
+                if (key >= 0) sm.vak[key] = vak + (cn.Jk[0] * df[0] + cn.Jk[1] * df[1] + cn.Jk[2] * df[2]) * cn.invMk;
+                // hand side: w = Jc^T df on the chain, va += Minv[:,chain] w
+                const double w = j0 * df[0] + j1 * df[1] + j2 * df[2];
+                double acc = 0;
+#pragma unroll kChUnroll
+                for (int d = 0; d <= dep; d++) {
+                  const int j = cn.chain[d];
+                  const double wj = shfl(w, j);
+                  acc -= Ah[j * RS + lc] * wj;
+                }
+                va += acc;
               }
-              va += acc;
               __syncwarp();
             }
             if (shared_key) block_sync<NW>();
@@ -1027,7 +1048,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
     if (hl) {
       qfrc_c = fr_f + lm_J * lm_f;
       for (int ci = 0; ci < nmine; ci++) {
-        const Contact& cn = sm.u.c.con[sm.hlist[h][ci]];
+        const Contact& cn = sm.u.con[sm.hlist[h][ci]];
         const int link = cn.link;
         if (lane <= link && link < lane + lsub) qfrc_c += cn.Jc[0][ldc] * cn.f[0] + cn.Jc[1][ldc] * cn.f[1] + cn.Jc[2][ldc] * cn.f[2];
       }
@@ -1037,7 +1058,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
     if (tid == 0) {
       for (int c = 0; c < nck; c++) sm.kfc[sm.ck[c].key] = sm.ck[c].J * sm.ck[c].f;
       for (int c = 0; c < ncon; c++) {
-        const Contact& cn = sm.u.c.con[c];
+        const Contact& cn = sm.u.con[c];
         if (cn.key >= 0) sm.kfc[cn.key] += cn.Jk[0] * cn.f[0] + cn.Jk[1] * cn.f[1] + cn.Jk[2] * cn.f[2];
       }
     }
@@ -1049,8 +1070,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
       kq_acc[s] = 0; kq_frc[s] = 0; kq_smooth[s] = 0;
       if (k < NK) {
         kq_frc[s] = sm.kfc[k];
-        kq_smooth[s] = sm.kfrc[k];
-        kq_acc[s] = sm.kqs[k] + sm.vak[k];
+        kq_smooth[s] = ks_qfrc[s];
+        kq_acc[s] = ks_qacc[s] + sm.vak[k];
       }
     }
     if (a.dbg && sub == 0) {
@@ -1058,7 +1079,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
 #pragma unroll
       for (int s = 0; s < KS; s++) {
         const int k = tid + KT * s;
-        if (k < NK) { dbg[RP_DBG_QACC_SMOOTH + k] = sm.kqs[k]; dbg[RP_DBG_QACC + k] = kq_acc[s]; dbg[RP_DBG_QFRC_C + k] = kq_frc[s]; dbg[RP_DBG_BIAS + k] = 0; }
+        if (k < NK) { dbg[RP_DBG_QACC_SMOOTH + k] = ks_qacc[s]; dbg[RP_DBG_QACC + k] = kq_acc[s]; dbg[RP_DBG_QFRC_C + k] = kq_frc[s]; dbg[RP_DBG_BIAS + k] = 0; }
       }
       if (hl) {
         dbg[RP_DBG_QACC_SMOOTH + NK + h * NL + lane] = qacc_smooth;
@@ -1068,7 +1089,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
       }
       if (tid == 0) { dbg[RP_DBG_SCALARS + 0] = ncon; dbg[RP_DBG_SCALARS + 1] = iter; dbg[RP_DBG_SCALARS + 2] = sm.overflow; }
       if (tid < ncon) {
-        const Contact& cn = sm.u.c.con[tid];
+        const Contact& cn = sm.u.con[tid];
         double* o = dbg + RP_DBG_CONTACTS + tid * 16;
         o[0] = cn.key; o[1] = cn.hand; o[2] = cn.link; o[3] = cn.f[0]; o[4] = cn.f[1]; o[5] = cn.f[2];
         o[6] = cn.b[0]; o[7] = cn.b[1]; o[8] = cn.b[2]; o[9] = cn.R[0]; o[10] = cn.A[0]; o[11] = cn.A[4]; o[12] = cn.A[1];
@@ -1085,7 +1106,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? 6 : 8) rp_step_kernel(RpKer
       if (hl) {
         for (int d = 0; d <= ldep; d++) {
           const int j = sm.anc[h][lane][d];
-          double v = sm.Mrow[h][lane][d];
+          double v = sm.Mrow[h][moff + d];
           if (d == ldep) v += hstep * dm->link_damping[h][lane];
           Aw[lane * RS + j] = v;
           Aw[j * RS + lane] = v;

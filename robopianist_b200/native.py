@@ -13,13 +13,15 @@ import numpy as np
 from . import cabi
 
 _LIB = None
-LIB_PATH = Path(__file__).resolve().parent / "libroboplay.so"
+import os
+# ROBOPLAY_LIB selects an alternative build of the same library (kernel tuning variants)
+LIB_PATH = Path(os.environ.get("ROBOPLAY_LIB") or Path(__file__).resolve().parent / "libroboplay.so")
 
 EXPORTS = [
     "rp_last_error", "rp_version", "rp_model_create", "rp_model_destroy", "rp_obs_dim", "rp_action_dim",
     "rp_reward_terms", "rp_batch_create", "rp_batch_destroy", "rp_set_option", "rp_reset", "rp_step",
     "rp_step_host", "rp_physics_step", "rp_get_state", "rp_set_state", "rp_get_diag", "rp_get_aux",
-    "rp_launch_count",
+    "rp_launch_count", "rp_step_staged", "rp_host_buffers",
 ]
 
 
@@ -54,6 +56,8 @@ def lib():
         L.rp_set_state.argtypes = [vp, dp, dp, dp, ip]
         L.rp_get_diag.argtypes = [vp, ip, ip, ip]
         L.rp_get_aux.argtypes = [vp, dp, dp, u8]
+        L.rp_step_staged.argtypes = [vp]
+        L.rp_host_buffers.argtypes = [vp, C.POINTER(dp), C.POINTER(dp)]
         L.rp_launch_count.restype = C.c_int64
         L.rp_launch_count.argtypes = [vp]
         L.rp_debug_enable.argtypes = [vp, C.c_int]
@@ -125,13 +129,28 @@ class Batch:
     def step(self, action_ptr, obs_ptr, reward_ptr, discount_ptr, step_type_ptr, terms_ptr=None):
         _check(lib().rp_step(self.ptr, action_ptr, obs_ptr, reward_ptr, discount_ptr, step_type_ptr, terms_ptr))
 
-    def step_host(self, action: np.ndarray):
-        N, m = self.nenv, self.model
-        action = np.ascontiguousarray(action, np.float64).reshape(N, m.act_dim)
-        obs = np.empty((N, m.obs_dim)); rew = np.empty(N); dis = np.empty(N)
-        st = np.empty(N, np.uint8); terms = np.empty((N, 5))
-        _check(lib().rp_step_host(self.ptr, _dp(action), _dp(obs), _dp(rew), _dp(dis),
-                                  st.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(terms)))
+    def _staging(self):
+        """numpy views of the pinned staging buffers (rp_host_buffers)."""
+        if getattr(self, "_views", None) is None:
+            N, m = self.nenv, self.model
+            pa, po = C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+            _check(lib().rp_host_buffers(self.ptr, C.byref(pa), C.byref(po)))
+            od = m.obs_dim
+            act = np.ctypeslib.as_array(pa, shape=(N, m.act_dim))
+            out = np.ctypeslib.as_array(po, shape=(N * (od + 7) + (N + 7) // 8,))
+            st = out[N * (od + 7):].view(np.uint8)[:N]
+            self._views = (act, out[:N * od].reshape(N, od), out[N * od:N * od + N], out[N * od + N:N * od + 2 * N],
+                           st, out[N * od + 2 * N:N * od + 7 * N].reshape(N, 5))
+        return self._views
+
+    def step_host(self, action: np.ndarray, copy: bool = True):
+        """One control step with host buffers in and out (H2D + launch + D2H + sync inside the library).
+        copy=False returns views of the pinned output buffer (overwritten by the next call)."""
+        act, obs, rew, dis, st, terms = self._staging()
+        np.copyto(act, np.asarray(action, np.float64).reshape(act.shape))
+        _check(lib().rp_step_staged(self.ptr))
+        if copy:
+            return obs.copy(), rew.copy(), dis.copy(), st.copy(), terms.copy()
         return obs, rew, dis, st, terms
 
     def physics_step(self, ctrl_ptr=None, nsub=1):

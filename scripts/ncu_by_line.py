@@ -5,7 +5,7 @@ import csv, re, sys
 from collections import defaultdict
 sass_csv, dis, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-HELPER_END = 131
+HELPER_END = 200
 # address offset -> line
 off2line, cur, inside = {}, None, False
 for ln in open(dis):
