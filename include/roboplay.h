@@ -145,6 +145,14 @@ int rp_get_diag(rp_batch *, int32_t *ncon, int32_t *niter, int32_t *flags);
  * positions [N,nsite,3], key activation [N,88] uint8. */
 int rp_get_aux(rp_batch *, double *actuator_force, double *site_xpos, uint8_t *activation);
 
+/* Musical metrics of robopianist/wrappers/evaluation.py:40-177 (MidiEvaluationWrapper), accumulated on
+ * the device per environment (HOST buffer, synchronous).  out [N,16]: [0..2] running sums over the steps
+ * of the current episode of the per-step key-press precision / recall / F1 (sklearn
+ * precision_recall_fscore_support, average="binary", zero_division=1, activation vs. the goal keys of
+ * that step), [3..5] the same for the sustain pedal, [6] steps in the sums, [7] completed episodes,
+ * [8..13] the six means of the last completed episode, [14..15] reserved. */
+int rp_get_metrics(rp_batch *, double *out);
+
 int64_t rp_launch_count(const rp_batch *); /* kernels launched by this batch so far */
 
 #ifdef __cplusplus

@@ -29,6 +29,15 @@ def tolerance(x, bounds, margin):
     return np.where(in_bounds, 1.0, np.exp(-0.5 * (d * scale) ** 2))
 
 
+def prf_binary(y_true, y_pred):
+    """precision_recall_fscore_support(average="binary", zero_division=1) as called by the reference's
+    MidiEvaluationWrapper (wrappers/evaluation.py:140-147): restated so the tests can pin it to sklearn."""
+    y_true, y_pred = np.asarray(y_true) > 0.5, np.asarray(y_pred) > 0.5
+    tp = float((y_true & y_pred).sum()); fp = float((~y_true & y_pred).sum()); fn = float((y_true & ~y_pred).sum())
+    div = lambda a, b: a / b if b > 0 else 1.0
+    return div(tp, tp + fp), div(tp, tp + fn), div(2 * tp, 2 * tp + fp + fn)
+
+
 class RefEnv:
     """One environment: oracle physics + the reference's task logic (dm_env semantics)."""
 
@@ -101,6 +110,7 @@ class RefEnv:
         self._update_key_state()
         self._need_reset = False
         self.last_actuator_force = np.zeros(self.nu)
+        self._key_prf, self._sustain_prf = [], []  # MidiEvaluationWrapper.reset (wrappers/evaluation.py:90-93)
         return FIRST, None, None, self._observation()
 
     def step(self, action):
@@ -159,6 +169,13 @@ class RefEnv:
             step_type = LAST
         elif self.kind == 0 and self.wrong_press_termination and failure:
             discount, step_type = 0.0, LAST
+        # MidiEvaluationWrapper.step (wrappers/evaluation.py:67-88): activation after this step vs. the
+        # ground truth of this step index (`_notes[i]` == the goal emitted with the previous observation)
+        self._key_prf.append(prf_binary(goal_current[:-1], self.activation))
+        self._sustain_prf.append(prf_binary([goal_current[-1]], [float(self.sustain_activation)]))
         if step_type == LAST:
             self._need_reset = True
+            k, su = np.mean(self._key_prf, axis=0), np.mean(self._sustain_prf, axis=0)
+            self.musical_metrics = dict(precision=k[0], recall=k[1], f1=k[2], sustain_precision=su[0],
+                                        sustain_recall=su[1], sustain_f1=su[2])
         return step_type, float(reward), discount, obs

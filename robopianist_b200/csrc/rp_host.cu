@@ -38,6 +38,7 @@ struct rp_batch {
   double *qpos, *qvel, *qacc_ws, *ctrl, *sustain, *act_force, *site_xpos, *dbg;
   int32_t *t_idx, *step_type_state, *diag;
   uint8_t* activation;
+  double* metrics;  // [N][RP_METRICS_STRIDE] musical metrics accumulators (see rp_get_metrics)
   // staging for rp_step_host
   double *h_action, *h_out;  // pinned
   double *d_action, *d_out;
@@ -334,6 +335,7 @@ extern "C" rp_batch* rp_batch_create(const rp_model* model, int nenv, int device
   chk(dalloc(&b->ctrl, N * nu)); chk(dalloc(&b->sustain, N)); chk(dalloc(&b->act_force, N * nu));
   chk(dalloc(&b->site_xpos, N * 30)); chk(dalloc(&b->t_idx, N)); chk(dalloc(&b->step_type_state, N));
   chk(dalloc(&b->diag, N * 3)); chk(dalloc(&b->activation, N * RP_NK));
+  chk(dalloc(&b->metrics, N * RP_METRICS_STRIDE));
   size_t out_doubles = N * (model->obs_dim + 2 + 5) + (N + 7) / 8 + 8;
   chk(cudaMallocHost((void**)&b->h_action, sizeof(double) * N * model->act_dim));
   chk(cudaMallocHost((void**)&b->h_out, sizeof(double) * out_doubles));
@@ -352,7 +354,7 @@ extern "C" int rp_batch_destroy(rp_batch* b) {
   cudaFree(b->d_dm); cudaFree(b->d_goal); cudaFree(b->d_fingering);
   cudaFree(b->qpos); cudaFree(b->qvel); cudaFree(b->qacc_ws); cudaFree(b->ctrl); cudaFree(b->sustain);
   cudaFree(b->act_force); cudaFree(b->site_xpos); cudaFree(b->t_idx); cudaFree(b->step_type_state);
-  cudaFree(b->diag); cudaFree(b->activation); cudaFree(b->dbg); cudaFree(b->d_action); cudaFree(b->d_out);
+  cudaFree(b->diag); cudaFree(b->activation); cudaFree(b->metrics); cudaFree(b->dbg); cudaFree(b->d_action); cudaFree(b->d_out);
   cudaFreeHost(b->h_action); cudaFreeHost(b->h_out);
   delete b;
   return 0;
@@ -371,7 +373,7 @@ static RpKernelArgs base_args(rp_batch* b, int mode) {
   a.qpos = b->qpos; a.qvel = b->qvel; a.qacc_ws = b->qacc_ws; a.ctrl = b->ctrl;
   a.t_idx = b->t_idx; a.step_type_state = b->step_type_state; a.sustain = b->sustain;
   a.goal = b->d_goal; a.fingering = b->d_fingering;
-  a.diag = b->diag; a.act_force = b->act_force; a.site_xpos = b->site_xpos; a.activation = b->activation;
+  a.diag = b->diag; a.act_force = b->act_force; a.site_xpos = b->site_xpos; a.activation = b->activation; a.metrics = b->metrics;
   a.dbg = b->dbg;
   return a;
 }
@@ -487,6 +489,13 @@ extern "C" int rp_get_aux(rp_batch* b, double* actuator_force, double* site_xpos
   if (activation) CUDA_OK(cudaMemcpy(activation, b->activation, N * RP_NK, cudaMemcpyDeviceToHost));
   return 0;
 }
+extern "C" int rp_get_metrics(rp_batch* b, double* out) {
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  CUDA_OK(cudaMemcpy(out, b->metrics, sizeof(double) * (size_t)b->nenv * RP_METRICS_STRIDE, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 extern "C" int64_t rp_launch_count(const rp_batch* b) { return b->launches; }
 
 // Debug hooks (not part of the public header): stage dump of substep 0 for every env.

@@ -74,7 +74,7 @@ struct Smem {
   double Mrow[RP_NHMAX][160];         // mass-matrix entries M[link][ancestor at depth d], packed by link (kept for the Euler solve)
   double ctrl[NK];                    // actuator controls of this control step
   double site[RP_NHMAX][RP_NSITE][3]; // fingertip sites (task epilogue)
-  double red[2][RP_NHMAX][8];         // block reductions (double buffered)
+  double red[2][RP_NHMAX][10];        // block reductions (double buffered)
   CKey ck[MAXCON];                    // limit rows of keys that also carry contacts
   signed char anc[RP_NHMAX][NL][MAXD];  // ancestor-or-self at depth d
   signed char dep[RP_NHMAX][32], sub[RP_NHMAX][32];  // link depth / subtree size
@@ -120,6 +120,9 @@ __device__ __noinline__ double tolerance_gauss(double x, double lo, double hi, d
   const double sc = sqrt(-2 * log(0.1));
   return exp(-0.5 * (dd * sc) * (dd * sc));
 }
+
+// precision / recall / F-score ratio with sklearn's zero_division=1
+__device__ __forceinline__ double prf_ratio(double num, double den) { return den > 0 ? num / den : 1.0; }
 
 struct KeyRow {  // active limit row of a key (at most one side can be active)
   double J, R, b, aref, ARinv, AR, f;
@@ -1218,7 +1221,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     const uint8_t* gcur = a.goal + (size_t)min(t_idx, T - 1) * RP_GOAL_DIM_;  // goal emitted with the previous observation
     const bool should_terminate = (t_new - 1) == T - 1;
     // ---- key-press / activation statistics (block reduction through red[0])
-    double sum_on = 0, n_on = 0, false_pos = 0, sq = 0, xent = 0, pw = 0;
+    double sum_on = 0, n_on = 0, false_pos = 0, true_pos = 0, sq = 0, xent = 0, pw = 0;  // false_pos / true_pos: counts
 #pragma unroll
     for (int s = 0; s < KS; s++) {
       const int k = tid + KT * s;
@@ -1227,7 +1230,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         if (g) {
           sum_on += tolerance_gauss((double)g - knorm[s], 0.0, 0.05, 0.5);  // goal - state/qmax
           n_on += 1.0;
-        } else if (kact[s]) false_pos = 1.0;
+          if (kact[s]) true_pos += 1.0;
+        } else if (kact[s]) false_pos += 1.0;
         const double df = (kact[s] ? 1.0 : 0.0) - (double)g;
         sq += df * df;
         const double pr = kact[s] ? 1.0 : 0.0;  // negative_binary_cross_entropy, eps 1e-6 (self_actuated_piano.py:38-47)
@@ -1244,15 +1248,24 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         pw = fabs(actforce) * fabs(vel);
       }
     }
-    sum_on = warp_sum(sum_on); n_on = warp_sum(n_on); false_pos = warp_sum(false_pos);
+    sum_on = warp_sum(sum_on); n_on = warp_sum(n_on); false_pos = warp_sum(false_pos); true_pos = warp_sum(true_pos);
     sq = warp_sum(sq); xent = warp_sum(xent); pw = warp_sum(pw);
     if (HANDS) {
-      if (lane == 0) { double* r = sm.red[0][h]; r[2] = sum_on; r[3] = n_on; r[4] = false_pos; r[5] = sq; r[6] = xent; r[7] = pw; }
+      if (lane == 0) { double* r = sm.red[0][h]; r[2] = sum_on; r[3] = n_on; r[4] = false_pos; r[5] = sq; r[6] = xent; r[7] = pw; r[8] = true_pos; }
       block_sync<NW>();  // also publishes the sites
       const double* r0 = sm.red[0][0]; const double* r1 = sm.red[0][H1];
-      sum_on = r0[2] + r1[2]; n_on = r0[3] + r1[3]; false_pos = r0[4] + r1[4]; sq = r0[5] + r1[5]; xent = r0[6] + r1[6]; pw = r0[7] + r1[7];
+      sum_on = r0[2] + r1[2]; n_on = r0[3] + r1[3]; false_pos = r0[4] + r1[4]; sq = r0[5] + r1[5]; xent = r0[6] + r1[6]; pw = r0[7] + r1[7]; true_pos = r0[8] + r1[8];
     }
     const int gs = gcur[NK];
+    // musical metrics of this step (wrappers/evaluation.py:114-177): activation vs. the goal of this step
+    if (a.metrics && tid == 0) {
+      double* mt = a.metrics + (size_t)env * RP_METRICS_STRIDE;
+      const double tp = true_pos, fp = false_pos, fn = n_on - true_pos;
+      const double stp = (gs && sustain_act) ? 1.0 : 0.0, sfp = (!gs && sustain_act) ? 1.0 : 0.0, sfn = (gs && !sustain_act) ? 1.0 : 0.0;
+      mt[0] += prf_ratio(tp, tp + fp); mt[1] += prf_ratio(tp, tp + fn); mt[2] += prf_ratio(2 * tp, 2 * tp + fp + fn);
+      mt[3] += prf_ratio(stp, stp + sfp); mt[4] += prf_ratio(stp, stp + sfn); mt[5] += prf_ratio(2 * stp, 2 * stp + sfp + sfn);
+      mt[6] += 1.0;
+    }
     if (dm->task_kind == 0) {
       const double r_key = (n_on > 0 ? 0.5 * sum_on / n_on : 0.0) + 0.5 * (false_pos > 0 ? 0.0 : 1.0);
       // sustain: tolerance(goal - sustain_activation)
@@ -1342,6 +1355,15 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         for (int k = 0; k < NK; k++) if (fc[k] == tid && a.goal[(size_t)tf * RP_GOAL_DIM_ + k]) v = 1.0;
         o[off + tid] = v;
       }
+    }
+  }
+  if (tid == 0 && a.metrics) {
+    double* mt = a.metrics + (size_t)env * RP_METRICS_STRIDE;
+    if (first) {
+      for (int k = 0; k < 7; k++) mt[k] = 0;  // a new episode starts
+    } else if (step_type == RP_STEP_LAST_ && mt[6] > 0) {
+      for (int k = 0; k < 6; k++) mt[8 + k] = mt[k] / mt[6];
+      mt[7] += 1.0;
     }
   }
   if (tid == 0) {

@@ -9,6 +9,7 @@
 enum { RP_MODE_STEP = 0, RP_MODE_RESET = 1, RP_MODE_PHYSICS = 2 };
 enum { RP_STEP_FIRST_ = 0, RP_STEP_MID_ = 1, RP_STEP_LAST_ = 2 };
 #define RP_GOAL_DIM_ 89
+#define RP_METRICS_STRIDE 16
 
 // debug dump layout (doubles per env), filled for substep 0 when RpKernelArgs::dbg != nullptr
 #define RP_DBG_QACC_SMOOTH 0
@@ -42,6 +43,7 @@ struct RpKernelArgs {
   double* act_force;         // [N][nu]
   double* site_xpos;         // [N][10][3]
   uint8_t* activation;       // [N][88]
+  double* metrics;           // [N][RP_METRICS_STRIDE]
   double* dbg;
 };
 

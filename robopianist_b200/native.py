@@ -21,7 +21,7 @@ EXPORTS = [
     "rp_last_error", "rp_version", "rp_model_create", "rp_model_destroy", "rp_obs_dim", "rp_action_dim",
     "rp_reward_terms", "rp_batch_create", "rp_batch_destroy", "rp_set_option", "rp_reset", "rp_step",
     "rp_step_host", "rp_physics_step", "rp_get_state", "rp_set_state", "rp_get_diag", "rp_get_aux",
-    "rp_launch_count", "rp_step_staged", "rp_host_buffers",
+    "rp_launch_count", "rp_step_staged", "rp_host_buffers", "rp_get_metrics",
 ]
 
 
@@ -58,6 +58,7 @@ def lib():
         L.rp_get_aux.argtypes = [vp, dp, dp, u8]
         L.rp_step_staged.argtypes = [vp]
         L.rp_host_buffers.argtypes = [vp, C.POINTER(dp), C.POINTER(dp)]
+        L.rp_get_metrics.argtypes = [vp, dp]
         L.rp_launch_count.restype = C.c_int64
         L.rp_launch_count.argtypes = [vp]
         L.rp_debug_enable.argtypes = [vp, C.c_int]
@@ -182,6 +183,17 @@ class Batch:
         f = np.empty((N, self.model.nu)); s = np.empty((N, 10, 3)); act = np.empty((N, 88), np.uint8)
         _check(lib().rp_get_aux(self.ptr, _dp(f), _dp(s), act.ctypes.data_as(C.POINTER(C.c_uint8))))
         return dict(actuator_force=f, site_xpos=s, activation=act)
+
+    def get_metrics(self):
+        """Per-env musical metrics (rp_get_metrics): dict of [N] arrays for the last completed episode,
+        plus the running sums of the current one."""
+        out = np.empty((self.nenv, 16))
+        _check(lib().rp_get_metrics(self.ptr, _dp(out)))
+        names = ("precision", "recall", "f1", "sustain_precision", "sustain_recall", "sustain_f1")
+        d = {n: out[:, 8 + i].copy() for i, n in enumerate(names)}
+        d["episodes"] = out[:, 7].astype(np.int64)
+        d["running_sums"], d["running_steps"] = out[:, :6].copy(), out[:, 6].astype(np.int64)
+        return d
 
     @property
     def launches(self):

@@ -220,6 +220,17 @@ class BatchedPianoEnv:
         """Host buffers in and out (pinned staging + copies inside the library): the e2e call."""
         return self.batch.step_host(actions)
 
+    def get_musical_metrics(self):
+        """Mean precision / recall / F1 (keys and sustain) over the envs that completed an episode:
+        the batched form of MidiEvaluationWrapper.get_musical_metrics (wrappers/evaluation.py:95-110,
+        deque_size=1), accumulated inside the step kernel."""
+        m = self.batch.get_metrics()
+        done = m["episodes"] > 0
+        if not done.any():
+            raise ValueError("No episode metrics available yet.")
+        return {k: float(m[k][done].mean()) for k in
+                ("precision", "recall", "f1", "sustain_precision", "sustain_recall", "sustain_f1")}
+
     def get_state(self):
         return self.batch.get_state()
 
@@ -307,6 +318,9 @@ class PianoEnv:
         if step_type == StepType.LAST:
             self._reset_next = True
         return TimeStep(step_type, float(rew[0]), float(dis[0]), self._obs_dict(obs[0]))
+
+    def get_musical_metrics(self):
+        return self._batched.get_musical_metrics()
 
     def close(self):
         self._batched.close()

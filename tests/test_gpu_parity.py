@@ -137,3 +137,136 @@ def test_e2e_host_call_and_launch_count():
     assert batch.launches == n0 + 1 and obs.shape == (64, 329) and np.isfinite(rew).all() and (st == 1).all()
     assert np.allclose(terms.sum(axis=1), rew)
     batch.close()
+
+
+def test_golden_oracle_fixture_through_cabi():
+    """CUDA path vs the committed oracle trajectory (tests/golden/oracle_twinkle_traj.npz; generator
+    scripts/gen_oracle_golden.py): no oracle code runs here."""
+    gold = np.load(helpers.GOLDEN / "oracle_twinkle_traj.npz")
+    fm, model, batch = helpers.make_native("piano_with_shadow_hands", nenv=1)
+    nv = fm.meta["nv"]
+    acts = helpers.twinkle_actions()
+    batch.set_state(np.zeros((1, nv)), np.zeros((1, nv)), np.zeros((1, nv)))
+    for t in range(60):
+        batch.physics_step(_dev(acts[t:t + 1, :44]).data_ptr(), 10)
+        if t in (9, 29, 59):
+            q, _, _, _ = batch.get_state()
+            assert np.abs(q[0] - gold[f"qpos_{t}"]).max() < 1e-9, t
+    batch.close()
+
+
+def test_heterogeneous_envs_match_their_own_oracles():
+    """Every env of a batch gets different (seeded) action noise; each is compared with its own oracle
+    instance: exercises per-env contact sets, iteration counts and early exits inside one launch."""
+    E, steps = 6, 25
+    fm, model, batch = helpers.make_native("piano_with_shadow_hands", nenv=E)
+    om = O.OracleModel(fm); om.set_option(maxcon=24)
+    ods = [O.OracleData(om) for _ in range(E)]
+    nv = fm.meta["nv"]
+    acts = helpers.twinkle_actions()
+    lo, hi = fm.actuator_ctrlrange[:, 0], fm.actuator_ctrlrange[:, 1]
+    rng = np.random.default_rng(12345)
+    batch.set_state(np.zeros((E, nv)), np.zeros((E, nv)), np.zeros((E, nv)))
+    for od in ods:
+        od.reset()
+    niters = set()
+    for t in range(steps):
+        ctrl = np.clip(acts[t, :44] + rng.normal(0, 0.05, (E, 44)) * (hi - lo) / 2, lo, hi)
+        ctrl[0] = acts[t, :44]
+        batch.physics_step(_dev(ctrl).data_ptr(), 10)
+        q, v, _, _ = batch.get_state()
+        dg = batch.get_diag()
+        for e, od in enumerate(ods):
+            od.control_step(ctrl[e])
+            assert np.abs(q[e] - od.qpos).max() < 1e-9, (t, e)
+            # (od.ncon after control_step belongs to the post-integration mj_step1, not to the last solve)
+            assert dg["niter"][e] == od.solver_niter, (t, e)
+            niters.add(int(od.solver_niter))
+    assert len(niters) > 3  # the envs really ran different sweep counts
+    batch.close()
+
+
+def test_key_shared_by_both_hands_matches_oracle():
+    """Left hand shifted over the right hand's keys (forearm_tx + 0.22): from control step 23 on key 58
+    carries contacts of both hands, which couples the two per-hand Gauss-Seidel streams (the kernel's
+    shared_key path: rows stepped in global order with a block barrier per row)."""
+    fm, model, batch = helpers.make_native("piano_with_shadow_hands", nenv=2)
+    om = O.OracleModel(fm); om.set_option(maxcon=24)
+    od = O.OracleData(om); od.reset()
+    nv = fm.meta["nv"]
+    gh = fm.arrays["geom_hand"]
+    acts = helpers.twinkle_actions()
+    batch.set_state(np.zeros((2, nv)), np.zeros((2, nv)), np.zeros((2, nv)))
+    shared_substeps = 0
+    for t in range(36):
+        ctrl = acts[t, :44].copy()
+        ctrl[42] += 0.22
+        ct = _dev(np.tile(ctrl, (2, 1)))
+        for s in range(10):
+            batch.physics_step(ct.data_ptr(), 1)
+            od.mj_step(ctrl)
+            keys = {}
+            for c in od.contacts():
+                if c["key"] >= 0:
+                    keys.setdefault(c["key"], set()).add(int(gh[c["geom1"]]))
+            shared_substeps += any(len(v) > 1 for v in keys.values())
+        q, v, _, _ = batch.get_state()
+        dg = batch.get_diag()
+        assert np.abs(q[0] - od.qpos).max() < 1e-9 and (q[0] == q[1]).all(), t
+        assert dg["ncon"][0] == od.ncon and dg["niter"][0] == od.solver_niter and dg["flags"][0] == 0, t
+    assert shared_substeps > 50
+    batch.close()
+
+
+@pytest.mark.parametrize("iterations", [10, 20, 100])
+def test_pgs_iteration_cap_sweep(iterations):
+    """BASELINE config 5 in miniature: the iteration cap is honoured identically on both sides."""
+    fm, model, batch = helpers.make_native("piano_with_shadow_hands", nenv=1)
+    batch.set_option(iterations=iterations)
+    om = O.OracleModel(fm); om.set_option(iterations=iterations, maxcon=24)
+    od = O.OracleData(om); od.reset()
+    nv = fm.meta["nv"]
+    acts = helpers.twinkle_actions()
+    batch.set_state(np.zeros((1, nv)), np.zeros((1, nv)), np.zeros((1, nv)))
+    capped = 0
+    for t in range(30):
+        batch.physics_step(_dev(acts[t:t + 1, :44]).data_ptr(), 10)
+        od.control_step(acts[t, :44])
+        q, _, _, _ = batch.get_state()
+        dg = batch.get_diag()
+        assert np.abs(q[0] - od.qpos).max() < 1e-9, t
+        assert dg["niter"][0] == od.solver_niter <= iterations
+        capped += od.solver_niter == iterations
+    assert iterations == 100 or capped > 0
+    batch.close()
+
+
+def test_musical_metrics_match_the_wrapper_logic():
+    """Device-side precision / recall / F1 (rp_get_metrics) vs the restated MidiEvaluationWrapper
+    (oracle/task_ref.py, pinned to sklearn in tests/test_oracle.py) over one whole episode."""
+    song = "TwinkleTwinkleRousseau"
+    fm, model, batch = helpers.make_native("piano_with_shadow_hands", song=song, nenv=2)
+    goal, fing = helpers.song_tables(song)
+    ref = task_ref.RefEnv(fm, goal, fing, n_steps_lookahead=1)
+    N = 2
+    obs = torch.empty((N, model.obs_dim), dtype=torch.float64, device="cuda")
+    rew = torch.empty(N, dtype=torch.float64, device="cuda"); dis = torch.empty_like(rew)
+    st = torch.empty(N, dtype=torch.uint8, device="cuda")
+    batch.reset(None, obs.data_ptr()); ref.reset()
+    acts = helpers.twinkle_actions()
+    for t in range(goal.shape[0]):
+        a = acts[t % 158]
+        batch.step(_dev(np.tile(a, (N, 1))).data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
+        rst, _, _, _ = ref.step(a)
+    torch.cuda.synchronize()
+    assert rst == task_ref.LAST and int(st[0]) == task_ref.LAST
+    m = batch.get_metrics()
+    assert (m["episodes"] == 1).all() and (m["running_steps"] == goal.shape[0]).all()
+    for k, v in ref.musical_metrics.items():
+        assert abs(m[k][0] - v) < 1e-12 and m[k][0] == m[k][1], (k, m[k], v)
+    assert 0.3 < m["recall"][0] <= 1.0   # the recorded policy really presses goal keys
+    # the next step auto-resets: running sums restart, the last episode's means stay
+    batch.step(_dev(np.tile(acts[0], (N, 1))).data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
+    m2 = batch.get_metrics()
+    assert (m2["running_steps"] == 0).all() and m2["f1"][0] == m["f1"][0]
+    batch.close()

@@ -112,3 +112,17 @@ def test_golden_trajectory_regression(hands):
         d.control_step(acts[t, :44])
         if t in (9, 29, 59):
             assert np.abs(d.qpos - gold[f"qpos_{t}"]).max() < 1e-9
+
+
+def test_prf_binary_matches_sklearn():
+    """The restated per-step metric of MidiEvaluationWrapper (wrappers/evaluation.py:140-147) against
+    sklearn itself, including every zero-division corner."""
+    from sklearn.metrics import precision_recall_fscore_support
+    rng = np.random.default_rng(0)
+    cases = [(np.zeros(88), np.zeros(88)), (np.zeros(88), np.ones(88)), (np.ones(88), np.zeros(88)), ([1.0], [0.0]), ([0.0], [0.0])]
+    for _ in range(50):
+        p = rng.choice([0.02, 0.1, 0.5])
+        cases.append(((rng.random(88) < p).astype(float), (rng.random(88) < p).astype(float)))
+    for y_true, y_pred in cases:
+        ref = precision_recall_fscore_support(y_true=np.asarray(y_true), y_pred=np.asarray(y_pred), average="binary", zero_division=1)[:3]
+        assert np.allclose(task_ref.prf_binary(y_true, y_pred), ref, atol=1e-15), (y_true, y_pred)
