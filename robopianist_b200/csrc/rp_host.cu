@@ -36,7 +36,8 @@ struct rp_batch {
   uint8_t* d_goal;
   int8_t* d_fingering;
   double *qpos, *qvel, *qacc_ws, *ctrl, *sustain, *act_force, *site_xpos, *dbg;
-  int32_t *t_idx, *step_type_state, *diag;
+  int32_t *t_idx, *step_type_state, *diag, *work, *order;
+  int order_valid;  // order[] holds a permutation (set after the first full step)
   uint8_t* activation;
   double* metrics;  // [N][RP_METRICS_STRIDE] musical metrics accumulators (see rp_get_metrics)
   // staging for rp_step_host
@@ -336,6 +337,7 @@ extern "C" rp_batch* rp_batch_create(const rp_model* model, int nenv, int device
   chk(dalloc(&b->site_xpos, N * 30)); chk(dalloc(&b->t_idx, N)); chk(dalloc(&b->step_type_state, N));
   chk(dalloc(&b->diag, N * 3)); chk(dalloc(&b->activation, N * RP_NK));
   chk(dalloc(&b->metrics, N * RP_METRICS_STRIDE));
+  chk(dalloc(&b->work, N)); chk(dalloc(&b->order, N));
   size_t out_doubles = N * (model->obs_dim + 2 + 5) + (N + 7) / 8 + 8;
   chk(cudaMallocHost((void**)&b->h_action, sizeof(double) * N * model->act_dim));
   chk(cudaMallocHost((void**)&b->h_out, sizeof(double) * out_doubles));
@@ -354,7 +356,7 @@ extern "C" int rp_batch_destroy(rp_batch* b) {
   cudaFree(b->d_dm); cudaFree(b->d_goal); cudaFree(b->d_fingering);
   cudaFree(b->qpos); cudaFree(b->qvel); cudaFree(b->qacc_ws); cudaFree(b->ctrl); cudaFree(b->sustain);
   cudaFree(b->act_force); cudaFree(b->site_xpos); cudaFree(b->t_idx); cudaFree(b->step_type_state);
-  cudaFree(b->diag); cudaFree(b->activation); cudaFree(b->metrics); cudaFree(b->dbg); cudaFree(b->d_action); cudaFree(b->d_out);
+  cudaFree(b->diag); cudaFree(b->activation); cudaFree(b->metrics); cudaFree(b->work); cudaFree(b->order); cudaFree(b->dbg); cudaFree(b->d_action); cudaFree(b->d_out);
   cudaFreeHost(b->h_action); cudaFreeHost(b->h_out);
   delete b;
   return 0;
@@ -374,6 +376,7 @@ static RpKernelArgs base_args(rp_batch* b, int mode) {
   a.t_idx = b->t_idx; a.step_type_state = b->step_type_state; a.sustain = b->sustain;
   a.goal = b->d_goal; a.fingering = b->d_fingering;
   a.diag = b->diag; a.act_force = b->act_force; a.site_xpos = b->site_xpos; a.activation = b->activation; a.metrics = b->metrics;
+  a.work = b->work; a.order = b->order_valid ? b->order : nullptr;
   a.dbg = b->dbg;
   return a;
 }
@@ -396,7 +399,14 @@ extern "C" int rp_step(rp_batch* b, const double* action_dev, double* obs_dev, d
   RpKernelArgs a = base_args(b, RP_MODE_STEP);
   a.action = action_dev; a.obs = obs_dev; a.reward = reward_dev; a.discount = discount_dev;
   a.step_type = step_type_dev; a.reward_terms = reward_terms_dev;
-  return launch(b, a);
+  if (launch(b, a)) return 1;
+  // more environments than resident slots: sort the next launch longest-expected-first
+  if (b->nenv >= 2048 && b->model->nhand > 0) {
+    CUDA_OK(rp_launch_order(b->work, b->order, b->nenv, b->stream));
+    b->order_valid = 1;
+    b->launches++;
+  }
+  return 0;
 }
 
 // Staged form of the host call: actions are written by the caller into the pinned input buffer and

@@ -34,13 +34,31 @@
 #ifndef RP_CH_UNROLL
 #define RP_CH_UNROLL 1
 #endif
+#ifndef RP_EULER_FACTOR
+#define RP_EULER_FACTOR 0  // tree-sparse L^T D L solve for the Euler step: 1.5k instead of 4.3k instructions but serial; measured 23.4 vs 23.0 ms/step
+#endif
+#ifndef RP_SWIZZLE
+#define RP_SWIZZLE 0  // measured: no effect (23.0 vs 23.0 ms/step)
+#endif
+#ifndef RP_FR_DEFER
+#define RP_FR_DEFER 0
+#endif
+#ifndef RP_FR_ICLAMP
+#define RP_FR_ICLAMP 0
+#endif
+#ifndef RP_FR_CHAIN
+#define RP_FR_CHAIN 0
+#endif
+#ifndef RP_SW_UNROLL
+#define RP_SW_UNROLL 2
+#endif
 #ifndef RP_MINBLOCKS
 #define RP_MINBLOCKS 6
 #endif
 
 namespace {
 
-constexpr int kFrUnroll = RP_FR_UNROLL, kChUnroll = RP_CH_UNROLL;
+constexpr int kFrUnroll = RP_FR_UNROLL, kChUnroll = RP_CH_UNROLL, kSwUnroll = RP_SW_UNROLL;
 
 struct Contact {  // lives in shared memory
   double Jc[3][MAXD];  // hand-chain Jacobian entries by depth (already signed: body2 - body1)
@@ -78,6 +96,7 @@ struct Smem {
   CKey ck[MAXCON];                    // limit rows of keys that also carry contacts
   signed char anc[RP_NHMAX][NL][MAXD];  // ancestor-or-self at depth d
   signed char dep[RP_NHMAX][32], sub[RP_NHMAX][32];  // link depth / subtree size
+  unsigned char moff[RP_NHMAX][32];   // offset of link k's packed mass-matrix row in Mrow
   signed char keyslot[NK];            // index into ck[] (-1: key not in contact)
   signed char hlist[RP_NHMAX][MAXCON];  // contacts of hand h, in sorted order
   signed char ckown[MAXCON];          // hand that sweeps the key row ck[i]
@@ -150,7 +169,7 @@ __device__ __noinline__ void sweep_inverse(double* A, const signed char* anc /*[
         const int i = anc[k * MAXD + d];
         myrow[i] -= rowk[i] * t;
       }
-#pragma unroll 2
+#pragma unroll kSwUnroll
       for (int i = k + 1; i < endk; i++) myrow[i] -= rowk[i] * t;
     }
     __syncwarp();
@@ -158,6 +177,61 @@ __device__ __noinline__ void sweep_inverse(double* A, const signed char* anc /*[
     if (lane == k) A[k * RS + k] = -dinv;
     __syncwarp();
   }
+}
+
+// Solves (M + h*D) x = rhs for one hand with the tree-sparse L^T D L factorisation (the scheme of
+// MuJoCo's mj_factorI / mj_solveLD), in place on the packed rows R[moff[k] + d] = M[k][anc(k, d)],
+// d = 0..dep[k] (d == dep[k]: the diagonal, already including h*damping).  Lane == dof; `xin` is the
+// lane's right-hand side, the return value its solution.  xs: 32 doubles of shared scratch.
+// About 1.5k instructions instead of the 4.3k of a second dense sweep + matrix-vector product.
+__device__ __noinline__ double factor_solve(double* R, const unsigned char* moff, const signed char* anc /*[NL][MAXD]*/,
+                                            const signed char* dep, const signed char* sub, double* xs, double xin, int lane) {
+  const bool hl = lane < NL;
+  const int mydep = hl ? dep[lane] : 0, myoff = hl ? moff[lane] : 0, mysub = hl ? sub[lane] : 0;
+  double* ri = R + myoff;
+  // ---- factorisation, leaves first: for every proper ancestor i of k, L[k][i] = M[k][i] / D[k] and
+  // row i -= L[k][i] * row k (restricted to the ancestors-or-self of i)
+#pragma unroll 1
+  for (int k = NL - 1; k >= 1; k--) {
+    const int depk = dep[k];
+    if (depk == 0) continue;  // a root has nothing above it (warp-uniform)
+    const double* rk = R + moff[k];
+    const bool isanc = hl && lane < k && k < lane + mysub;
+    double t = 0;
+    if (isanc) {
+      t = rk[mydep] / rk[depk];
+      for (int d = 0; d <= mydep; d++) ri[d] -= rk[d] * t;
+    }
+    __syncwarp();
+    if (isanc) R[moff[k] + mydep] = t;
+    __syncwarp();
+  }
+  // ---- x <- L^-T x: descending k, every ancestor i of k takes x[i] -= L[k][i] * x[k]
+  double x = xin;
+#pragma unroll 1
+  for (int k = NL - 1; k >= 1; k--) {
+    if (dep[k] == 0) continue;
+    const double xk = __shfl_sync(FULL, x, k);
+    const bool isanc = hl && lane < k && k < lane + mysub;
+    if (isanc) x -= R[moff[k] + mydep] * xk;
+  }
+  // ---- x <- D^-1 x
+  if (hl) x /= ri[mydep];
+  // ---- x <- L^-1 x: by depth level, x[k] -= sum over ancestors i of L[k][i] * x[i] (all final by then)
+  const int maxd = __reduce_max_sync(FULL, hl ? mydep : 0);
+  xs[lane] = x;
+  __syncwarp();
+#pragma unroll 1
+  for (int lvl = 1; lvl <= maxd; lvl++) {
+    if (hl && mydep == lvl) {
+      double acc = x;
+      for (int d = 0; d < lvl; d++) acc -= ri[d] * xs[anc[lane * MAXD + d]];
+      x = acc;
+      xs[lane] = acc;
+    }
+    __syncwarp();
+  }
+  return x;
 }
 
 }  // namespace
@@ -175,9 +249,16 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
   const int tid = threadIdx.x;
   int lane;
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // opaque: keeps the compiler from re-reading S2R in loops
-  const int h = HANDS ? (tid >> 5) : 0;  // warp == hand
-  const int env = blockIdx.x;
-  if (env >= a.nenv) return;
+  // warp <-> hand; swizzled by block parity so that the warps of the (usually busier) right hand do not
+  // all land on the same two warp schedulers of an SM
+#if RP_SWIZZLE
+  const int h = HANDS ? ((tid >> 5) ^ (blockIdx.x & 1)) : 0;
+#else
+  const int h = HANDS ? (tid >> 5) : 0;
+#endif
+  if ((int)blockIdx.x >= a.nenv) return;
+  // longest-expected-first launch order (rp_order_kernel) shortens the tail of the last wave
+  const int env = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
   const int nvtot = NK + (HANDS ? 2 * NL : 0);
   const int nu = dm->nu;
   double* __restrict__ gq = a.qpos + (size_t)env * nvtot;
@@ -245,6 +326,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
     moff = incl - v;
+    sm.moff[h][lane] = (unsigned char)moff;
     if (__shfl_sync(FULL, incl, 31) > 160) flags_init_overflow = 1;
   }
   // topology tables into shared memory (read in the inner loops of the sweep / contact rows)
@@ -261,9 +343,16 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
 #pragma unroll
   for (int s = 0; s < KS; s++) key_actforce[s] = 0;
   int niter_last = 0, ncon_last = 0, flags = flags_init_overflow ? 4 : 0;
+  int work = 0;  // sum over substeps of sweeps x (1 + contacts): predictor of the next step's duration
   const int maxiter = a.iterations > 0 ? a.iterations : dm->iterations;
   const double tol = a.tolerance >= 0 ? a.tolerance : dm->tol;
 
+#ifdef RP_PROFILE
+  long long tacc[16] = {0}, tlast = clock64();
+#define TICK(i) { const long long tn = clock64(); tacc[i] += tn - tlast; tlast = tn; }
+#else
+#define TICK(i)
+#endif
   // link world pose (kept for the task epilogue)
   double xp[3] = {0, 0, 0}, xq[4] = {1, 0, 0, 0};
   block_sync<NW>();
@@ -326,6 +415,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     }
     if (last_pass) break;
 
+    TICK(0)
     // ------------------------------------------------------------------ publish S, velocities
     double Sown[6] = {0, 0, 0, 0, 0, 0};
     if (hl) {
@@ -422,6 +512,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         double* dbg = a.dbg + (size_t)env * RP_DBG_STRIDE;
         for (int i = 0; i < NL; i++) if (hl) dbg[RP_DBG_M + i * NL + lane] = Aw[i * RS + lane];
       }
+    TICK(1)
       // ---------------------------------------------------------------- invert M (symmetric sweep): A = -M^-1
       sweep_inverse(Aw, &sm.anc[h][0][0], sm.dep[h], sm.sub[h], lane);
       if (a.dbg && sub == 0 && h == 0) {
@@ -431,6 +522,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     }
     const double* Ah = sm.A[h];
 
+    TICK(2)
     // ------------------------------------------------------------------ actuation (lane = actuator)
     if (HANDS) {
       const bool isact = lane < dm->nact[h];
@@ -549,9 +641,11 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     }
     const unsigned lm_mask = HANDS ? __ballot_sync(FULL, lm_on) : 0u;
 
+    TICK(3)
     // ------------------------------------------------------------------ collision (lane = geom of this warp's hand)
     if (tid == 0) { sm.nraw = 0; sm.ncon = 0; sm.overflow = 0; sm.nck = 0; sm.shared_key = 0; sm.nhc[0] = 0; sm.nhc[H1] = 0; }
     block_sync<NW>();  // key arrays published; acc scratch of both hands dead (it aliases the contact lists)
+    TICK(4)
     if (HANDS) {
       const bool isg = lane < dm->ngeom[h];
       const int gl = isg ? dm->geom_link[h][lane] : 0;
@@ -664,12 +758,14 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         }
       }
     }
+    TICK(5)
     // publish what the contact rows read from the other warp: qacc_smooth / qacc_warmstart of the hand
     // dofs (wbuf / wsb) and of the keys (vak / kfc; kfc is free until the end of the sweep)
     if (hl) { sm.wbuf[h][lane] = qacc_smooth; sm.wsb[h][lane] = wh; }
 #pragma unroll
     for (int s = 0; s < KS; s++) { const int k = tid + KT * s; if (k < NK) { sm.vak[k] = ks_qacc[s]; sm.kfc[k] = wk[s]; } }
     block_sync<NW>();
+    TICK(4)
     const int nraw = min(sm.nraw, MAXCON);
     if (sm.nraw > MAXCON) flags |= 1;
     // NOTE: on overflow the kept subset depends on atomic order; the flag marks the env invalid.
@@ -814,6 +910,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         if (lane == 0) { sm.nck = __popc(fmask); sm.shared_key = smask != 0; sm.nhc[0] = __popc(h0mask); sm.nhc[H1] = __popc(h1mask); }
       }
     }
+    TICK(6)
     // =============================================================== warm start
     // forces from qacc_warmstart through the primal map; kept only if the dual cost is negative
     if (hl && fr_on) {
@@ -832,6 +929,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
       }
     }
     block_sync<NW>();
+    TICK(4)
     const int nck = sm.nck;
     const int shared_key = sm.shared_key;
     const int nmine = HANDS ? sm.nhc[h] : 0;
@@ -921,6 +1019,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     }
     block_sync<NW>();
 
+    TICK(7)
     // =============================================================== PGS
     // Row order inside a sweep follows MuJoCo: friction-loss dofs, joint limits (keys, then hand
     // joints), contacts.  The two hands are independent islands unless they touch the same key, so
@@ -937,19 +1036,67 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
           // ---- friction-loss rows, dof order: every lane evaluates the candidate update of its own
           // row; lane i commits at step i and broadcasts the force change
           const double fbase = fr_b + fr_R * fr_f;  // f only changes at the lane's own commit
+          const double fr_lo = -fr_hi;
+          const double* prow = Ah + lc;
+#if RP_FR_CHAIN
+          // short dependency chain: the force change is clamped directly, dl = clamp(-(fbase + va) / AR,
+          // lo - f, hi - f), so a row costs FMA -> compare/select -> shuffle -> FMA on the critical path
+          const double fq = -(fbase * fr_ARi), dlo = fr_lo - fr_f, dhi = fr_hi - fr_f;
 #pragma unroll kFrUnroll
-          for (int i = 0; i < NL; i++) {
-            const double mrow = Ah[i * RS + lc];
+          for (int i = 0; i < NL; i++, prow += RS) {
+            const double mrow = *prow;
+            const double d = fma(-va, fr_ARi, fq);
+            const bool plo = d < dlo, phi = d > dhi;
+            double dl = plo ? dlo : d;
+            dl = phi ? dhi : dl;
+            const double dbc = shfl(dl, i);
+            const double res = fbase + va;
+            va -= mrow * dbc;
+            if (lane == i) {
+              improvement -= dl * (0.5 * dl * fr_AR + res);
+              fr_f = phi ? fr_hi : (plo ? fr_lo : fr_f + dl);
+            }
+          }
+#elif RP_FR_DEFER
+          // the owner lane only records (dl, res) at its commit; the cost change is evaluated once after
+          // the sweep, which keeps three fp64 instructions per row off the 16-lane fp64 pipe
+          double dl_own = 0, res_own = 0;
+#pragma unroll kFrUnroll
+          for (int i = 0; i < NL; i++, prow += RS) {
+            const double mrow = *prow;
             const double res = fbase + va;
             const double x = fr_f - res * fr_ARi;
-            double fx = x < -fr_hi ? -fr_hi : x;
+#if RP_FR_ICLAMP
+            // |x| > hi on the integer pipe (non-negative doubles order like their bit patterns)
+            const unsigned long long xb = (unsigned long long)__double_as_longlong(x);
+            const bool big = (xb & 0x7fffffffffffffffull) > (unsigned long long)__double_as_longlong(fr_hi);
+            const double fx = big ? __longlong_as_double((long long)((xb & 0x8000000000000000ull) | (unsigned long long)__double_as_longlong(fr_hi))) : x;
+#else
+            double fx = x < fr_lo ? fr_lo : x;
+            fx = x > fr_hi ? fr_hi : fx;
+#endif
+            const double dl = fx - fr_f;
+            const double dbc = shfl(dl, i);
+            va -= mrow * dbc;
+            if (lane == i) { dl_own = dl; res_own = res; fr_f = fx; }
+          }
+          improvement -= dl_own * (0.5 * dl_own * fr_AR + res_own);
+#else
+#pragma unroll kFrUnroll
+          for (int i = 0; i < NL; i++, prow += RS) {
+            const double mrow = *prow;
+            const double res = fbase + va;
+            const double x = fr_f - res * fr_ARi;
+            double fx = x < fr_lo ? fr_lo : x;
             fx = x > fr_hi ? fr_hi : fx;
             const double dl = fx - fr_f;
             const double dbc = shfl(dl, i);
             va -= mrow * dbc;
             if (lane == i) { improvement -= dl * (0.5 * dl * fr_AR + res); fr_f = fx; }
           }
+#endif
         }
+    TICK(8)
         // ---- limit rows of keys that carry contacts (values in shared memory)
         for (int c = 0; c < nck; c++) {
           const bool mine = (!HANDS || shared_key) ? (h == 0) : (sm.ckown[c] == h);
@@ -981,6 +1128,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
             va -= Ah[i * RS + lc] * dbc;
             if (lane == i) { improvement -= dl * (0.5 * dl * lm_AR + res); lm_f = fn; }
           }
+    TICK(9)
           // ---- contacts of this hand, sorted order
           const int ntrip = shared_key ? ncon : nmine;
           for (int ci = 0; ci < ntrip; ci++) {
@@ -1031,10 +1179,12 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
             if (shared_key) block_sync<NW>();
           }
         }
+    TICK(10)
         improvement = warp_sum(improvement);
         if (HANDS) {
           if (lane == 0) sm.red[iter & 1][h][1] = improvement;
           block_sync<NW>();
+          TICK(11)
           improvement = sm.red[iter & 1][0][1] + sm.red[iter & 1][H1][1];
         }
         improvement *= dm->solver_scale;
@@ -1043,7 +1193,9 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
       }
     }
     niter_last = iter;
+    work += iter * (1 + ncon);
 
+    TICK(12)
     // =============================================================== dual -> primal, Euler
     // qacc = qacc_smooth + va ; qfrc_constraint = J^T f
     const double qacc = qacc_smooth + va;
@@ -1099,9 +1251,16 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         o[13] = cn.aref[0]; o[14] = cn.mu; o[15] = cn.Jk[0];
       }
     }
+    TICK(13)
     // Euler with implicit joint damping: (M + h*D) a = qfrc_smooth + qfrc_constraint
     double aeul = 0;
     if (HANDS) {
+#if RP_EULER_FACTOR
+      __syncwarp();
+      if (hl) sm.Mrow[h][moff + ldep] += hstep * dm->link_damping[h][lane];  // the diagonal of this link's packed row
+      __syncwarp();
+      aeul = factor_solve(sm.Mrow[h], sm.moff[h], &sm.anc[h][0][0], sm.dep[h], sm.sub[h], sm.wbuf[h], qfrc_smooth + qfrc_c, lane);
+#else
       double* Aw = sm.A[h];
       __syncwarp();
       for (int idx = lane; idx < NL * RS; idx += 32) Aw[idx] = 0;
@@ -1124,6 +1283,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         for (int i = 0; i < NL; i++) acc -= Aw[lane * RS + i] * sm.wbuf[h][i];
         aeul = acc;
       }
+#endif
     }
     // integrate
     if (hl) {
@@ -1156,6 +1316,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     const int anybad = __syncthreads_or(bad ? 1 : 0);  // also publishes the key sin/cos of the final pass
     if (anybad) flags |= 2;
     if (tid == 0 && a.diag) { a.diag[3 * env + 0] = ncon_last; a.diag[3 * env + 1] = niter_last; a.diag[3 * env + 2] = flags; }
+    if (tid == 0 && a.work) a.work[env] = work;
     if (a.act_force) {
       if (HANDS && lane < dm->nact[h]) a.act_force[(size_t)env * nu + h * dm->nact[0] + lane] = actforce;
       if (dm->nkey_act) {
@@ -1164,6 +1325,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
       }
     }
   }
+#ifdef RP_PROFILE
+  TICK(15)
+  if (a.dbg && lane == 0) for (int i = 0; i < 16; i++) a.dbg[(size_t)env * RP_DBG_STRIDE + RP_DBG_PROFILE + h * 16 + i] = (double)tacc[i];
+#endif
   if (a.mode == RP_MODE_PHYSICS) return;
 
   // =============================================================================================
@@ -1374,6 +1539,29 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     if (a.step_type) a.step_type[env] = (uint8_t)step_type;
     if (a.reward_terms) for (int k = 0; k < 5; k++) a.reward_terms[(size_t)env * 5 + k] = first ? 0.0 : terms[k];
   }
+}
+
+// Launch order for the next step: environments sorted by decreasing work of the last step (bucket sort,
+// one block).  Durations vary 4x between environments (PGS sweeps x contacts); starting the long ones
+// first shortens the tail of the last wave.  Order inside a bucket is arbitrary (results do not depend
+// on which block runs which environment).
+__global__ void __launch_bounds__(1024) rp_order_kernel(const int32_t* __restrict__ work, int32_t* __restrict__ order, int n) {
+  __shared__ int hist[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[255 - min(255, work[i] >> 4)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int b = 0; b < 256; b++) { const int c = hist[b]; hist[b] = run; run += c; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) order[atomicAdd(&hist[255 - min(255, work[i] >> 4)], 1)] = i;
+}
+
+cudaError_t rp_launch_order(const int32_t* work, int32_t* order, int n, cudaStream_t stream) {
+  rp_order_kernel<<<1, 1024, 0, stream>>>(work, order, n);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -20,7 +20,8 @@ enum { RP_STEP_FIRST_ = 0, RP_STEP_MID_ = 1, RP_STEP_LAST_ = 2 };
 #define RP_DBG_CONTACTS 656   // 24 x 16
 #define RP_DBG_M 1040         // 26 x 26 (hand 0)
 #define RP_DBG_MINV 1716      // 26 x 26 (hand 0)
-#define RP_DBG_STRIDE 2400
+#define RP_DBG_PROFILE 2392      // 2 x 16 phase cycle counters (RP_PROFILE builds)
+#define RP_DBG_STRIDE 2432
 
 struct RpKernelArgs {
   const RpDevModel* dm;
@@ -44,8 +45,11 @@ struct RpKernelArgs {
   double* site_xpos;         // [N][10][3]
   uint8_t* activation;       // [N][88]
   double* metrics;           // [N][RP_METRICS_STRIDE]
+  int32_t* work;             // [N] work estimate of this step (out)
+  const int32_t* order;      // [N] block -> environment (optional)
   double* dbg;
 };
 
 size_t rp_kernel_smem_bytes();
 cudaError_t rp_launch_step(const RpKernelArgs& a, int nhand, cudaStream_t stream);
+cudaError_t rp_launch_order(const int32_t* work, int32_t* order, int n, cudaStream_t stream);

@@ -1,9 +1,11 @@
 #!/bin/bash
-# Times every library in robopianist_b200/variants/ with the bench workload (no CPU baseline) and the identical-action sweep.
+# Every library in robopianist_b200/variants/: parity tests (ROBOPLAY_LIB selects the build) + bench timing.
 OUT=gpurun_out/${1:-variants}; mkdir -p $OUT
+STEPS=${2:-20}
 for lib in robopianist_b200/variants/lib_*.so; do
   n=$(basename $lib .so)
-  ROBOPLAY_LIB=$PWD/$lib timeout 300 python bench.py --steps 12 --warmup 3 --no-cpu-baseline > $OUT/$n.json 2> $OUT/$n.err
+  ROBOPLAY_LIB=$PWD/$lib timeout 600 python -m pytest tests/test_gpu_parity.py -x -q > $OUT/$n.pytest 2>&1; echo "$n pytest: $(tail -1 $OUT/$n.pytest)"
+  ROBOPLAY_LIB=$PWD/$lib timeout 300 python bench.py --steps $STEPS --warmup 3 --no-cpu-baseline > $OUT/$n.json 2> $OUT/$n.err
   python - <<PY
 import json
 try:
