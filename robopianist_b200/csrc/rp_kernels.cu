@@ -100,6 +100,7 @@ struct Smem {
   signed char keyslot[NK];            // index into ck[] (-1: key not in contact)
   signed char hlist[RP_NHMAX][MAXCON];  // contacts of hand h, in sorted order
   signed char ckown[MAXCON];          // hand that sweeps the key row ck[i]
+  signed char perm[MAXCON];           // sorted position -> raw[] slot
   int nhc[RP_NHMAX];
   int nck, shared_key;                // shared_key: some key carries contacts of both hands
   union {
@@ -771,8 +772,128 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     // NOTE: on overflow the kept subset depends on atomic order; the flag marks the env invalid.
     const int ncon = nraw;
     ncon_last = ncon;
-    // ---- contact rows: warp 0, lane c builds contact c (rank-sorted into con[])
-    if (HANDS && h == 0 && ncon > 0) {
+    // ---- contact rows (rank-sorted into con[]).  Up to 21 contacts: one thread per (contact, frame row),
+    // spread over both warps, which cuts the serial length of this stage ~3x; more: one lane per contact.
+    if (HANDS && ncon > 0 && 3 * ncon <= KT) {
+      if (tid < nraw) {
+        const unsigned mykey = sm.u.raw[tid].sortkey;
+        int rank = 0;
+        for (int j = 0; j < nraw; j++) rank += (sm.u.raw[j].sortkey < mykey) ? 1 : 0;
+        sm.perm[rank] = (signed char)tid;
+      }
+      block_sync<NW>();
+      const bool rowt = tid < 3 * ncon;
+      const int c = rowt ? tid / 3 : 0, r = tid - 3 * c;
+      // contact geometry to registers: raw[] and con[] share the same shared memory
+      double c_dist = 0, c_pos[3] = {0, 0, 0}, c_frame[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      int ch = 0, c_geom = 0, c_key = -1;
+      if (rowt) {
+        const RawContact rc = sm.u.raw[sm.perm[c]];
+        c_dist = rc.dist;
+        for (int k = 0; k < 3; k++) { c_pos[k] = rc.pos[k]; c_frame[k] = rc.n[k]; }
+        const double nn = sqrt(rp::dot3(c_frame, c_frame));
+        for (int k = 0; k < 3; k++) c_frame[k] /= nn;
+        rp::make_frame(c_frame);
+        ch = rc.hand; c_geom = rc.geom; c_key = rc.key;
+      }
+      block_sync<NW>();
+      double u[MAXD], arefr = 0;
+      int link = 0, dep = 0;
+      if (rowt) {
+        Contact& cn = sm.u.con[c];
+        link = dm->geom_link[ch][c_geom];
+        dep = sm.dep[ch][link];
+        const double* dir = c_frame + 3 * r;
+        const double* Ac = sm.A[ch];
+        // Jacobian row: frame direction r, body2 (key) minus body1 (hand link)
+        double jrow[MAXD];
+#pragma unroll 1
+        for (int d = 0; d < MAXD; d++) {
+          double v = 0;
+          if (d <= dep) {
+            const double* S = sm.S[ch][sm.anc[ch][link][d]];
+            double wxp[3];
+            rp::cross3(wxp, S, c_pos);
+            v = -(dir[0] * (S[3] + wxp[0]) + dir[1] * (S[4] + wxp[1]) + dir[2] * (S[5] + wxp[2]));
+          }
+          jrow[d] = v;
+          cn.Jc[r][d] = v;
+        }
+        double jk = 0;
+        if (c_key >= 0) {
+          double ax[3] = {dm->key_axis[c_key][0], dm->key_axis[c_key][1], dm->key_axis[c_key][2]};
+          double an[3] = {dm->key_pos[c_key][0] + dm->key_jpos[c_key][0], dm->key_pos[c_key][1] + dm->key_jpos[c_key][1],
+                          dm->key_pos[c_key][2] + dm->key_jpos[c_key][2]};
+          double lin[3], wxp[3];
+          rp::cross3(lin, an, ax);  // S_lin = anchor x axis
+          rp::cross3(wxp, ax, c_pos);
+          jk = dir[0] * (lin[0] + wxp[0]) + dir[1] * (lin[1] + wxp[1]) + dir[2] * (lin[2] + wxp[2]);
+        }
+        cn.Jk[r] = jk;
+        // mixed parameters, impedance / regularisation (evaluated by each of the three row threads)
+        const RpGeomParams& g1 = dm->geom_gp[ch][c_geom];
+        const RpGeomParams& g2 = c_key < 0 ? dm->base_gp : dm->key_gp[c_key];
+        double solref[2], solimp[5], mu;
+        rp::mix_params(g1.solref, g1.solimp, g1.friction, g1.solmix, g1.priority, g2.solref, g2.solimp, g2.friction,
+                       g2.solmix, g2.priority, solref, solimp, &mu);
+        const double margin = fmax(g1.margin, g2.margin), gap = fmax(g1.gap, g2.gap), incl = margin - gap;
+        const double imp = rp::impedance(solimp, c_dist, incl);
+        double K, B;
+        rp::ref_KB(solref, solimp[1], hstep, &K, &B);
+        const double diag = dm->link_body_invw[ch][link] + (c_key >= 0 ? dm->key_body_invw[c_key] : 0.0);
+        const double Rn = fmax(RP_MINVAL, (1 - imp) * diag / imp);
+        cn.R[r] = r == 0 ? Rn : Rn / fmax(RP_MINVAL, dm->impratio);
+        // row velocity -> reference acceleration
+        double sv = 0;
+        for (int d = 0; d <= dep; d++) sv += jrow[d] * sm.vh[ch][sm.anc[ch][link][d]];
+        if (c_key >= 0) sv += jk * sm.vk[c_key];
+        arefr = r == 0 ? -B * sv - K * imp * (c_dist - incl) : -B * sv;
+        cn.aref[r] = arefr;
+        // u = Minv_chain Jc_r^T (kept in registers for the A block)
+#pragma unroll 1
+        for (int d = 0; d <= dep; d++) {
+          const int jd = sm.anc[ch][link][d];
+          double s2 = 0;
+          for (int e = 0; e <= dep; e++) s2 -= Ac[jd * RS + sm.anc[ch][link][e]] * jrow[e];
+          u[d] = s2;
+        }
+        if (r == 0) {
+          cn.hand = ch; cn.link = link; cn.key = c_key; cn.dep = dep; cn.mu = mu;
+          cn.invMk = c_key >= 0 ? 1.0 / dm->key_M[c_key] : 0.0;
+          for (int d = 0; d < 16; d++) cn.chain[d] = (signed char)(d <= dep ? sm.anc[ch][link][d] : 0);
+        }
+      }
+      block_sync<NW>();
+      if (rowt) {
+        Contact& cn = sm.u.con[c];
+        // A[s2][r] = Jc_s2 Minv Jc_r^T + Jk_s2 Jk_r / Mk + R (diagonal)
+        for (int s2 = 0; s2 < 3; s2++) {
+          double v = 0;
+          for (int d = 0; d <= dep; d++) v += cn.Jc[s2][d] * u[d];
+          v += cn.Jk[r] * cn.Jk[s2] * cn.invMk;
+          if (r == s2) v += cn.R[r];
+          cn.A[3 * s2 + r] = v;
+        }
+        // b = J qacc_smooth - aref; jar = J qacc_warmstart - aref (parked in f[] for the primal map)
+        double s2 = 0, s3 = 0;
+        for (int d = 0; d <= dep; d++) {
+          const int j = sm.anc[ch][link][d];
+          s2 += cn.Jc[r][d] * sm.wbuf[ch][j];
+          s3 += cn.Jc[r][d] * sm.wsb[ch][j];
+        }
+        if (c_key >= 0) { s2 += cn.Jk[r] * sm.vak[c_key]; s3 += cn.Jk[r] * sm.kfc[c_key]; }
+        cn.b[r] = s2 - arefr;
+        cn.f[r] = s3 - arefr;
+      }
+      block_sync<NW>();
+      if (rowt && r == 0) {
+        Contact& cn = sm.u.con[c];
+        double jar[3] = {cn.f[0], cn.f[1], cn.f[2]}, D[3] = {1.0 / cn.R[0], 1.0 / cn.R[1], 1.0 / cn.R[2]};
+        rp::elliptic_primal_force(jar, D, cn.mu, cn.f);
+      }
+      block_sync<NW>();
+    } else
+    if (HANDS && h == 0 && ncon > 0) {  // > 21 contacts: warp 0, lane c builds contact c
       int myrank = -1;
       if (lane < nraw) {
         const unsigned mykey = sm.u.raw[lane].sortkey;
@@ -889,6 +1010,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         rp::elliptic_primal_force(jar, D, cn.mu, cn.f);
       }
       __syncwarp();
+    }
+    if (HANDS && h == 0 && ncon > 0) {
       // coupled keys, per-hand contact lists, cross-hand key sharing (sorted order: same key => adjacent)
       {
         bool firstc = false, sharedc = false;
