@@ -46,11 +46,20 @@
 #ifndef RP_FR_ICLAMP
 #define RP_FR_ICLAMP 0
 #endif
+#ifndef RP_FR_ABS
+#define RP_FR_ABS 0
+#endif
 #ifndef RP_FR_CHAIN
 #define RP_FR_CHAIN 0
 #endif
 #ifndef RP_SW_UNROLL
 #define RP_SW_UNROLL 2
+#endif
+#ifndef RP_CH_ACC2
+#define RP_CH_ACC2 0
+#endif
+#ifndef RP_CON_PRE
+#define RP_CON_PRE 1  // residual-independent half of the contact update ahead of the J*v reduction
 #endif
 #ifndef RP_MINBLOCKS
 #define RP_MINBLOCKS 6
@@ -1180,6 +1189,47 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
               fr_f = phi ? fr_hi : (plo ? fr_lo : fr_f + dl);
             }
           }
+#elif RP_FR_ABS
+          // Absolute-force form: lane j tracks g_j, the unclamped minimiser of its own row given the forces of
+          // the rows before it (already updated) and after it (still old).  Committing row i then costs
+          // clamp -> shuffle -> one FMA on the serial chain (the classic form has four more dependent fp64
+          // operations per row); the two matrix-vector products this needs (removing the old forces of the
+          // earlier rows up front, folding the force changes into va afterwards) have no serial dependence.
+          // K_ij = Ah_ij * ARi_j.  Same Gauss-Seidel iterates up to rounding.
+          {
+            double g0 = fr_f - (fbase + va) * fr_ARi, g1 = 0;
+            const double* pr = prow;
+#pragma unroll 2
+            for (int i = 0; i < NL; i += 2, pr += 2 * RS) {
+              const double f0 = shfl(fr_f, i), f1 = shfl(fr_f, i + 1);
+              const double k0 = i < lane ? pr[0] * fr_ARi : 0.0, k1 = i + 1 < lane ? pr[RS] * fr_ARi : 0.0;
+              g0 = fma(-k0, f0, g0);
+              g1 = fma(-k1, f1, g1);
+            }
+            double g = g0 + g1, fx_own = fr_f, g_own = 0;
+            pr = prow;
+#pragma unroll kFrUnroll
+            for (int i = 0; i < NL; i++, pr += RS) {
+              const double k = i < lane ? pr[0] * fr_ARi : 0.0;
+              double fx = g < fr_lo ? fr_lo : g;
+              fx = g > fr_hi ? fr_hi : fx;
+              const double fbc = shfl(fx, i);
+              if (lane == i) { fx_own = fx; g_own = g; }
+              g = fma(k, fbc, g);
+            }
+            const double dl = fx_own - fr_f, res_own = (fr_f - g_own) * fr_AR;
+            improvement -= dl * (0.5 * dl * fr_AR + res_own);
+            fr_f = fx_own;
+            double a0 = 0, a1 = 0;
+            pr = prow;
+#pragma unroll 2
+            for (int i = 0; i < NL; i += 2, pr += 2 * RS) {
+              const double d0 = shfl(dl, i), d1 = shfl(dl, i + 1);
+              a0 = fma(-pr[0], d0, a0);
+              a1 = fma(-pr[RS], d1, a1);
+            }
+            va += a0 + a1;
+          }
 #elif RP_FR_DEFER
           // the owner lane only records (dl, res) at its commit; the cost change is evaluated once after
           // the sweep, which keeps three fp64 instructions per row off the 16-lane fp64 pipe
@@ -1262,6 +1312,21 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
               const bool anc = lane <= link && link < lane + lsub;
               const double j0 = anc ? cn.Jc[0][ldc] : 0.0, j1 = anc ? cn.Jc[1][ldc] : 0.0, j2 = anc ? cn.Jc[2][ldc] : 0.0;
               double part[3] = {j0 * va, j1 * va, j2 * va};
+#if RP_CON_PRE
+              // residual-independent part of the update, issued ahead of the reduction so that it runs in the
+              // shadow of the shuffle latency: block loads, ray denominators, the lambda = 0 pass of the QCQP
+              double Ab[9], fold[3], rbase[3];
+#pragma unroll
+              for (int k = 0; k < 9; k++) Ab[k] = cn.A[k];
+              const double cmu = cn.mu;
+              {
+                const double vak0 = sm.vak[key >= 0 ? key : 0], jkm0 = key >= 0 ? 1.0 : 0.0;
+#pragma unroll
+                for (int r = 0; r < 3; r++) { fold[r] = cn.f[r]; rbase[r] = cn.b[r] + cn.R[r] * fold[r] + jkm0 * cn.Jk[r] * vak0; }
+              }
+              rp::EllPre pre;
+              rp::pgs_elliptic_pre(pre, Ab, fold, cmu);
+#endif
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -1270,6 +1335,11 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
               double res[3], f[3];
               const double vak = sm.vak[key >= 0 ? key : 0];
               const double jkm = key >= 0 ? 1.0 : 0.0;
+#if RP_CON_PRE
+              for (int r = 0; r < 3; r++) res[r] = rbase[r] + part[r];
+              f[0] = fold[0]; f[1] = fold[1]; f[2] = fold[2];
+              const double change = rp::pgs_elliptic_post(pre, Ab, res, f, cmu);
+#else
 #pragma unroll
               for (int r = 0; r < 3; r++) {
                 f[r] = cn.f[r];
@@ -1280,6 +1350,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
               for (int k = 0; k < 9; k++) Ab[k] = cn.A[k];
               const double fold[3] = {f[0], f[1], f[2]};
               const double change = rp::pgs_elliptic_update(Ab, res, f, cn.mu);
+#endif
               const double df[3] = {f[0] - fold[0], f[1] - fold[1], f[2] - fold[2]};
               __syncwarp();
               improvement -= lane == 0 ? change : 0.0;
@@ -1289,12 +1360,25 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
                 // hand side: w = Jc^T df on the chain, va += Minv[:,chain] w
                 const double w = j0 * df[0] + j1 * df[1] + j2 * df[2];
                 double acc = 0;
+#if RP_CH_ACC2
+                // two partial sums: halves the serial length of the accumulation (chain[] is zero-padded)
+                double acc2 = 0;
+#pragma unroll 1
+                for (int d = 0; d <= dep; d += 2) {
+                  const int j = cn.chain[d], j2 = cn.chain[d + 1];
+                  const double wj = shfl(w, j), wj2 = shfl(w, j2);
+                  acc -= Ah[j * RS + lc] * wj;
+                  acc2 -= Ah[j2 * RS + lc] * (d + 1 <= dep ? wj2 : 0.0);
+                }
+                acc += acc2;
+#else
 #pragma unroll kChUnroll
                 for (int d = 0; d <= dep; d++) {
                   const int j = cn.chain[d];
                   const double wj = shfl(w, j);
                   acc -= Ah[j * RS + lc] * wj;
                 }
+#endif
                 va += acc;
               }
               __syncwarp();

@@ -304,6 +304,90 @@ RP_HD double pgs_elliptic_update(const double* A, const double* res, double* f, 
   if (change > 1e-10) { f[0] = old[0]; f[1] = old[1]; f[2] = old[2]; change = 0; }
   return change;
 }
+// ---- The same update split in two, for the warp-wide Gauss-Seidel of the step kernel: everything that
+// does not depend on the residual (the ray denominators, the lambda = 0 pass of the QCQP) is evaluated by
+// pgs_elliptic_pre while the J*v reduction is still in flight, so that only the residual-dependent
+// operations stay on the serial chain.  Same operations, same order, same results as pgs_elliptic_update.
+struct QcqpPre { double A11, A22, A12, P11, P22, P12; int ok; };
+struct EllPre { double old[3], rA0, rden; QcqpPre q; int lowf, den_ok; };
+RP_HD void qcqp2_prepare(QcqpPre& q, const double* Ain, const double* d) {
+  q.A11 = Ain[0] * d[0] * d[0]; q.A22 = Ain[3] * d[1] * d[1]; q.A12 = Ain[1] * d[0] * d[1];
+  const double det = q.A11 * q.A22 - q.A12 * q.A12;  // (A11 + la) * (A22 + la) - A12^2 at la = 0
+  q.ok = !(det < 1e-10);
+  const double detinv = rcp(det);  // unused when !ok
+  q.P11 = q.A22 * detinv; q.P22 = q.A11 * detinv; q.P12 = -q.A12 * detinv;
+}
+RP_HD int qcqp2_solve(double* res, const QcqpPre& q, const double* bin, const double* d, double r) {
+  const double b1 = bin[0] * d[0], b2 = bin[1] * d[1];
+  if (!q.ok) { res[0] = 0; res[1] = 0; return 0; }
+  double la = 0, P11 = q.P11, P22 = q.P22, P12 = q.P12, v1, v2;
+  for (int iter = 0;;) {
+    v1 = -P11 * b1 - P12 * b2;
+    v2 = -P12 * b1 - P22 * b2;
+    const double val = v1 * v1 + v2 * v2 - r * r;
+    if (val < 1e-10) break;
+    const double deriv = -2 * (P11 * v1 * v1 + 2 * P12 * v1 * v2 + P22 * v2 * v2);
+    const double delta = -val * rcp(deriv);
+    if (delta < 1e-10) break;
+    la += delta;
+    if (++iter >= 20) break;
+    const double det = (q.A11 + la) * (q.A22 + la) - q.A12 * q.A12;
+    if (det < 1e-10) { res[0] = 0; res[1] = 0; return 0; }
+    const double detinv = rcp(det);
+    P11 = (q.A22 + la) * detinv; P22 = (q.A11 + la) * detinv; P12 = -q.A12 * detinv;
+  }
+  res[0] = v1 * d[0];
+  res[1] = v2 * d[1];
+  return la != 0;
+}
+RP_HD void pgs_elliptic_pre(EllPre& p, const double* A, const double* f, double mu) {
+  p.old[0] = f[0]; p.old[1] = f[1]; p.old[2] = f[2];
+  p.lowf = f[0] < RP_MINVAL;
+  p.rA0 = rcp(A[0]);
+  double v1[3];
+  for (int r = 0; r < 3; r++) v1[r] = A[3 * r] * f[0] + A[3 * r + 1] * f[1] + A[3 * r + 2] * f[2];
+  const double denom = dot3(f, v1);
+  p.den_ok = denom >= RP_MINVAL;
+  p.rden = rcp(denom);  // unused when !den_ok
+  const double Ac[4] = {A[4], A[5], A[7], A[8]}, fr[2] = {mu, mu};
+  qcqp2_prepare(p.q, Ac, fr);
+}
+RP_HD double pgs_elliptic_post(const EllPre& p, const double* A, const double* res, double* f, double mu) {
+  const double* old = p.old;
+  const double fr[2] = {mu, mu};
+  if (p.lowf) {
+    f[0] -= res[0] * p.rA0;
+    if (f[0] < 0) f[0] = 0;
+    f[1] = f[2] = 0;
+  } else if (p.den_ok) {
+    double x = -dot3(old, res) * p.rden;
+    if (f[0] + x * old[0] < 0) x = -1.0;
+    for (int r = 0; r < 3; r++) f[r] += x * old[r];
+  }
+  if (f[0] >= RP_MINVAL) {
+    double bc[2], vv[2];
+    for (int r = 1; r < 3; r++) {
+      double t = res[r];
+      for (int s = 1; s < 3; s++) t -= A[3 * r + s] * old[s];
+      t += A[3 * r] * (f[0] - old[0]);
+      bc[r - 1] = t;
+    }
+    const int flg = qcqp2_solve(vv, p.q, bc, fr, f[0]);
+    if (flg) {
+      const double imu2 = rcp(fr[0] * fr[0]);
+      double s = vv[0] * vv[0] * imu2 + vv[1] * vv[1] * imu2;
+      s = sqrt(f[0] * f[0] * rcp(fmax(RP_MINVAL, s)));
+      vv[0] *= s; vv[1] *= s;
+    }
+    f[1] = vv[0]; f[2] = vv[1];
+  }
+  const double dl[3] = {f[0] - old[0], f[1] - old[1], f[2] - old[2]};
+  double Ad[3];
+  for (int r = 0; r < 3; r++) Ad[r] = A[3 * r] * dl[0] + A[3 * r + 1] * dl[1] + A[3 * r + 2] * dl[2];
+  double change = 0.5 * dot3(dl, Ad) + dot3(dl, res);
+  if (change > 1e-10) { f[0] = old[0]; f[1] = old[1]; f[2] = old[2]; change = 0; }
+  return change;
+}
 // primal map of an elliptic contact: jar (3) -> force (3)  (mj_constraintUpdate)
 RP_HD void elliptic_primal_force(const double* jar, const double* D, double mu, double* force) {
   double U0 = jar[0] * mu, U1 = jar[1] * mu, U2 = jar[2] * mu;

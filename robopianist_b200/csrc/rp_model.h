@@ -15,7 +15,9 @@
 #define RP_NGH 20     // colliding primitive geoms per hand (capsules / spheres), max
 #define RP_NAH 24     // actuators per hand, max
 #define RP_NSITE 5    // fingertip sites per hand
-#define RP_MAXCON 24  // contact capacity per environment
+#ifndef RP_MAXCON
+#define RP_MAXCON 24  // contact capacity per environment (shared memory: 480 B each)
+#endif
 #define RP_NPIANO 89  // piano boxes: index 0 = base, 1 + k = key k (MuJoCo body order)
 
 struct RpGeomParams {  // contact-relevant geom fields
