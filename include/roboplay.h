@@ -153,6 +153,19 @@ int rp_get_aux(rp_batch *, double *actuator_force, double *site_xpos, uint8_t *a
  * [8..13] the six means of the last completed episode, [14..15] reserved. */
 int rp_get_metrics(rp_batch *, double *out);
 
+/* Device-side MIDI event stream: replaces robopianist/models/piano/midi_module.py:47-98
+ * (MidiModule.after_substep, called per physics substep from Piano.after_substep, piano.py:154-162).
+ * rp_midi_enable allocates `capacity` event words per environment; from then on every rp_step records,
+ * per substep, the keys whose activation changed and pedal changes.  Event word (uint32):
+ * (tick << 9) | (class << 7) | key, tick = substeps since the episode start (message time = tick *
+ * timestep), class 0 NoteOn (velocity 127 as in the reference), 1 NoteOff, 2 SustainOn, 3 SustainOff,
+ * key = 0..87 (MIDI note = key + 21).  Sorting one environment's words ascending yields the reference's
+ * message order.  The list restarts when the environment starts a new episode.
+ * rp_get_midi (HOST buffers, synchronous): events [N,capacity] (unsorted), counts [N] (> capacity means
+ * events were dropped). */
+int rp_midi_enable(rp_batch *, int capacity);
+int rp_get_midi(rp_batch *, uint32_t *events, int32_t *counts);
+
 int64_t rp_launch_count(const rp_batch *); /* kernels launched by this batch so far */
 
 #ifdef __cplusplus

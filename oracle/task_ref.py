@@ -5,7 +5,8 @@ Follows, line by line, the reference's Python:
   Piano.after_substep) -> after_step -> observables -> reward -> termination;
   robopianist/suite/tasks/piano_with_shadow_hands.py:176-220 (before/after_step, termination),
   :251-331 (rewards), :371-412 (goal / fingering state), robopianist/models/piano/piano.py:178-192
-  (key state), robopianist/suite/tasks/self_actuated_piano.py:38-57,143-243,
+  (key state), robopianist/models/piano/midi_module.py:40-98 (MIDI messages per substep, record_midi=True),
+  robopianist/suite/tasks/self_actuated_piano.py:38-57,143-243,
   dm_control.utils.rewards.tolerance (gaussian sigmoid, value_at_margin=0.1).
 PARITY UNPINNED for the physics underneath (see oracle.c).
 """
@@ -59,6 +60,8 @@ class RefEnv:
         self.nu = fm.meta["nu"]
         self._need_reset = True
         self.reward_terms = {}
+        self.record_midi = False
+        self.midi_messages = []
 
     # ---------------------------------------------------------------- helpers
     def _update_key_state(self):
@@ -71,6 +74,23 @@ class RefEnv:
             self.normalized = self.state / self.qmax
             self.activation = np.abs(self.state - self.qmax) <= KEY_THRESHOLD
         self.sustain_activation = self.sustain_state >= SUSTAIN_THRESHOLD
+
+    def _midi_after_substep(self):
+        """MidiModule.after_substep (midi_module.py:47-98): note-ons (ascending key), note-offs, pedal."""
+        self._substeps += 1
+        t = self._substeps * self.fm.meta["timestep"]
+        act, prev = np.asarray(self.activation, bool), self._prev_activation
+        change = act ^ prev
+        for k in np.flatnonzero(change & ~prev):
+            self.midi_messages.append((t, "note_on", int(k) + 21))
+        for k in np.flatnonzero(change & ~act):
+            self.midi_messages.append((t, "note_off", int(k) + 21))
+        sus, psus = bool(self.sustain_activation), self._prev_sustain_activation
+        if (sus != psus) and not psus:
+            self.midi_messages.append((t, "sustain_on", None))
+        if (sus != psus) and not sus:
+            self.midi_messages.append((t, "sustain_off", None))
+        self._prev_activation, self._prev_sustain_activation = act.copy(), sus
 
     def _update_goal_state(self):
         if self.t_idx == self.T:
@@ -111,6 +131,11 @@ class RefEnv:
         self._need_reset = False
         self.last_actuator_force = np.zeros(self.nu)
         self._key_prf, self._sustain_prf = [], []  # MidiEvaluationWrapper.reset (wrappers/evaluation.py:90-93)
+        # MidiModule.initialize_episode (midi_module.py:40-45)
+        self._prev_activation = np.zeros(88, dtype=bool)
+        self._prev_sustain_activation = False
+        self.midi_messages = []
+        self._substeps = 0
         return FIRST, None, None, self._observation()
 
     def step(self, action):
@@ -119,7 +144,13 @@ class RefEnv:
         d, fm = self.d, self.fm
         action = np.asarray(action, np.float64)
         self.sustain_state = float(action[-1])
-        d.control_step(action[:-1])  # nsub x (mj_step2; mj_step1): legacy_step=True
+        if not self.record_midi:
+            d.control_step(action[:-1])  # nsub x (mj_step2; mj_step1): legacy_step=True
+        else:
+            for _ in range(self.om.nsubstep):
+                d.control_step(action[:-1], 1)
+                self._update_key_state()  # Piano.after_substep (piano.py:154-162)
+                self._midi_after_substep()
         self._update_key_state()
         # after_step
         self.t_idx += 1

@@ -40,6 +40,9 @@ struct rp_batch {
   int order_valid;  // order[] holds a permutation (set after the first full step)
   uint8_t* activation;
   double* metrics;  // [N][RP_METRICS_STRIDE] musical metrics accumulators (see rp_get_metrics)
+  uint32_t* midi_events;  // [N][midi_cap], allocated by rp_midi_enable
+  int32_t* midi_count;
+  int midi_cap;
   // staging for rp_step_host
   double *h_action, *h_out;  // pinned
   double *d_action, *d_out;
@@ -357,6 +360,7 @@ extern "C" int rp_batch_destroy(rp_batch* b) {
   cudaFree(b->qpos); cudaFree(b->qvel); cudaFree(b->qacc_ws); cudaFree(b->ctrl); cudaFree(b->sustain);
   cudaFree(b->act_force); cudaFree(b->site_xpos); cudaFree(b->t_idx); cudaFree(b->step_type_state);
   cudaFree(b->diag); cudaFree(b->activation); cudaFree(b->metrics); cudaFree(b->work); cudaFree(b->order); cudaFree(b->dbg); cudaFree(b->d_action); cudaFree(b->d_out);
+  cudaFree(b->midi_events); cudaFree(b->midi_count);
   cudaFreeHost(b->h_action); cudaFreeHost(b->h_out);
   delete b;
   return 0;
@@ -376,6 +380,7 @@ static RpKernelArgs base_args(rp_batch* b, int mode) {
   a.t_idx = b->t_idx; a.step_type_state = b->step_type_state; a.sustain = b->sustain;
   a.goal = b->d_goal; a.fingering = b->d_fingering;
   a.diag = b->diag; a.act_force = b->act_force; a.site_xpos = b->site_xpos; a.activation = b->activation; a.metrics = b->metrics;
+  a.midi_events = b->midi_events; a.midi_count = b->midi_count; a.midi_cap = b->midi_cap;
   a.work = b->work; a.order = b->order_valid ? b->order : nullptr;
   a.dbg = b->dbg;
   return a;
@@ -503,6 +508,26 @@ extern "C" int rp_get_metrics(rp_batch* b, double* out) {
   CUDA_OK(cudaSetDevice(b->device));
   CUDA_OK(cudaStreamSynchronize(b->stream));
   CUDA_OK(cudaMemcpy(out, b->metrics, sizeof(double) * (size_t)b->nenv * RP_METRICS_STRIDE, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int rp_midi_enable(rp_batch* b, int capacity) {
+  if (capacity <= 0) return fail("capacity must be positive");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  cudaFree(b->midi_events); cudaFree(b->midi_count);
+  b->midi_events = nullptr; b->midi_count = nullptr; b->midi_cap = 0;
+  CUDA_OK(dalloc(&b->midi_events, (size_t)b->nenv * capacity));
+  CUDA_OK(dalloc(&b->midi_count, (size_t)b->nenv));
+  b->midi_cap = capacity;
+  return 0;
+}
+extern "C" int rp_get_midi(rp_batch* b, uint32_t* events, int32_t* counts) {
+  if (!b->midi_events) return fail("rp_midi_enable was not called");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  if (events) CUDA_OK(cudaMemcpy(events, b->midi_events, sizeof(uint32_t) * (size_t)b->nenv * b->midi_cap, cudaMemcpyDeviceToHost));
+  if (counts) CUDA_OK(cudaMemcpy(counts, b->midi_count, sizeof(int32_t) * (size_t)b->nenv, cudaMemcpyDeviceToHost));
   return 0;
 }
 

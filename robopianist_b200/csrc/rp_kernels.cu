@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     if (!do_reset) return;
   }
   const int act_dim = dm->act_dim;
+  double sustain_prev = 0;  // thread 0: sustain state before this step's action (MIDI sustain events)
   // controls of this step -> shared memory (and the persistent ctrl state)
   if (do_reset) {
     for (int j = tid; j < nu; j += KT) { sm.ctrl[j] = 0; gctrl[j] = 0; }
@@ -297,7 +298,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     // before_step: ctrl <- action[:-1] verbatim (clamping happens in the actuator model), sustain <- action[-1]
     const double* act = a.action + (size_t)env * act_dim;
     for (int j = tid; j < nu; j += KT) { const double c = act[j]; sm.ctrl[j] = c; gctrl[j] = c; }
-    if (tid == 0) a.sustain[env] = act[act_dim - 1];
+    if (tid == 0) {
+      sustain_prev = a.sustain[env];
+      a.sustain[env] = act[act_dim - 1];
+    }
   } else if (a.mode == RP_MODE_PHYSICS && a.ctrl_in != nullptr) {
     const double* c = a.ctrl_in + (size_t)env * nu;
     for (int j = tid; j < nu; j += KT) { const double cv = c[j]; sm.ctrl[j] = cv; gctrl[j] = cv; }
@@ -305,6 +309,26 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     for (int j = tid; j < nu; j += KT) sm.ctrl[j] = gctrl[j];
   }
   if (do_reset && tid == 0) { a.t_idx[env] = 0; a.sustain[env] = 0; }
+  // ---- MIDI event stream (models/piano/midi_module.py:47-98): activation changes per physics substep.
+  // The previous activation is the one stored by the last step's epilogue; an episode start clears it.
+  const bool midi_on = a.midi_events != nullptr && a.mode != RP_MODE_PHYSICS;
+  bool midi_prev[KS];
+#pragma unroll
+  for (int s = 0; s < KS; s++) {
+    const int k = tid + KT * s;
+    midi_prev[s] = midi_on && !do_reset && k < NK && a.activation[(size_t)env * NK + k] != 0;
+  }
+  if (midi_on && tid == 0) {
+    if (do_reset) a.midi_count[env] = 0;
+    else if (a.mode == RP_MODE_STEP) {
+      // the pedal state only changes with the action, so its event belongs to the first substep
+      const bool was = sustain_prev >= 0.5, is = a.sustain[env] >= 0.5;
+      if (was != is) {
+        const int slot = atomicAdd(&a.midi_count[env], 1);
+        if (slot < a.midi_cap) a.midi_events[(size_t)env * a.midi_cap + slot] = RP_MIDI_WORD(t_idx * a.nsub + 1, is ? 2 : 3, 0);
+      }
+    }
+  }
 
   // ------------------------------------------------------------------ load state
   double qk[KS], vk[KS], wk[KS];  // keys tid, tid+KT, ...
@@ -1260,8 +1284,16 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
             const double mrow = *prow;
             const double res = fbase + va;
             const double x = fr_f - res * fr_ARi;
+#if RP_FR_ICLAMP
+            // symmetric clamp on the integer pipe: |x| > hi compares like the bit patterns (non-negative doubles),
+            // the result takes the sign of x; a DSETP + select pair costs about twice the latency
+            const unsigned long long xb = (unsigned long long)__double_as_longlong(x);
+            const bool big = (xb & 0x7fffffffffffffffull) > (unsigned long long)__double_as_longlong(fr_hi);
+            const double fx = big ? __longlong_as_double((long long)((xb & 0x8000000000000000ull) | (unsigned long long)__double_as_longlong(fr_hi))) : x;
+#else
             double fx = x < fr_lo ? fr_lo : x;
             fx = x > fr_hi ? fr_hi : fx;
+#endif
             const double dl = fx - fr_f;
             const double dbc = shfl(dl, i);
             va -= mrow * dbc;
@@ -1506,6 +1538,27 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         vk[s] += hstep * ae;
         qk[s] += hstep * vk[s];
         wk[s] = kq_acc[s];
+      }
+    }
+    if (midi_on) {  // Piano.after_substep -> MidiModule.after_substep: activation XOR previous activation
+#pragma unroll
+      for (int s = 0; s < KS; s++) {
+        const int k = tid + KT * s;
+        if (k < NK) {
+          bool act;
+          if (dm->task_kind == 1) {
+            act = sm.ctrl[k] >= 0.5 * (dm->key_act_range[k][0] + dm->key_act_range[k][1]);
+          } else {
+            const double hi = dm->key_range[k][1];
+            act = fabs(fmin(fmax(qk[s], dm->key_range[k][0]), hi) - hi) <= 0.00872665;
+          }
+          if (act != midi_prev[s]) {
+            const int slot = atomicAdd(&a.midi_count[env], 1);
+            if (slot < a.midi_cap)
+              a.midi_events[(size_t)env * a.midi_cap + slot] = RP_MIDI_WORD(t_idx * a.nsub + sub + 1, act ? 0 : 1, k);
+            midi_prev[s] = act;
+          }
+        }
       }
     }
     block_sync<NW>();

@@ -10,6 +10,10 @@ enum { RP_MODE_STEP = 0, RP_MODE_RESET = 1, RP_MODE_PHYSICS = 2 };
 enum { RP_STEP_FIRST_ = 0, RP_STEP_MID_ = 1, RP_STEP_LAST_ = 2 };
 #define RP_GOAL_DIM_ 89
 #define RP_METRICS_STRIDE 16
+// MIDI event word: (tick << 9) | (class << 7) | key; tick = physics substeps since the episode start
+// (event time = tick * timestep); class 0 NoteOn, 1 NoteOff, 2 SustainOn, 3 SustainOff.  Sorting the
+// words of one environment ascending gives the reference's message order (midi_module.py:47-98).
+#define RP_MIDI_WORD(tick, cls, key) (((uint32_t)(tick) << 9) | ((uint32_t)(cls) << 7) | (uint32_t)(key))
 
 // debug dump layout (doubles per env), filled for substep 0 when RpKernelArgs::dbg != nullptr
 #define RP_DBG_QACC_SMOOTH 0
@@ -45,6 +49,9 @@ struct RpKernelArgs {
   double* site_xpos;         // [N][10][3]
   uint8_t* activation;       // [N][88]
   double* metrics;           // [N][RP_METRICS_STRIDE]
+  uint32_t* midi_events;     // [N][midi_cap] packed key / sustain events of the running episode (optional)
+  int32_t* midi_count;       // [N] events emitted so far this episode (may exceed midi_cap: overflow)
+  int midi_cap, pad_midi;
   int32_t* work;             // [N] work estimate of this step (out)
   const int32_t* order;      // [N] block -> environment (optional)
   double* dbg;

@@ -21,7 +21,7 @@ EXPORTS = [
     "rp_last_error", "rp_version", "rp_model_create", "rp_model_destroy", "rp_obs_dim", "rp_action_dim",
     "rp_reward_terms", "rp_batch_create", "rp_batch_destroy", "rp_set_option", "rp_reset", "rp_step",
     "rp_step_host", "rp_physics_step", "rp_get_state", "rp_set_state", "rp_get_diag", "rp_get_aux",
-    "rp_launch_count", "rp_step_staged", "rp_host_buffers", "rp_get_metrics",
+    "rp_launch_count", "rp_step_staged", "rp_host_buffers", "rp_get_metrics", "rp_midi_enable", "rp_get_midi",
 ]
 
 
@@ -59,6 +59,8 @@ def lib():
         L.rp_step_staged.argtypes = [vp]
         L.rp_host_buffers.argtypes = [vp, C.POINTER(dp), C.POINTER(dp)]
         L.rp_get_metrics.argtypes = [vp, dp]
+        L.rp_midi_enable.argtypes = [vp, C.c_int]
+        L.rp_get_midi.argtypes = [vp, C.POINTER(C.c_uint32), ip]
         L.rp_launch_count.restype = C.c_int64
         L.rp_launch_count.argtypes = [vp]
         L.rp_debug_enable.argtypes = [vp, C.c_int]
@@ -194,6 +196,28 @@ class Batch:
         d["episodes"] = out[:, 7].astype(np.int64)
         d["running_sums"], d["running_steps"] = out[:, :6].copy(), out[:, 6].astype(np.int64)
         return d
+
+    def midi_enable(self, capacity=4096):
+        """Start recording the per-substep MIDI event stream (rp_midi_enable)."""
+        _check(lib().rp_midi_enable(self.ptr, int(capacity)))
+        self._midi_cap = int(capacity)
+
+    def get_midi(self, timestep=0.005):
+        """Events of the running episode per env, in the reference's message order: list (len N) of lists of
+        (time_seconds, kind, midi_note) with kind in {"note_on", "note_off", "sustain_on", "sustain_off"}
+        (midi_note is None for pedal events; velocity of note_on is 127 as in midi_module.py:67-72)."""
+        cap = self._midi_cap
+        ev = np.empty((self.nenv, cap), np.uint32); cnt = np.empty(self.nenv, np.int32)
+        _check(lib().rp_get_midi(self.ptr, ev.ctypes.data_as(C.POINTER(C.c_uint32)), cnt.ctypes.data_as(C.POINTER(C.c_int32))))
+        if (cnt > cap).any():
+            raise NativeError(f"MIDI event buffer overflow (capacity {cap}, needed {int(cnt.max())})")
+        kinds = ("note_on", "note_off", "sustain_on", "sustain_off")
+        out = []
+        for e in range(self.nenv):
+            w = np.sort(ev[e, :cnt[e]])
+            out.append([(float(x >> 9) * timestep, kinds[(x >> 7) & 3], int(x & 127) + 21 if ((x >> 7) & 3) < 2 else None)
+                        for x in w.tolist()])
+        return out
 
     @property
     def launches(self):

@@ -231,6 +231,16 @@ class BatchedPianoEnv:
         return {k: float(m[k][done].mean()) for k in
                 ("precision", "recall", "f1", "sustain_precision", "sustain_recall", "sustain_f1")}
 
+    def enable_midi(self, capacity: int = 4096):
+        """Record the MIDI message stream of every env on the device (Piano.midi_module of the reference:
+        models/piano/midi_module.py:47-98, one activation XOR per physics substep)."""
+        self.batch.midi_enable(capacity)
+
+    def get_all_midi_messages(self):
+        """Per env, the messages of the running episode as (time, kind, midi_note) in the reference's order
+        (MidiModule.get_all_midi_messages); read them before stepping past the end of the episode."""
+        return self.batch.get_midi(self.flat.meta["timestep"])
+
     def get_state(self):
         return self.batch.get_state()
 
@@ -254,6 +264,14 @@ class _Piano:
     @property
     def sustain_activation(self):
         return np.array([self._env._sustain >= 0.5])
+
+    @property
+    def midi_module(self):
+        return self
+
+    def get_all_midi_messages(self):
+        """`env.task.piano.midi_module.get_all_midi_messages()` (needs `env.enable_midi()` before reset)."""
+        return self._env._batched.get_all_midi_messages()[0]
 
 
 class _RewardFn:
@@ -321,6 +339,9 @@ class PianoEnv:
 
     def get_musical_metrics(self):
         return self._batched.get_musical_metrics()
+
+    def enable_midi(self, capacity: int = 4096):
+        self._batched.enable_midi(capacity)
 
     def close(self):
         self._batched.close()

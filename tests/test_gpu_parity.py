@@ -270,3 +270,47 @@ def test_musical_metrics_match_the_wrapper_logic():
     m2 = batch.get_metrics()
     assert (m2["running_steps"] == 0).all() and m2["f1"][0] == m["f1"][0]
     batch.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["piano_with_shadow_hands", "self_actuated_piano"])
+def test_midi_event_stream_matches_midi_module(task):
+    """Device-side MIDI messages (rp_midi_enable / rp_get_midi) vs the restated MidiModule.after_substep
+    (models/piano/midi_module.py:47-98) over the oracle's substeps: same messages, same order, same times;
+    the list restarts with the next episode."""
+    song = "TwinkleTwinkleRousseau"
+    fm, model, batch = helpers.make_native(task, song=song, nenv=3)
+    goal, fing = helpers.song_tables(song)
+    hands = task == "piano_with_shadow_hands"
+    ref = task_ref.RefEnv(fm, goal, fing, kind=0 if hands else 1, n_steps_lookahead=1)
+    ref.record_midi = True
+    N = 3
+    obs = torch.empty((N, model.obs_dim), dtype=torch.float64, device="cuda")
+    rew = torch.empty(N, dtype=torch.float64, device="cuda"); dis = torch.empty_like(rew)
+    st = torch.empty(N, dtype=torch.uint8, device="cuda")
+    batch.midi_enable(2048)
+    batch.reset(None, obs.data_ptr()); ref.reset()
+    if hands:
+        acts = helpers.twinkle_actions()
+        acts[:, -1] = (np.arange(len(acts)) // 7) % 2   # exercise the pedal as well
+    else:
+        rng = np.random.default_rng(3)
+        qmax = fm.actuator_ctrlrange[:, 1]
+        acts = np.concatenate([rng.uniform(0, 1, (goal.shape[0], 88)) ** 6 * qmax, rng.integers(0, 2, (goal.shape[0], 1))], axis=1)
+    T = goal.shape[0]
+    for t in range(T):
+        a = acts[t % len(acts)]
+        batch.step(_dev(np.tile(a, (N, 1))).data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
+        ref.step(a)
+        if t in (0, 40, T - 1):
+            got = batch.get_midi(fm.meta["timestep"])
+            assert got[0] == got[2]
+            assert len(got[0]) == len(ref.midi_messages), (t, len(got[0]), len(ref.midi_messages))
+            for g, r in zip(got[0], ref.midi_messages):
+                assert g[1:] == r[1:] and abs(g[0] - r[0]) < 1e-12, (t, g, r)
+    kinds = {m[1] for m in ref.midi_messages}
+    assert {"note_on", "note_off", "sustain_on", "sustain_off"} <= kinds and len(ref.midi_messages) > 20
+    # stepping past the end of the episode starts an empty list
+    batch.step(_dev(np.tile(acts[0] * 0, (N, 1))).data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
+    assert all(len(m) == 0 for m in batch.get_midi(fm.meta["timestep"]))
+    batch.close()

@@ -126,3 +126,37 @@ def test_prf_binary_matches_sklearn():
     for y_true, y_pred in cases:
         ref = precision_recall_fscore_support(y_true=np.asarray(y_true), y_pred=np.asarray(y_pred), average="binary", zero_division=1)[:3]
         assert np.allclose(task_ref.prf_binary(y_true, y_pred), ref, atol=1e-15), (y_true, y_pred)
+
+
+def test_midi_messages_of_the_reference_restatement(hands):
+    """RefEnv(record_midi=True) restates MidiModule.after_substep: every note_on is closed by a note_off of the
+    same note unless still held, times are multiples of the physics timestep, pedal events alternate."""
+    fm = hands[0]
+    goal, fing = helpers.song_tables("TwinkleTwinkleRousseau")
+    ref = task_ref.RefEnv(fm, goal, fing, n_steps_lookahead=1)
+    ref.record_midi = True
+    ref.reset()
+    acts = helpers.twinkle_actions()
+    acts[:, -1] = (np.arange(len(acts)) // 7) % 2
+    for t in range(45):
+        ref.step(acts[t])
+    msgs = ref.midi_messages
+    assert len(msgs) > 10
+    held, pedal = set(), False
+    for tm, kind, note in msgs:
+        assert abs(tm / 0.005 - round(tm / 0.005)) < 1e-9
+        if kind == "note_on":
+            assert note not in held; held.add(note)
+        elif kind == "note_off":
+            assert note in held; held.remove(note)
+        elif kind == "sustain_on":
+            assert not pedal; pedal = True
+        else:
+            assert pedal; pedal = False
+    assert [m[0] for m in msgs] == sorted(m[0] for m in msgs)
+    # identical physics with and without per-substep stepping
+    ref2 = task_ref.RefEnv(fm, goal, fing, n_steps_lookahead=1)
+    ref2.reset()
+    for t in range(45):
+        ref2.step(acts[t])
+    assert np.array_equal(ref.d.qpos, ref2.d.qpos)
