@@ -46,6 +46,9 @@
 #ifndef RP_FR_ICLAMP
 #define RP_FR_ICLAMP 0
 #endif
+#ifndef RP_FR_SKIP
+#define RP_FR_SKIP 1  // step only the friction-loss rows whose force changes (bit-identical; see the sweep)
+#endif
 #ifndef RP_FR_ABS
 #define RP_FR_ABS 0
 #endif
@@ -54,6 +57,15 @@
 #endif
 #ifndef RP_SW_UNROLL
 #define RP_SW_UNROLL 2
+#endif
+#ifndef RP_NU
+#define RP_NU 8  // contacts whose M^-1 Jc^T is kept in shared memory (the others walk the kinematic chain)
+#endif
+#ifndef RP_JV_GATHER
+#define RP_JV_GATHER 0
+#endif
+#ifndef RP_CH_PIPE
+#define RP_CH_PIPE 0
 #endif
 #ifndef RP_CH_ACC2
 #define RP_CH_ACC2 0
@@ -90,13 +102,19 @@ struct RawContact {  // narrowphase output before sorting
 
 struct Smem {
   double A[RP_NHMAX][NL * RS];  // per hand: M, then -M^-1 (sweep), later -(M + h*D)^-1; symmetric, row-major
-  double S[RP_NHMAX][NL][6];
-  double vk[NK], vak[NK];
-  double ksn[NK], kcs[NK];            // sin / cos of the key angles of this substep
+  union {
+    struct {  // per-substep scratch, dead once the contact rows are built
+      double S[RP_NHMAX][NL][6];
+      double vk[NK];
+      double ksn[NK], kcs[NK];          // sin / cos of the key angles of this substep
+      double wsb[RP_NHMAX][32];         // qacc_warmstart of the hand dofs (read by the contact rows)
+      double vh[RP_NHMAX][NL];          // hand joint velocities (for chain walks)
+    } pre;
+    double U[RP_NU > 0 ? RP_NU : 1][3][NL];  // Gauss-Seidel: M^-1 Jc^T of the first RP_NU contacts, lane-major
+  } v;
+  double vak[NK];
   double wbuf[RP_NHMAX][32];
-  double wsb[RP_NHMAX][32];           // qacc_warmstart of the hand dofs (read by the contact rows)
   double actf[RP_NHMAX][RP_NAH];
-  double vh[RP_NHMAX][NL];            // hand joint velocities (for chain walks)
   double kfc[NK];                     // per key: constraint force J^T f (qacc_warmstart before the sweep)
   double Mrow[RP_NHMAX][160];         // mass-matrix entries M[link][ancestor at depth d], packed by link (kept for the Euler solve)
   double ctrl[NK];                    // actuator controls of this control step
@@ -400,6 +418,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     if (HANDS) {
       xp[0] = xp[1] = xp[2] = 0;
       xq[0] = 1; xq[1] = xq[2] = xq[3] = 0;
+      // half-angle sine / cosine of the lane's own hinge, once (the level loop below runs its whole body
+      // for every level: anything lane-local that is hoisted out of it is executed once instead of 9 times)
+      double hsn = 0, hcs = 1;
+      if (hl && ljt != 2) sincos(0.5 * qh, &hsn, &hcs);
       for (int d = 0; d <= maxd; d++) {
         const int src = lpar >= 0 ? lpar : lane;
         double pp[3], pq[4];
@@ -423,8 +445,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
           if (ljt == 2) {
             for (int k = 0; k < 3; k++) pos[k] += xaxis[k] * qh;
           } else {
-            double sn, cs;
-            sincos(0.5 * qh, &sn, &cs);
+            const double sn = hsn, cs = hcs;
             double ql[4] = {cs, ja[0] * sn, ja[1] * sn, ja[2] * sn}, qn[4];
             rp::quat_mul(qn, quat, ql);
             for (int k = 0; k < 4; k++) quat[k] = qn[k];
@@ -444,7 +465,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
       if (k < NK) {
         double sn, cs;
         sincos(qk[s], &sn, &cs);
-        sm.vk[k] = vk[s]; sm.ksn[k] = sn; sm.kcs[k] = cs;
+        sm.v.pre.vk[k] = vk[s]; sm.v.pre.ksn[k] = sn; sm.v.pre.kcs[k] = cs;
       }
     }
     if (last_pass) break;
@@ -459,8 +480,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
       } else {
         for (int k = 0; k < 3; k++) { Sown[k] = 0; Sown[3 + k] = xaxis[k]; }
       }
-      for (int k = 0; k < 6; k++) sm.S[h][lane][k] = Sown[k];
-      sm.vh[h][lane] = vh;
+      for (int k = 0; k < 6; k++) sm.v.pre.S[h][lane][k] = Sown[k];
+      sm.v.pre.vh[h][lane] = vh;
     }
     __syncwarp();
 
@@ -471,8 +492,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
       for (int d = 0; d <= ldep; d++) {
         const int j = sm.anc[h][lane][d];
         double Sj[6], Sd[6];
-        for (int k = 0; k < 6; k++) Sj[k] = sm.S[h][j][k];
-        const double qd = sm.vh[h][j];
+        for (int k = 0; k < 6; k++) Sj[k] = sm.v.pre.S[h][j][k];
+        const double qd = sm.v.pre.vh[h][j];
         rp::cross_motion(Sd, V, Sj);
         for (int k = 0; k < 6; k++) { Ac[k] += Sd[k] * qd; V[k] += Sj[k] * qd; }
       }
@@ -522,7 +543,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
       for (int d = 0; d <= ldep; d++) {
         const int j = sm.anc[h][lane][d];
         double Sj[6];
-        for (int k = 0; k < 6; k++) Sj[k] = sm.S[h][j][k];
+        for (int k = 0; k < 6; k++) Sj[k] = sm.v.pre.S[h][j][k];
         double m = rp::dot6(Sj, fI);
         if (d == ldep) m += dm->link_armature[h][lane];
         sm.Mrow[h][moff + d] = m;
@@ -606,7 +627,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         double ax[3] = {dm->key_axis[k][0], dm->key_axis[k][1], dm->key_axis[k][2]};
         double r0[3] = {dm->key_ipos[k][0] - dm->key_jpos[k][0], dm->key_ipos[k][1] - dm->key_jpos[k][1], dm->key_ipos[k][2] - dm->key_jpos[k][2]};
         double r[3], mg[3], t[3];
-        rot_axis(r, ax, sm.ksn[k], sm.kcs[k], r0);
+        rot_axis(r, ax, sm.v.pre.ksn[k], sm.v.pre.kcs[k], r0);
         const double mass = dm->key_mass[k];
         for (int c = 0; c < 3; c++) mg[c] = mass * g3[c];
         rp::cross3(t, r, mg);
@@ -735,7 +756,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
             margin = fmax(gmargin, dm->base_gp.margin);
           } else {
             double ax[3] = {dm->key_axis[key][0], dm->key_axis[key][1], dm->key_axis[key][2]};
-            const double sn = sm.ksn[key], cs = sm.kcs[key];
+            const double sn = sm.v.pre.ksn[key], cs = sm.v.pre.kcs[key];
             // rotation matrix about axis: columns = rotated basis vectors
             double ex[3] = {1, 0, 0}, ey[3] = {0, 1, 0}, ez[3] = {0, 0, 1}, cx[3], cy[3], cz[3];
             rot_axis(cx, ax, sn, cs, ex); rot_axis(cy, ax, sn, cs, ey); rot_axis(cz, ax, sn, cs, ez);
@@ -795,7 +816,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     TICK(5)
     // publish what the contact rows read from the other warp: qacc_smooth / qacc_warmstart of the hand
     // dofs (wbuf / wsb) and of the keys (vak / kfc; kfc is free until the end of the sweep)
-    if (hl) { sm.wbuf[h][lane] = qacc_smooth; sm.wsb[h][lane] = wh; }
+    if (hl) { sm.wbuf[h][lane] = qacc_smooth; sm.v.pre.wsb[h][lane] = wh; }
 #pragma unroll
     for (int s = 0; s < KS; s++) { const int k = tid + KT * s; if (k < NK) { sm.vak[k] = ks_qacc[s]; sm.kfc[k] = wk[s]; } }
     block_sync<NW>();
@@ -844,7 +865,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         for (int d = 0; d < MAXD; d++) {
           double v = 0;
           if (d <= dep) {
-            const double* S = sm.S[ch][sm.anc[ch][link][d]];
+            const double* S = sm.v.pre.S[ch][sm.anc[ch][link][d]];
             double wxp[3];
             rp::cross3(wxp, S, c_pos);
             v = -(dir[0] * (S[3] + wxp[0]) + dir[1] * (S[4] + wxp[1]) + dir[2] * (S[5] + wxp[2]));
@@ -878,8 +899,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         cn.R[r] = r == 0 ? Rn : Rn / fmax(RP_MINVAL, dm->impratio);
         // row velocity -> reference acceleration
         double sv = 0;
-        for (int d = 0; d <= dep; d++) sv += jrow[d] * sm.vh[ch][sm.anc[ch][link][d]];
-        if (c_key >= 0) sv += jk * sm.vk[c_key];
+        for (int d = 0; d <= dep; d++) sv += jrow[d] * sm.v.pre.vh[ch][sm.anc[ch][link][d]];
+        if (c_key >= 0) sv += jk * sm.v.pre.vk[c_key];
         arefr = r == 0 ? -B * sv - K * imp * (c_dist - incl) : -B * sv;
         cn.aref[r] = arefr;
         // u = Minv_chain Jc_r^T (kept in registers for the A block)
@@ -912,7 +933,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         for (int d = 0; d <= dep; d++) {
           const int j = sm.anc[ch][link][d];
           s2 += cn.Jc[r][d] * sm.wbuf[ch][j];
-          s3 += cn.Jc[r][d] * sm.wsb[ch][j];
+          s3 += cn.Jc[r][d] * sm.v.pre.wsb[ch][j];
         }
         if (c_key >= 0) { s2 += cn.Jk[r] * sm.vak[c_key]; s3 += cn.Jk[r] * sm.kfc[c_key]; }
         cn.b[r] = s2 - arefr;
@@ -969,7 +990,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
             double v = 0;
             if (d <= dep) {
               const int j = sm.anc[ch][link][d];
-              const double* S = sm.S[ch][j];
+              const double* S = sm.v.pre.S[ch][j];
               double wxp[3];
               rp::cross3(wxp, S, c_pos);
               v = -(dir[0] * (S[3] + wxp[0]) + dir[1] * (S[4] + wxp[1]) + dir[2] * (S[5] + wxp[2]));
@@ -1002,8 +1023,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         double vel[3];
         for (int r = 0; r < 3; r++) {
           double sv = 0;
-          for (int d = 0; d <= dep; d++) sv += cn.Jc[r][d] * sm.vh[ch][sm.anc[ch][link][d]];
-          if (c_key >= 0) sv += cn.Jk[r] * sm.vk[c_key];
+          for (int d = 0; d <= dep; d++) sv += cn.Jc[r][d] * sm.v.pre.vh[ch][sm.anc[ch][link][d]];
+          if (c_key >= 0) sv += cn.Jk[r] * sm.v.pre.vk[c_key];
           vel[r] = sv;
         }
         cn.aref[0] = -B * vel[0] - K * imp * (c_dist - incl);
@@ -1033,7 +1054,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
           for (int d = 0; d <= dep; d++) {
             const int j = sm.anc[ch][link][d];
             s2 += cn.Jc[r][d] * sm.wbuf[ch][j];
-            s3 += cn.Jc[r][d] * sm.wsb[ch][j];
+            s3 += cn.Jc[r][d] * sm.v.pre.wsb[ch][j];
           }
           if (c_key >= 0) { s2 += cn.Jk[r] * sm.vak[c_key]; s3 += cn.Jk[r] * sm.kfc[c_key]; }
           cn.b[r] = s2 - cn.aref[r];
@@ -1089,6 +1110,28 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     const int nck = sm.nck;
     const int shared_key = sm.shared_key;
     const int nmine = HANDS ? sm.nhc[h] : 0;
+#if RP_NU > 0
+    // U_c = M^-1 Jc^T (three 26-vectors per contact, lane == dof) for the first RP_NU contacts: turns the
+    // per-update walk along the kinematic chain (index load -> shuffle -> load -> FMA per chain dof, ~115
+    // instructions) into three loads and three FMAs.  Lives in the scratch the contact rows no longer need.
+    if (HANDS) {
+      for (int ci = 0; ci < nmine; ci++) {
+        const int c = sm.hlist[h][ci];
+        if (c < RP_NU) {  // warp-uniform
+          const Contact& cn = sm.u.con[c];
+          const int dep = cn.dep;
+          double u0 = 0, u1 = 0, u2 = 0;
+#pragma unroll 1
+          for (int d = 0; d <= dep; d++) {
+            const double m = Ah[cn.chain[d] * RS + lc];
+            u0 -= m * cn.Jc[0][d]; u1 -= m * cn.Jc[1][d]; u2 -= m * cn.Jc[2][d];
+          }
+          if (hl) { sm.v.U[c][0][lane] = u0; sm.v.U[c][1][lane] = u1; sm.v.U[c][2][lane] = u2; }
+        }
+      }
+      __syncwarp();
+    }
+#endif
     // va = Minv J^T f ; cost = 0.5 f'(J va) + 0.5 sum R f^2 + f'b
     double va = 0;
     double improvement0 = 0;  // contribution of the closed-form key rows to the first sweep
@@ -1194,7 +1237,33 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
           const double fbase = fr_b + fr_R * fr_f;  // f only changes at the lane's own commit
           const double fr_lo = -fr_hi;
           const double* prow = Ah + lc;
-#if RP_FR_CHAIN
+#if RP_FR_SKIP
+          // Only rows whose force actually changes are stepped.  Every lane evaluates the update of its own row
+          // against the current va; a ballot finds the first row at or after the cursor with a non-zero change,
+          // that row commits and broadcasts, and the search resumes behind it.  The rows skipped in between
+          // would have committed a change of exactly zero at their turn (nothing moved since their candidate
+          // was evaluated), so the iterates are bit-identical to the row-by-row sweep.  In the bench workload
+          // 86 % of the friction-loss updates are such no-ops (rows saturated at +-frictionloss): a sweep costs
+          // ~4 serial steps per hand instead of 26.
+          {
+            const double* const pcol = Ah + lc;
+            int cursor = 0;
+            while (true) {
+              const double res = fbase + va;
+              const double x = fr_f - res * fr_ARi;
+              double fx = x < fr_lo ? fr_lo : x;
+              fx = x > fr_hi ? fr_hi : fx;
+              const unsigned m = __ballot_sync(FULL, hl && lane >= cursor && fx != fr_f);
+              if (m == 0u) break;
+              const int i = __ffs(m) - 1;
+              const double dl = fx - fr_f;
+              const double dbc = shfl(dl, i);
+              va -= pcol[i * RS] * dbc;
+              if (lane == i) { improvement -= dl * (0.5 * dl * fr_AR + res); fr_f = fx; }
+              cursor = i + 1;
+            }
+          }
+#elif RP_FR_CHAIN
           // short dependency chain: the force change is clamped directly, dl = clamp(-(fbase + va) / AR,
           // lo - f, hi - f), so a row costs FMA -> compare/select -> shuffle -> FMA on the critical path
           const double fq = -(fbase * fr_ARi), dlo = fr_lo - fr_f, dhi = fr_hi - fr_f;
@@ -1359,11 +1428,33 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
               rp::EllPre pre;
               rp::pgs_elliptic_pre(pre, Ab, fold, cmu);
 #endif
+#if RP_JV_GATHER
+              // J*va by gathering the (at most MAXD) chain entries of va with independent shuffles and summing
+              // them redundantly on every lane (Jc[][d] and chain[d] are zero-padded past the chain): one
+              // shuffle latency plus five dependent FMAs instead of five dependent shuffle + add rounds
+              {
+                const unsigned long long c0 = *reinterpret_cast<const unsigned long long*>(cn.chain);
+                const unsigned long long c1 = *reinterpret_cast<const unsigned long long*>(cn.chain + 8);
+                double pa[3] = {0, 0, 0}, pb[3] = {0, 0, 0};
+#pragma unroll
+                for (int d = 0; d < MAXD; d++) {
+                  const int j = (int)((d < 8 ? c0 >> (8 * d) : c1 >> (8 * (d - 8))) & 0xffull);
+                  const double vj = shfl(va, j);
+#pragma unroll
+                  for (int r = 0; r < 3; r++) {
+                    if (d & 1) pb[r] = fma(cn.Jc[r][d], vj, pb[r]); else pa[r] = fma(cn.Jc[r][d], vj, pa[r]);
+                  }
+                }
+#pragma unroll
+                for (int r = 0; r < 3; r++) part[r] = pa[r] + pb[r];
+              }
+#else
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
                 for (int r = 0; r < 3; r++) part[r] += __shfl_xor_sync(FULL, part[r], o);
               }
+#endif
               double res[3], f[3];
               const double vak = sm.vak[key >= 0 ? key : 0];
               const double jkm = key >= 0 ? 1.0 : 0.0;
@@ -1389,10 +1480,36 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
               cn.f[0] = f[0]; cn.f[1] = f[1]; cn.f[2] = f[2];  // identical on every lane
               if (df[0] != 0.0 || df[1] != 0.0 || df[2] != 0.0) {  // warp-uniform; an unchanged force moves nothing
                 if (key >= 0) sm.vak[key] = vak + (cn.Jk[0] * df[0] + cn.Jk[1] * df[1] + cn.Jk[2] * df[2]) * cn.invMk;
+#if RP_NU > 0
+                if (c < RP_NU) {
+                  const double* Uc = &sm.v.U[c][0][lc];
+                  va += fma(Uc[2 * NL], df[2], fma(Uc[NL], df[1], Uc[0] * df[0]));
+                } else
+#endif
+                {
                 // hand side: w = Jc^T df on the chain, va += Minv[:,chain] w
                 const double w = j0 * df[0] + j1 * df[1] + j2 * df[2];
                 double acc = 0;
-#if RP_CH_ACC2
+#if RP_CH_PIPE
+                // Software-pipelined: the chain indices come as two packed words, then every shuffle and every
+                // M^-1 load is issued before the first FMA (fully unrolled over MAXD, entries past the chain
+                // contribute zero; chain[] is zero-padded so the shuffle source is always a valid lane).  The
+                // rolled loop pays index load -> shuffle -> load -> FMA serially, about 40 cycles per chain dof.
+                {
+                  const unsigned long long c0 = *reinterpret_cast<const unsigned long long*>(cn.chain);
+                  const unsigned long long c1 = *reinterpret_cast<const unsigned long long*>(cn.chain + 8);
+                  double acc1 = 0;
+#pragma unroll
+                  for (int d = 0; d < MAXD; d++) {
+                    const int j = (int)((d < 8 ? c0 >> (8 * d) : c1 >> (8 * (d - 8))) & 0xffull);
+                    const double wj = shfl(w, j);
+                    const double m = Ah[j * RS + lc];
+                    const double t = d <= dep ? wj : 0.0;
+                    if (d & 1) acc1 = fma(-m, t, acc1); else acc = fma(-m, t, acc);
+                  }
+                  acc += acc1;
+                }
+#elif RP_CH_ACC2
                 // two partial sums: halves the serial length of the accumulation (chain[] is zero-padded)
                 double acc2 = 0;
 #pragma unroll 1
@@ -1412,6 +1529,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
                 }
 #endif
                 va += acc;
+                }
               }
               __syncwarp();
             }
@@ -1708,7 +1826,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
           // key geom centre in the world: body pos rotated about the hinge (angles of the final pass)
           double ax[3] = {dm->key_axis[k][0], dm->key_axis[k][1], dm->key_axis[k][2]};
           double r0[3] = {-dm->key_jpos[k][0], -dm->key_jpos[k][1], -dm->key_jpos[k][2]}, rr[3];
-          rot_axis(rr, ax, sm.ksn[k], sm.kcs[k], r0);
+          rot_axis(rr, ax, sm.v.pre.ksn[k], sm.v.pre.kcs[k], r0);
           double kp[3];
           for (int c = 0; c < 3; c++) kp[c] = dm->key_pos[k][c] + dm->key_jpos[k][c] + rr[c];
           kp[2] += 0.5 * dm->key_half[k][2];

@@ -320,7 +320,7 @@ RP_HD double pgs_elliptic_update(const double* A, const double* res, double* f, 
 // pgs_elliptic_pre while the J*v reduction is still in flight, so that only the residual-dependent
 // operations stay on the serial chain.  Same operations, same order, same results as pgs_elliptic_update.
 struct QcqpPre { double A11, A22, A12, P11, P22, P12; int ok; };
-struct EllPre { double old[3], rA0, rden; QcqpPre q; int lowf, den_ok; };
+struct EllPre { double old[3], rA0, rden, imu2; QcqpPre q; int lowf, den_ok; };
 RP_HD void qcqp2_prepare(QcqpPre& q, const double* Ain, const double* d) {
   q.A11 = Ain[0] * d[0] * d[0]; q.A22 = Ain[3] * d[1] * d[1]; q.A12 = Ain[1] * d[0] * d[1];
   const double det = q.A11 * q.A22 - q.A12 * q.A12;  // (A11 + la) * (A22 + la) - A12^2 at la = 0
@@ -362,6 +362,7 @@ RP_HD void pgs_elliptic_pre(EllPre& p, const double* A, const double* f, double 
   p.rden = rcp(denom);  // unused when !den_ok
   const double Ac[4] = {A[4], A[5], A[7], A[8]}, fr[2] = {mu, mu};
   qcqp2_prepare(p.q, Ac, fr);
+  p.imu2 = rcp(fr[0] * fr[0]);
 }
 RP_HD double pgs_elliptic_post(const EllPre& p, const double* A, const double* res, double* f, double mu) {
   const double* old = p.old;
@@ -385,7 +386,7 @@ RP_HD double pgs_elliptic_post(const EllPre& p, const double* A, const double* r
     }
     const int flg = qcqp2_solve(vv, p.q, bc, fr, f[0]);
     if (flg) {
-      const double imu2 = rcp(fr[0] * fr[0]);
+      const double imu2 = p.imu2;
       double s = vv[0] * vv[0] * imu2 + vv[1] * vv[1] * imu2;
       s = sqrt(f[0] * f[0] * rcp(fmax(RP_MINVAL, s)));
       vv[0] *= s; vv[1] *= s;

@@ -288,7 +288,7 @@ def test_midi_event_stream_matches_midi_module(task):
     obs = torch.empty((N, model.obs_dim), dtype=torch.float64, device="cuda")
     rew = torch.empty(N, dtype=torch.float64, device="cuda"); dis = torch.empty_like(rew)
     st = torch.empty(N, dtype=torch.uint8, device="cuda")
-    batch.midi_enable(2048)
+    batch.midi_enable(16384)
     batch.reset(None, obs.data_ptr()); ref.reset()
     if hands:
         acts = helpers.twinkle_actions()
