@@ -34,7 +34,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 ENVS_PER_GPU = 4096
-NCU_DRAM_BYTES_PER_LAUNCH = 46.1e6  # profiles/r01_ncu_r01c.csv: dram__bytes_read.sum + dram__bytes_write.sum, 4096 envs
+NCU_DRAM_BYTES_PER_LAUNCH = 48.9e6  # profiles/r01_ncu_r01e.csv: dram__bytes_read.sum + dram__bytes_write.sum, 4096 envs
 SONG = "TwinkleTwinkleRousseau"
 METRIC = "env-steps/sec at 4096 envs/GPU (piano_with_shadow_hands, 10 substeps/step)"
 
