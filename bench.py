@@ -143,7 +143,8 @@ def main():
     config = {"workload": f"piano_with_shadow_hands/{SONG} trim_silence gravcomp primitive_fingertips "
                           f"disable_hand_collisions, {args.envs_per_gpu} envs/GPU, PGS<=50 it tol 1e-8, elliptic, dt=0.005x10",
               "global_envs": args.envs_per_gpu * max(world, 1), "parallelism": f"env-shard x{max(world, 1)}",
-              "l2": "flushed between timed steps (256 MiB device memset)"}
+              "l2": "flushed between timed steps (256 MiB device memset)",
+              "launch_shape": "6 environments per thread block, phase-locked (chosen by batch size; rp_set_block_envs)"}
 
     if args.impl == "reference":
         if rank != 0:

@@ -48,6 +48,7 @@ struct rp_batch {
   double *d_action, *d_out;
   int iterations;
   double tolerance;
+  int block_envs;  // environments per thread block (0: chosen by batch size)
   int64_t launches;
 };
 
@@ -366,6 +367,12 @@ extern "C" int rp_batch_destroy(rp_batch* b) {
   return 0;
 }
 
+extern "C" int rp_set_block_envs(rp_batch* b, int block_envs) {
+  if (block_envs != 0 && block_envs != 1 && block_envs != RP_BLOCK_ENVS) return fail("block_envs must be 0 (auto), 1 or RP_BLOCK_ENVS");
+  b->block_envs = block_envs;
+  return 0;
+}
+
 extern "C" int rp_set_option(rp_batch* b, int iterations, double tolerance) {
   b->iterations = iterations; b->tolerance = tolerance;
   return 0;
@@ -387,7 +394,7 @@ static RpKernelArgs base_args(rp_batch* b, int mode) {
 }
 static int launch(rp_batch* b, const RpKernelArgs& a) {
   CUDA_OK(cudaSetDevice(b->device));
-  CUDA_OK(rp_launch_step(a, b->model->nhand, b->stream));
+  CUDA_OK(rp_launch_step(a, b->model->nhand, b->stream, b->block_envs));
   b->launches++;
   return 0;
 }

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/roboplay.h"
 #include "rp_kernels.h"
 #include "rp_math.cuh"
 
@@ -38,7 +39,7 @@
 #define RP_EULER_FACTOR 0  // tree-sparse L^T D L solve for the Euler step: 1.5k instead of 4.3k instructions but serial; measured 23.4 vs 23.0 ms/step
 #endif
 #ifndef RP_SWIZZLE
-#define RP_SWIZZLE 0  // measured: no effect (23.0 vs 23.0 ms/step)
+#define RP_SWIZZLE 1  // no effect with one environment per block (23.0 vs 23.0 ms/step); 15.50 -> 15.31 with six
 #endif
 #ifndef RP_FR_DEFER
 #define RP_FR_DEFER 0
@@ -57,6 +58,15 @@
 #endif
 #ifndef RP_SW_UNROLL
 #define RP_SW_UNROLL 2
+#endif
+#ifndef RP_EPB
+#define RP_EPB RP_BLOCK_ENVS  // environments per thread block of the phase-locked variant (see rp_step_kernel)
+#endif
+#ifndef RP_EPB_MINBLOCKS
+#define RP_EPB_MINBLOCKS 1  // resident blocks per SM the register allocation has to allow when RP_EPB > 1
+#endif
+#ifndef RP_PHASE_MASK
+#define RP_PHASE_MASK 0  // extra block-wide phase barriers per substep (RP_EPB > 1): 1 before collision, 2 before PGS, 4 after PGS
 #endif
 #ifndef RP_NU
 #define RP_NU 8  // contacts whose M^-1 Jc^T is kept in shared memory (the others walk the kinematic chain)
@@ -79,6 +89,7 @@
 
 namespace {
 
+constexpr int kPhaseExtra = ((RP_PHASE_MASK) & 1) + (((RP_PHASE_MASK) >> 1) & 1) + (((RP_PHASE_MASK) >> 2) & 1);
 constexpr int kFrUnroll = RP_FR_UNROLL, kChUnroll = RP_CH_UNROLL, kSwUnroll = RP_SW_UNROLL;
 
 struct Contact {  // lives in shared memory
@@ -138,15 +149,22 @@ struct Smem {
   int ncon, nraw, overflow, pad;
 };
 
+constexpr size_t kSmemStride = (sizeof(Smem) + 15) / 16 * 16;  // per-environment shared memory (RP_EPB > 1: slot stride)
+
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
-template <int NW>
-__device__ __forceinline__ void block_sync() {
-  if (NW == 1) __syncwarp(); else __syncthreads();
+// Barrier over the threads of one environment.  With several environments per thread block (RP_EPB > 1) each
+// environment owns a named barrier (ids 1..EPB, 64 threads); barrier 0 (__syncthreads) is the block-wide
+// phase barrier.
+template <int NW, int EPB>
+__device__ __forceinline__ void env_sync(int bar_id) {
+  if (NW == 1) __syncwarp();
+  else if (EPB == 1) __syncthreads();
+  else { __syncwarp(); asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); }
 }
 __device__ __forceinline__ void rotq(double* r, const double* q, const double* v) {
   double m[9];
@@ -266,27 +284,39 @@ __device__ __noinline__ double factor_solve(double* R, const unsigned char* moff
 
 // The kernel proper is large; it is written as one function so that lane-owned state stays in
 // registers across the stages of a substep.
-template <int NW>
-__global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_kernel(RpKernelArgs a) {
+// EPB environments share a thread block (EPB x NW warps).  EPB > 1 keeps the environments of a block in step:
+// a block-wide barrier at the top of every substep re-aligns their warps, so that the warps resident on an SM
+// run the same stage (the same instruction lines) at the same time instead of each streaming its own
+// position of a 370 KB program through the instruction caches.
+template <int NW, int EPB>
+__global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (NW == 2 ? RP_MINBLOCKS : 8)) rp_step_kernel(RpKernelArgs a) {
   constexpr bool HANDS = NW == 2;
   constexpr int KT = 32 * NW;               // threads per environment
   constexpr int KS = (NK + KT - 1) / KT;    // keys per thread
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  const int slot = EPB > 1 ? (int)threadIdx.x / KT : 0;  // environment slot inside the block
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw + (size_t)slot * kSmemStride);
+  const int bar_id = slot + 1;
   const RpDevModel* __restrict__ dm = a.dm;
-  const int tid = threadIdx.x;
+  const int tid = (int)threadIdx.x - slot * KT;
   int lane;
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // opaque: keeps the compiler from re-reading S2R in loops
   // warp <-> hand; swizzled by block parity so that the warps of the (usually busier) right hand do not
   // all land on the same two warp schedulers of an SM
 #if RP_SWIZZLE
-  const int h = HANDS ? ((tid >> 5) ^ (blockIdx.x & 1)) : 0;
+  const int h = HANDS ? ((tid >> 5) ^ (EPB > 1 ? ((slot >> 1) & 1) : (int)(blockIdx.x & 1))) : 0;
 #else
   const int h = HANDS ? (tid >> 5) : 0;
 #endif
-  if ((int)blockIdx.x >= a.nenv) return;
+  // block-wide phase barriers every thread of the block has to pass: one per iteration of the substep loop
+  const int nsub_loop = a.mode == RP_MODE_RESET ? 0 : a.nsub;
+  const int eidx = (int)blockIdx.x * EPB + slot;
+  if (eidx >= a.nenv) {
+    if (EPB > 1) for (int s2 = 0; s2 <= nsub_loop; s2++) { __syncthreads(); if (s2 < nsub_loop) for (int p = 0; p < kPhaseExtra; p++) __syncthreads(); }
+    return;
+  }
   // longest-expected-first launch order (rp_order_kernel) shortens the tail of the last wave
-  const int env = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
+  const int env = a.order ? a.order[eidx] : eidx;
   const int nvtot = NK + (HANDS ? 2 * NL : 0);
   const int nu = dm->nu;
   double* __restrict__ gq = a.qpos + (size_t)env * nvtot;
@@ -304,7 +334,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     do_reset = (a.step_type_state[env] == RP_STEP_LAST_);
   } else if (a.mode == RP_MODE_RESET) {
     do_reset = a.reset_mask == nullptr ? true : (a.reset_mask[env] != 0);
-    if (!do_reset) return;
+    if (!do_reset) {
+      if (EPB > 1) for (int s2 = 0; s2 <= nsub_loop; s2++) { __syncthreads(); if (s2 < nsub_loop) for (int p = 0; p < kPhaseExtra; p++) __syncthreads(); }
+      return;
+    }
   }
   const int act_dim = dm->act_dim;
   double sustain_prev = 0;  // thread 0: sustain state before this step's action (MIDI sustain events)
@@ -407,10 +440,17 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
 #endif
   // link world pose (kept for the task epilogue)
   double xp[3] = {0, 0, 0}, xq[4] = {1, 0, 0, 0};
-  block_sync<NW>();
+  env_sync<NW, EPB>(bar_id);
 
   // =============================================================================================
-  for (int sub = 0; sub <= nsub; sub++) {
+  for (int sub = 0; sub <= (EPB > 1 ? nsub_loop : nsub); sub++) {
+    if (EPB > 1) {
+      __syncthreads();           // phase barrier: every environment of the block starts the substep together
+      if (sub > nsub) {  // this environment is done (episode reset: no physics), only keeps the barrier count
+        if (sub < nsub_loop) for (int p = 0; p < kPhaseExtra; p++) __syncthreads();
+        continue;
+      }
+    }
     const bool last_pass = (sub == nsub);  // kinematics-only pass for the task epilogue / reset
     if (last_pass && a.mode == RP_MODE_PHYSICS) break;
     // ---------------------------------------------------------------- hand kinematics (by level)
@@ -468,7 +508,11 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         sm.v.pre.vk[k] = vk[s]; sm.v.pre.ksn[k] = sn; sm.v.pre.kcs[k] = cs;
       }
     }
-    if (last_pass) break;
+    if (last_pass) {
+      if (EPB == 1) break;
+      if (sub < nsub_loop) for (int p = 0; p < kPhaseExtra; p++) __syncthreads();  // an episode-reset env among stepping ones
+      continue;
+    }
 
     TICK(0)
     // ------------------------------------------------------------------ publish S, velocities
@@ -697,9 +741,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     const unsigned lm_mask = HANDS ? __ballot_sync(FULL, lm_on) : 0u;
 
     TICK(3)
+    if (EPB > 1 && ((RP_PHASE_MASK) & 1)) __syncthreads();
     // ------------------------------------------------------------------ collision (lane = geom of this warp's hand)
     if (tid == 0) { sm.nraw = 0; sm.ncon = 0; sm.overflow = 0; sm.nck = 0; sm.shared_key = 0; sm.nhc[0] = 0; sm.nhc[H1] = 0; }
-    block_sync<NW>();  // key arrays published; acc scratch of both hands dead (it aliases the contact lists)
+    env_sync<NW, EPB>(bar_id);  // key arrays published; acc scratch of both hands dead (it aliases the contact lists)
     TICK(4)
     if (HANDS) {
       const bool isg = lane < dm->ngeom[h];
@@ -819,7 +864,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     if (hl) { sm.wbuf[h][lane] = qacc_smooth; sm.v.pre.wsb[h][lane] = wh; }
 #pragma unroll
     for (int s = 0; s < KS; s++) { const int k = tid + KT * s; if (k < NK) { sm.vak[k] = ks_qacc[s]; sm.kfc[k] = wk[s]; } }
-    block_sync<NW>();
+    env_sync<NW, EPB>(bar_id);
     TICK(4)
     const int nraw = min(sm.nraw, MAXCON);
     if (sm.nraw > MAXCON) flags |= 1;
@@ -835,7 +880,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         for (int j = 0; j < nraw; j++) rank += (sm.u.raw[j].sortkey < mykey) ? 1 : 0;
         sm.perm[rank] = (signed char)tid;
       }
-      block_sync<NW>();
+      env_sync<NW, EPB>(bar_id);
       const bool rowt = tid < 3 * ncon;
       const int c = rowt ? tid / 3 : 0, r = tid - 3 * c;
       // contact geometry to registers: raw[] and con[] share the same shared memory
@@ -850,7 +895,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         rp::make_frame(c_frame);
         ch = rc.hand; c_geom = rc.geom; c_key = rc.key;
       }
-      block_sync<NW>();
+      env_sync<NW, EPB>(bar_id);
       double u[MAXD], arefr = 0;
       int link = 0, dep = 0;
       if (rowt) {
@@ -917,7 +962,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
           for (int d = 0; d < 16; d++) cn.chain[d] = (signed char)(d <= dep ? sm.anc[ch][link][d] : 0);
         }
       }
-      block_sync<NW>();
+      env_sync<NW, EPB>(bar_id);
       if (rowt) {
         Contact& cn = sm.u.con[c];
         // A[s2][r] = Jc_s2 Minv Jc_r^T + Jk_s2 Jk_r / Mk + R (diagonal)
@@ -939,13 +984,13 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         cn.b[r] = s2 - arefr;
         cn.f[r] = s3 - arefr;
       }
-      block_sync<NW>();
+      env_sync<NW, EPB>(bar_id);
       if (rowt && r == 0) {
         Contact& cn = sm.u.con[c];
         double jar[3] = {cn.f[0], cn.f[1], cn.f[2]}, D[3] = {1.0 / cn.R[0], 1.0 / cn.R[1], 1.0 / cn.R[2]};
         rp::elliptic_primal_force(jar, D, cn.mu, cn.f);
       }
-      block_sync<NW>();
+      env_sync<NW, EPB>(bar_id);
     } else
     if (HANDS && h == 0 && ncon > 0) {  // > 21 contacts: warp 0, lane c builds contact c
       int myrank = -1;
@@ -1105,7 +1150,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         krow[s].f = jar < 0 ? -jar / krow[s].R : 0.0;
       }
     }
-    block_sync<NW>();
+    env_sync<NW, EPB>(bar_id);
     TICK(4)
     const int nck = sm.nck;
     const int shared_key = sm.shared_key;
@@ -1178,7 +1223,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
       cost = warp_sum(cost);
       if (HANDS) {
         if (lane == 0) sm.red[0][h][0] = cost;
-        block_sync<NW>();
+        env_sync<NW, EPB>(bar_id);
         cost = sm.red[0][0][0] + sm.red[0][H1][0];
       }
       const bool keep = !(cost > 0);
@@ -1216,9 +1261,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         }
       }
     }
-    block_sync<NW>();
+    env_sync<NW, EPB>(bar_id);
 
     TICK(7)
+    if (EPB > 1 && ((RP_PHASE_MASK) & 2)) __syncthreads();  // every environment of the block enters the solver together
     // =============================================================== PGS
     // Row order inside a sweep follows MuJoCo: friction-loss dofs, joint limits (keys, then hand
     // joints), contacts.  The two hands are independent islands unless they touch the same key, so
@@ -1388,7 +1434,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
             __syncwarp();
           }
         }
-        if (HANDS && shared_key) block_sync<NW>();
+        if (HANDS && shared_key) env_sync<NW, EPB>(bar_id);
         if (HANDS) {
           // ---- hand limit rows
           const double lbase = lm_b + lm_R * lm_f;
@@ -1533,14 +1579,14 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
               }
               __syncwarp();
             }
-            if (shared_key) block_sync<NW>();
+            if (shared_key) env_sync<NW, EPB>(bar_id);
           }
         }
     TICK(10)
         improvement = warp_sum(improvement);
         if (HANDS) {
           if (lane == 0) sm.red[iter & 1][h][1] = improvement;
-          block_sync<NW>();
+          env_sync<NW, EPB>(bar_id);
           TICK(11)
           improvement = sm.red[iter & 1][0][1] + sm.red[iter & 1][H1][1];
         }
@@ -1553,6 +1599,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     work += iter * (1 + ncon);
 
     TICK(12)
+    if (EPB > 1 && ((RP_PHASE_MASK) & 4)) __syncthreads();
     // =============================================================== dual -> primal, Euler
     // qacc = qacc_smooth + va ; qfrc_constraint = J^T f
     const double qacc = qacc_smooth + va;
@@ -1574,7 +1621,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         if (cn.key >= 0) sm.kfc[cn.key] += cn.Jk[0] * cn.f[0] + cn.Jk[1] * cn.f[1] + cn.Jk[2] * cn.f[2];
       }
     }
-    block_sync<NW>();
+    env_sync<NW, EPB>(bar_id);
     double kq_acc[KS], kq_frc[KS], kq_smooth[KS];
 #pragma unroll
     for (int s = 0; s < KS; s++) {
@@ -1679,7 +1726,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
         }
       }
     }
-    block_sync<NW>();
+    env_sync<NW, EPB>(bar_id);
   }  // substeps
 
   // ------------------------------------------------------------------ store state
@@ -1691,7 +1738,16 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
       if (k < NK) { gq[k] = qk[s]; gv[k] = vk[s]; gw[k] = wk[s]; bad |= !isfinite(qk[s]) || !isfinite(vk[s]); }
     }
     if (hl) { gq[NK + h * NL + lane] = qh; gv[NK + h * NL + lane] = vh; gw[NK + h * NL + lane] = wh; bad |= !isfinite(qh) || !isfinite(vh); }
-    const int anybad = __syncthreads_or(bad ? 1 : 0);  // also publishes the key sin/cos of the final pass
+    int anybad;
+    if (EPB == 1) {
+      anybad = __syncthreads_or(bad ? 1 : 0);  // also publishes the key sin/cos of the final pass
+    } else {
+      if (tid == 0) sm.pad = 0;
+      env_sync<NW, EPB>(bar_id);
+      if (bad) atomicOr(&sm.pad, 1);
+      env_sync<NW, EPB>(bar_id);
+      anybad = sm.pad;
+    }
     if (anybad) flags |= 2;
     if (tid == 0 && a.diag) { a.diag[3 * env + 0] = ncon_last; a.diag[3 * env + 1] = niter_last; a.diag[3 * env + 2] = flags; }
     if (tid == 0 && a.work) a.work[env] = work;
@@ -1795,7 +1851,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 2 ? RP_MINBLOCKS : 8) rp_step_k
     sq = warp_sum(sq); xent = warp_sum(xent); pw = warp_sum(pw);
     if (HANDS) {
       if (lane == 0) { double* r = sm.red[0][h]; r[2] = sum_on; r[3] = n_on; r[4] = false_pos; r[5] = sq; r[6] = xent; r[7] = pw; r[8] = true_pos; }
-      block_sync<NW>();  // also publishes the sites
+      env_sync<NW, EPB>(bar_id);  // also publishes the sites
       const double* r0 = sm.red[0][0]; const double* r1 = sm.red[0][H1];
       sum_on = r0[2] + r1[2]; n_on = r0[3] + r1[3]; false_pos = r0[4] + r1[4]; sq = r0[5] + r1[5]; xent = r0[6] + r1[6]; pw = r0[7] + r1[7]; true_pos = r0[8] + r1[8];
     }
@@ -1943,25 +1999,41 @@ cudaError_t rp_launch_order(const int32_t* work, int32_t* order, int n, cudaStre
 }
 
 // ------------------------------------------------------------------------------------------------
-size_t rp_kernel_smem_bytes() { return sizeof(Smem); }
+size_t rp_kernel_smem_bytes() { return kSmemStride * RP_EPB; }
 
-cudaError_t rp_launch_step(const RpKernelArgs& a, int nhand, cudaStream_t stream) {
-  const size_t smem = sizeof(Smem);
-  static bool configured[2] = {false, false};
-  if (nhand == 2) {
-    if (!configured[0]) {
-      cudaError_t e = cudaFuncSetAttribute(rp_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      configured[0] = true;
-    }
-    rp_step_kernel<2><<<a.nenv, 64, smem, stream>>>(a);
-  } else {
-    if (!configured[1]) {
-      cudaError_t e = cudaFuncSetAttribute(rp_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      configured[1] = true;
-    }
-    rp_step_kernel<1><<<a.nenv, 32, smem, stream>>>(a);
+template <int EPB>
+static cudaError_t launch_hands(const RpKernelArgs& a, cudaStream_t stream) {
+  static bool configured = false;
+  const size_t smem = kSmemStride * EPB;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(rp_step_kernel<2, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
   }
+  rp_step_kernel<2, EPB><<<(a.nenv + EPB - 1) / EPB, 64 * EPB, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// block_envs: environments per thread block for the hands kernel (1 or RP_EPB; 0 = choose by batch size: the
+// phase-locked RP_EPB-environment blocks need at least two full waves of blocks to pay off).
+cudaError_t rp_launch_step(const RpKernelArgs& a, int nhand, cudaStream_t stream, int block_envs) {
+  if (nhand == 2) {
+    int epb = block_envs;
+    if (epb <= 0) {
+      int dev = 0, sms = 148;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      epb = a.nenv >= 2 * sms * RP_EPB ? RP_EPB : 1;
+    }
+    if (epb != 1 && epb != RP_EPB) return cudaErrorInvalidValue;
+    return epb == 1 ? launch_hands<1>(a, stream) : launch_hands<RP_EPB>(a, stream);
+  }
+  static bool configured = false;
+  const size_t smem = kSmemStride;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(rp_step_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  rp_step_kernel<1, 1><<<a.nenv, 32, smem, stream>>>(a);
   return cudaGetLastError();
 }

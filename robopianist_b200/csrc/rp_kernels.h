@@ -58,5 +58,5 @@ struct RpKernelArgs {
 };
 
 size_t rp_kernel_smem_bytes();
-cudaError_t rp_launch_step(const RpKernelArgs& a, int nhand, cudaStream_t stream);
+cudaError_t rp_launch_step(const RpKernelArgs& a, int nhand, cudaStream_t stream, int block_envs);
 cudaError_t rp_launch_order(const int32_t* work, int32_t* order, int n, cudaStream_t stream);

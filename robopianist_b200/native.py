@@ -21,7 +21,7 @@ EXPORTS = [
     "rp_last_error", "rp_version", "rp_model_create", "rp_model_destroy", "rp_obs_dim", "rp_action_dim",
     "rp_reward_terms", "rp_batch_create", "rp_batch_destroy", "rp_set_option", "rp_reset", "rp_step",
     "rp_step_host", "rp_physics_step", "rp_get_state", "rp_set_state", "rp_get_diag", "rp_get_aux",
-    "rp_launch_count", "rp_step_staged", "rp_host_buffers", "rp_get_metrics", "rp_midi_enable", "rp_get_midi",
+    "rp_launch_count", "rp_step_staged", "rp_host_buffers", "rp_get_metrics", "rp_midi_enable", "rp_get_midi", "rp_set_block_envs",
 ]
 
 
@@ -60,6 +60,7 @@ def lib():
         L.rp_host_buffers.argtypes = [vp, C.POINTER(dp), C.POINTER(dp)]
         L.rp_get_metrics.argtypes = [vp, dp]
         L.rp_midi_enable.argtypes = [vp, C.c_int]
+        L.rp_set_block_envs.argtypes = [vp, C.c_int]
         L.rp_get_midi.argtypes = [vp, C.POINTER(C.c_uint32), ip]
         L.rp_launch_count.restype = C.c_int64
         L.rp_launch_count.argtypes = [vp]
@@ -125,6 +126,10 @@ class Batch:
 
     def set_option(self, iterations=-1, tolerance=-1.0):
         _check(lib().rp_set_option(self.ptr, iterations, tolerance))
+
+    def set_block_envs(self, block_envs=0):
+        """Environments per thread block of the step kernel: 0 auto, 1, or 6 (rp_set_block_envs)."""
+        _check(lib().rp_set_block_envs(self.ptr, int(block_envs)))
 
     def reset(self, mask_ptr=None, obs_ptr=None):
         _check(lib().rp_reset(self.ptr, mask_ptr, obs_ptr))

@@ -1,4 +1,5 @@
 """Shared builders for the tests (scene, song tables, oracle / native handles)."""
+import os
 from pathlib import Path
 
 import numpy as np
@@ -28,4 +29,7 @@ def make_native(task="piano_with_shadow_hands", song="TwinkleTwinkleRousseau", g
     goal, fing = song_tables(song)
     kind = 0 if task == "piano_with_shadow_hands" else 1
     model = native.Model(fm, goal, fing, kind=kind, n_steps_lookahead=lookahead, **task_kw)
-    return fm, model, native.Batch(model, nenv)
+    batch = native.Batch(model, nenv)
+    if os.environ.get("ROBOPLAY_BLOCK_ENVS"):  # launch shape under test (results must not depend on it)
+        batch.set_block_envs(int(os.environ["ROBOPLAY_BLOCK_ENVS"]))
+    return fm, model, batch

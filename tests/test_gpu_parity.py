@@ -314,3 +314,57 @@ def test_midi_event_stream_matches_midi_module(task):
     batch.step(_dev(np.tile(acts[0] * 0, (N, 1))).data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
     assert all(len(m) == 0 for m in batch.get_midi(fm.meta["timestep"]))
     batch.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["substeps", "heterogeneous", "shared_key", "task", "midi"])
+def test_six_envs_per_block_match_the_oracle(monkeypatch, case):
+    """The phase-locked launch shape (rp_set_block_envs(6): six environments per thread block, named barriers
+    per environment, a block-wide barrier per substep) against the same oracles as the default shape."""
+    monkeypatch.setenv("ROBOPLAY_BLOCK_ENVS", "6")
+    if case == "substeps":
+        test_hands_1000_substeps_match_oracle()
+    elif case == "heterogeneous":
+        test_heterogeneous_envs_match_their_own_oracles()
+    elif case == "shared_key":
+        test_key_shared_by_both_hands_matches_oracle()
+    elif case == "task":
+        test_task_layer_matches_reference_logic("TwinkleTwinkleRousseau", 1)
+    else:
+        test_midi_event_stream_matches_midi_module("piano_with_shadow_hands")
+
+
+@pytest.mark.gpu
+def test_launch_shapes_are_bitwise_identical():
+    """13 environments (three 6-environment blocks, the last one partly empty) stepped through an episode end
+    (auto-reset of some environments only: wrong-press termination), a masked reset and plain physics steps:
+    every output of the 6-per-block shape equals the 1-per-block shape bit for bit."""
+    N = 13
+    outs = []
+    for be in (1, 6):
+        fm, model, batch = helpers.make_native("piano_with_shadow_hands", nenv=N, wrong_press_termination=True)
+        batch.set_block_envs(be)
+        lo = np.concatenate([fm.actuator_ctrlrange[:, 0], [0.0]]); hi = np.concatenate([fm.actuator_ctrlrange[:, 1], [1.0]])
+        rng = np.random.default_rng(5)
+        acts = helpers.twinkle_actions()
+        obs = torch.empty((N, model.obs_dim), dtype=torch.float64, device="cuda")
+        rew = torch.empty(N, dtype=torch.float64, device="cuda"); dis = torch.empty_like(rew)
+        st = torch.empty(N, dtype=torch.uint8, device="cuda")
+        batch.reset(None, obs.data_ptr())
+        rec = []
+        for t in range(30):
+            a = np.clip(acts[t] + rng.normal(0, 0.1, (N, 45)) * (hi - lo) / 2, lo, hi)
+            batch.step(_dev(a).data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
+            rec += [obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), st.cpu().numpy().copy()]
+            if t == 12:
+                mask = torch.tensor([i % 3 == 0 for i in range(N)], dtype=torch.uint8, device="cuda")
+                batch.reset(mask.data_ptr(), obs.data_ptr())
+                rec.append(obs.cpu().numpy().copy())
+        batch.physics_step(_dev(a[:, :44]).data_ptr(), 3)
+        q, v, w, ti = batch.get_state()
+        rec += [q, v, w, ti]
+        outs.append(rec)
+        batch.close()
+    assert any(x.dtype == np.uint8 and (x == 2).any() for x in outs[0])  # some environments ended their episode early
+    for x, y in zip(*outs):
+        assert np.array_equal(x, y)
