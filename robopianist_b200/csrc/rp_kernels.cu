@@ -65,6 +65,10 @@
 #ifndef RP_EPB_MINBLOCKS
 #define RP_EPB_MINBLOCKS 1  // resident blocks per SM the register allocation has to allow when RP_EPB > 1
 #endif
+#ifndef RP_PHASE_EVERY
+#define RP_PHASE_EVERY 1  // block-wide phase barrier at the top of every RP_PHASE_EVERY-th substep (RP_EPB > 1)
+#endif
+#define RP_PHASE_AT(sub_) ((sub_) % (RP_PHASE_EVERY) == 0)
 #ifndef RP_PHASE_MASK
 #define RP_PHASE_MASK 0  // extra block-wide phase barriers per substep (RP_EPB > 1): 1 before collision, 2 before PGS, 4 after PGS
 #endif
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
   const int nsub_loop = a.mode == RP_MODE_RESET ? 0 : a.nsub;
   const int eidx = (int)blockIdx.x * EPB + slot;
   if (eidx >= a.nenv) {
-    if (EPB > 1) for (int s2 = 0; s2 <= nsub_loop; s2++) { __syncthreads(); if (s2 < nsub_loop) for (int p = 0; p < kPhaseExtra; p++) __syncthreads(); }
+    if (EPB > 1) for (int s2 = 0; s2 <= nsub_loop; s2++) { if (RP_PHASE_AT(s2)) __syncthreads(); if (s2 < nsub_loop) for (int p = 0; p < kPhaseExtra; p++) __syncthreads(); }
     return;
   }
   // longest-expected-first launch order (rp_order_kernel) shortens the tail of the last wave
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
   } else if (a.mode == RP_MODE_RESET) {
     do_reset = a.reset_mask == nullptr ? true : (a.reset_mask[env] != 0);
     if (!do_reset) {
-      if (EPB > 1) for (int s2 = 0; s2 <= nsub_loop; s2++) { __syncthreads(); if (s2 < nsub_loop) for (int p = 0; p < kPhaseExtra; p++) __syncthreads(); }
+      if (EPB > 1) for (int s2 = 0; s2 <= nsub_loop; s2++) { if (RP_PHASE_AT(s2)) __syncthreads(); if (s2 < nsub_loop) for (int p = 0; p < kPhaseExtra; p++) __syncthreads(); }
       return;
     }
   }
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
   // =============================================================================================
   for (int sub = 0; sub <= (EPB > 1 ? nsub_loop : nsub); sub++) {
     if (EPB > 1) {
-      __syncthreads();           // phase barrier: every environment of the block starts the substep together
+      if (RP_PHASE_AT(sub)) __syncthreads();  // phase barrier: the environments of the block start the substep together
       if (sub > nsub) {  // this environment is done (episode reset: no physics), only keeps the barrier count
         if (sub < nsub_loop) for (int p = 0; p < kPhaseExtra; p++) __syncthreads();
         continue;
