@@ -34,7 +34,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 ENVS_PER_GPU = 4096
-NCU_DRAM_BYTES_PER_LAUNCH = 48.9e6  # profiles/r01_ncu_r01e.csv: dram__bytes_read.sum + dram__bytes_write.sum, 4096 envs
+NCU_DRAM_BYTES_PER_LAUNCH = 57.0e6  # profiles/r01_ncu_r01g.csv: dram__bytes_read.sum + dram__bytes_write.sum, 4096 envs
 SONG = "TwinkleTwinkleRousseau"
 METRIC = "env-steps/sec at 4096 envs/GPU (piano_with_shadow_hands, 10 substeps/step)"
 
@@ -144,7 +144,7 @@ def main():
                           f"disable_hand_collisions, {args.envs_per_gpu} envs/GPU, PGS<=50 it tol 1e-8, elliptic, dt=0.005x10",
               "global_envs": args.envs_per_gpu * max(world, 1), "parallelism": f"env-shard x{max(world, 1)}",
               "l2": "flushed between timed steps (256 MiB device memset)",
-              "launch_shape": "6 environments per thread block, phase-locked (chosen by batch size; rp_set_block_envs)"}
+              "launch_shape": "3 environments per thread block (2 blocks per SM), phase-locked per substep (chosen by batch size; rp_set_block_envs)"}
 
     if args.impl == "reference":
         if rank != 0:

@@ -169,7 +169,7 @@ int rp_get_midi(rp_batch *, uint32_t *events, int32_t *counts);
 /* Launch shape of the step kernel (results do not depend on it): environments per thread block, 1 or
  * RP_BLOCK_ENVS (blocks whose environments run each substep in step with each other, which shares their
  * instruction fetches); 0 = chosen from the batch size (default). */
-#define RP_BLOCK_ENVS 6
+#define RP_BLOCK_ENVS 3
 int rp_set_block_envs(rp_batch *, int block_envs);
 
 int64_t rp_launch_count(const rp_batch *); /* kernels launched by this batch so far */

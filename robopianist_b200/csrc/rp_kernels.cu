@@ -1,4 +1,4 @@
-// rp_kernels.cu — sm_100a step kernel: one thread block per environment, fp64.
+// rp_kernels.cu — sm_100a step kernel: 64 threads per environment, RP_BLOCK_ENVS environments per block, fp64.
 //
 // Replaces the reference's per-control-step host loop
 //   before_step -> 10 x physics.step() -> after_step -> observables -> reward -> termination
@@ -63,7 +63,7 @@
 #define RP_EPB RP_BLOCK_ENVS  // environments per thread block of the phase-locked variant (see rp_step_kernel)
 #endif
 #ifndef RP_EPB_MINBLOCKS
-#define RP_EPB_MINBLOCKS 1  // resident blocks per SM the register allocation has to allow when RP_EPB > 1
+#define RP_EPB_MINBLOCKS (RP_EPB <= 6 ? 6 / RP_EPB : 1)  // resident blocks per SM the register allocation has to allow (six environments per SM)
 #endif
 #ifndef RP_PHASE_EVERY
 #define RP_PHASE_EVERY 1  // block-wide phase barrier at the top of every RP_PHASE_EVERY-th substep (RP_EPB > 1)
@@ -2026,7 +2026,7 @@ cudaError_t rp_launch_step(const RpKernelArgs& a, int nhand, cudaStream_t stream
     if (epb <= 0) {
       int dev = 0, sms = 148;
       if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      epb = a.nenv >= 2 * sms * RP_EPB ? RP_EPB : 1;
+      epb = a.nenv >= 2 * sms * 6 ? RP_EPB : 1;  // two waves at six environments per SM
     }
     if (epb != 1 && epb != RP_EPB) return cudaErrorInvalidValue;
     return epb == 1 ? launch_hands<1>(a, stream) : launch_hands<RP_EPB>(a, stream);

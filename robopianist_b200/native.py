@@ -25,6 +25,9 @@ EXPORTS = [
 ]
 
 
+BLOCK_ENVS = 3  # RP_BLOCK_ENVS of include/roboplay.h (the phase-locked launch shape)
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -128,7 +131,7 @@ class Batch:
         _check(lib().rp_set_option(self.ptr, iterations, tolerance))
 
     def set_block_envs(self, block_envs=0):
-        """Environments per thread block of the step kernel: 0 auto, 1, or 6 (rp_set_block_envs)."""
+        """Environments per thread block of the step kernel: 0 auto, 1, or BLOCK_ENVS (rp_set_block_envs)."""
         _check(lib().rp_set_block_envs(self.ptr, int(block_envs)))
 
     def reset(self, mask_ptr=None, obs_ptr=None):

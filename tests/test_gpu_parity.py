@@ -318,10 +318,12 @@ def test_midi_event_stream_matches_midi_module(task):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["substeps", "heterogeneous", "shared_key", "task", "midi"])
-def test_six_envs_per_block_match_the_oracle(monkeypatch, case):
-    """The phase-locked launch shape (rp_set_block_envs(6): six environments per thread block, named barriers
-    per environment, a block-wide barrier per substep) against the same oracles as the default shape."""
-    monkeypatch.setenv("ROBOPLAY_BLOCK_ENVS", "6")
+def test_phase_locked_blocks_match_the_oracle(monkeypatch, case):
+    """The phase-locked launch shape (rp_set_block_envs(RP_BLOCK_ENVS): several environments per thread block,
+    named barriers per environment, a block-wide barrier per substep) against the same oracles as the
+    one-environment-per-block shape small batches get by default."""
+    from robopianist_b200 import native
+    monkeypatch.setenv("ROBOPLAY_BLOCK_ENVS", str(native.BLOCK_ENVS))
     if case == "substeps":
         test_hands_1000_substeps_match_oracle()
     elif case == "heterogeneous":
@@ -336,12 +338,13 @@ def test_six_envs_per_block_match_the_oracle(monkeypatch, case):
 
 @pytest.mark.gpu
 def test_launch_shapes_are_bitwise_identical():
-    """13 environments (three 6-environment blocks, the last one partly empty) stepped through an episode end
+    """13 environments (multi-environment blocks, the last one partly empty) stepped through an episode end
     (auto-reset of some environments only: wrong-press termination), a masked reset and plain physics steps:
-    every output of the 6-per-block shape equals the 1-per-block shape bit for bit."""
+    every output of the phase-locked shape equals the 1-per-block shape bit for bit."""
+    from robopianist_b200 import native
     N = 13
     outs = []
-    for be in (1, 6):
+    for be in (1, native.BLOCK_ENVS):
         fm, model, batch = helpers.make_native("piano_with_shadow_hands", nenv=N, wrong_press_termination=True)
         batch.set_block_envs(be)
         lo = np.concatenate([fm.actuator_ctrlrange[:, 0], [0.0]]); hi = np.concatenate([fm.actuator_ctrlrange[:, 1], [1.0]])
