@@ -951,9 +951,11 @@ static double row_residual(orc_data *d, int i) {
   d->mac_count += n;
   return res;
 }
-void orc_solve(const orc_model *o, orc_data *d) {
+/* orc_solve = orc_solve_init (b, warm start, cost test) + orc_solve_iterate (the PGS sweeps); split so that the
+ * tests can read the solver's starting point (efc_b, warm-start efc_force) before the sweeps overwrite it. */
+void orc_solve_init(const orc_model *o, orc_data *d) {
   const rp_flat_model *m = &o->m;
-  int nv = m->nv, nefc = d->nefc, cap = d->efc_cap;
+  int nv = m->nv, nefc = d->nefc;
   double *jar = (double *)calloc((size_t)nefc + 1, sizeof(double));
   /* b = J*qacc_smooth - aref */
   for (int i = 0; i < nefc; i++) {
@@ -978,6 +980,11 @@ void orc_solve(const orc_model *o, orc_data *d) {
     }
     if (cost > 0) memset(d->efc_force, 0, sizeof(double) * nefc);
   }
+  free(jar);
+}
+void orc_solve_iterate(const orc_model *o, orc_data *d) {
+  const rp_flat_model *m = &o->m;
+  int nv = m->nv, nefc = d->nefc, cap = d->efc_cap;
   double scale = 1.0 / (m->meaninertia * (nv > 1 ? nv : 1));
   int iter = 0;
   d->solver_improvement = 0;
@@ -1062,7 +1069,10 @@ void orc_solve(const orc_model *o, orc_data *d) {
   memcpy(d->qacc, d->qfrc_constraint, sizeof(double) * nv);
   solve_M(o, d->L, nv, d->qacc);
   for (int j = 0; j < nv; j++) d->qacc[j] += d->qacc_smooth[j];
-  free(jar);
+}
+void orc_solve(const orc_model *o, orc_data *d) {
+  orc_solve_init(o, d);
+  orc_solve_iterate(o, d);
 }
 
 /* ---------------------------------------- steps -------------------------------------------- */
@@ -1076,16 +1086,21 @@ void orc_step1(const orc_model *o, orc_data *d) {
   orc_velocity(o, d);
 }
 /* mj_step2 = mj_fwdActuation + mj_fwdAcceleration + mj_fwdConstraint + mj_Euler */
-void orc_step2(const orc_model *o, orc_data *d) {
-  const rp_flat_model *m = &o->m;
-  int nv = m->nv;
-  double h = m->timestep;
+/* mj_fwdActuation + mj_fwdAcceleration: qfrc_smooth, qacc_smooth */
+void orc_smooth(const orc_model *o, orc_data *d) {
+  int nv = o->m.nv;
   orc_actuation(o, d);
   for (int j = 0; j < nv; j++) {
     d->qfrc_smooth[j] = d->qfrc_passive[j] - d->qfrc_bias[j] + d->qfrc_actuator[j] + d->qfrc_applied[j];
     d->qacc_smooth[j] = d->qfrc_smooth[j];
   }
   solve_M(o, d->L, nv, d->qacc_smooth);
+}
+void orc_step2(const orc_model *o, orc_data *d) {
+  const rp_flat_model *m = &o->m;
+  int nv = m->nv;
+  double h = m->timestep;
+  orc_smooth(o, d);
   orc_solve(o, d);
   /* mj_Euler with implicit joint damping: (M + h*diag(damping)) a = qfrc_smooth + qfrc_constraint */
   double *a = (double *)malloc(sizeof(double) * nv);

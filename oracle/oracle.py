@@ -38,7 +38,8 @@ def lib():
         L.orc_data_create.argtypes = [C.c_void_p]
         L.orc_data_destroy.argtypes = [C.c_void_p]
         for fn in ("orc_kinematics", "orc_crb", "orc_velocity", "orc_collision", "orc_make_constraint",
-                   "orc_project_constraint", "orc_actuation", "orc_solve", "orc_step1", "orc_step2",
+                   "orc_project_constraint", "orc_actuation", "orc_solve", "orc_solve_init", "orc_solve_iterate",
+                   "orc_smooth", "orc_step1", "orc_step2",
                    "orc_reset"):
             getattr(L, fn).argtypes = [C.c_void_p, C.c_void_p]
             getattr(L, fn).restype = None

@@ -87,6 +87,9 @@
 #ifndef RP_CON_PRE
 #define RP_CON_PRE 1  // residual-independent half of the contact update ahead of the J*v reduction
 #endif
+#ifndef RP_SW_BATCH
+#define RP_SW_BATCH 0  // element updates of a sweep pivot loaded in batches of this size (0: one by one)
+#endif
 #ifndef RP_MINBLOCKS
 #define RP_MINBLOCKS 6
 #endif
@@ -214,6 +217,35 @@ __device__ __noinline__ void sweep_inverse(double* A, const signed char* anc /*[
     const bool upd = lane < NL && lane != k;  // lane k's own row is rewritten after the updates
     const double t = upd ? rowk[lane] * dinv : 0.0;
     const int depk = dep[k], endk = k + sub[k];
+#if RP_SW_BATCH
+    // Row `lane` changes only if it is an ancestor of k or inside k's subtree (t != 0; the others would
+    // subtract exact zeros).  The element updates of one pivot are independent, but written one by one the
+    // compiler has to assume that the store of element i aliases the loads of element i + 1 and serialises
+    // LDS -> FMA -> STS per element; loading a batch first gives the shared-memory pipe RP_SW_BATCH
+    // independent element updates in flight.  Entries past the end re-load the last valid one and are not stored.
+    if (upd && t != 0.0) {
+      constexpr int B = RP_SW_BATCH;
+#pragma unroll 1
+      for (int d0 = 0; d0 < depk; d0 += B) {
+        int idx[B];
+        double r[B], m[B];
+#pragma unroll
+        for (int u = 0; u < B; u++) idx[u] = anc[k * MAXD + min(d0 + u, depk - 1)];
+#pragma unroll
+        for (int u = 0; u < B; u++) { r[u] = rowk[idx[u]]; m[u] = myrow[idx[u]]; }
+#pragma unroll
+        for (int u = 0; u < B; u++) if (d0 + u < depk) myrow[idx[u]] = m[u] - r[u] * t;
+      }
+#pragma unroll 1
+      for (int i0 = k + 1; i0 < endk; i0 += B) {
+        double r[B], m[B];
+#pragma unroll
+        for (int u = 0; u < B; u++) { const int i = min(i0 + u, endk - 1); r[u] = rowk[i]; m[u] = myrow[i]; }
+#pragma unroll
+        for (int u = 0; u < B; u++) if (i0 + u < endk) myrow[i0 + u] = m[u] - r[u] * t;
+      }
+    }
+#else
     if (upd) {
       for (int d = 0; d < depk; d++) {
         const int i = anc[k * MAXD + d];
@@ -222,6 +254,7 @@ __device__ __noinline__ void sweep_inverse(double* A, const signed char* anc /*[
 #pragma unroll kSwUnroll
       for (int i = k + 1; i < endk; i++) myrow[i] -= rowk[i] * t;
     }
+#endif
     __syncwarp();
     if (upd) { myrow[k] = t; A[k * RS + lane] = t; }
     if (lane == k) A[k * RS + k] = -dinv;
