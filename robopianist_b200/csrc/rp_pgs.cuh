@@ -3,9 +3,9 @@
 // DESIGN.md §5 "next steps" (setup kernel -> this solver -> finish kernel).  NOT on the product path yet:
 // the fused step kernel (rp_kernels.cu) carries its own copy of this solve, spread over two warps.
 //
-// What it restates: MuJoCo's mj_solPGS with elliptic cones as the reference's mj_step runs it
-// (oracle/oracle.c: orc_solve_iterate), on the representation the step kernel builds instead of a dense
-// efc_J / efc_AR: per hand M^-1 (26 x 26), scalar rows for the 52 friction-loss dofs and the active joint
+// What it restates: MuJoCo's mj_solPGS with elliptic cones as the reference's mj_step runs it (the tests pin
+// it to the dense restatement of the CPU oracle (oracle/)), on the representation the step kernel builds
+// instead of a dense efc_J / efc_AR: per hand M^-1 (26 x 26), scalar rows for the 52 friction-loss dofs and the active joint
 // limits, the limit rows of keys that carry contacts, and per contact the 3 x 3 block, the chain Jacobian
 // and U = M^-1 Jc^T.  Keys without contacts are 1 x 1 islands: their limit row is solved exactly by the
 // producer of the problem (one update, then it never moves again) and enters only through `improvement0`.
@@ -50,10 +50,14 @@ struct PgsView {
   size_t stride;  // number of environments in the buffer
   int env;
   RP_HD double& at(int e) const { return P[(size_t)e * stride + env]; }
+  RP_HD double ld(int e) const { return P[(size_t)e * stride + env]; }  // element the solve never writes
 };
 
-// One environment's solve.  va: 2*NL doubles of scratch (va[i * va_stride]); returns the number of sweeps.
-RP_HD int pgs_solve_env(const PgsView p, int maxiter, double tol, double solver_scale, double* va, int va_stride) {
+// One environment's solve.  View: anything with `double& at(int element) const` (PgsView reads the global
+// buffer; the kernel's staged view keeps the scalar rows in shared memory).  va: 2*NL doubles of scratch
+// (va[i * va_stride]); returns the number of sweeps.
+template <class View>
+RP_HD int pgs_solve_env(const View p, int maxiter, double tol, double solver_scale, double* va, int va_stride) {
   const int NL = RP_NL;
   const int ncon = (int)p.at(PG_NCON), nck = (int)p.at(PG_NCK);
   for (int i = 0; i < 2 * NL; i++) va[i * va_stride] = p.at(PG_VA + i);
@@ -63,7 +67,7 @@ RP_HD int pgs_solve_env(const PgsView p, int maxiter, double tol, double solver_
     // ---- friction-loss rows
     for (int i = 0; i < 2 * NL; i++) {
       const int r = PG_FR + 5 * i;
-      const double R = p.at(r), b = p.at(r + 1), AR = p.at(r + 2), ARi = p.at(r + 3), hi = p.at(r + 4);
+      const double R = p.ld(r), b = p.ld(r + 1), AR = p.ld(r + 2), ARi = p.ld(r + 3), hi = p.ld(r + 4);
       const double f = p.at(PG_FR_F + i);
       const double res = b + R * f + va[i * va_stride];
       const double x = f - res * ARi;
@@ -72,7 +76,7 @@ RP_HD int pgs_solve_env(const PgsView p, int maxiter, double tol, double solver_
       if (fx != f) {
         const double dl = fx - f;
         const int h = i / NL, col = i - h * NL;
-        for (int j = 0; j < NL; j++) va[(h * NL + j) * va_stride] += p.at(PG_MINV + (h * NL + col) * NL + j) * dl;
+        for (int j = 0; j < NL; j++) va[(h * NL + j) * va_stride] += p.ld(PG_MINV + (h * NL + col) * NL + j) * dl;
         improvement -= dl * (0.5 * dl * AR + res);
         p.at(PG_FR_F + i) = fx;
       }
@@ -80,8 +84,8 @@ RP_HD int pgs_solve_env(const PgsView p, int maxiter, double tol, double solver_
     // ---- limit rows of keys that carry contacts
     for (int c = 0; c < nck; c++) {
       const int r = PG_CK + 8 * c;
-      const double active = p.at(r + 1), J = p.at(r + 2), R = p.at(r + 3), b = p.at(r + 4), AR = p.at(r + 5),
-                   ARi = p.at(r + 6), invM = p.at(r + 7);
+      const double active = p.ld(r + 1), J = p.ld(r + 2), R = p.ld(r + 3), b = p.ld(r + 4), AR = p.ld(r + 5),
+                   ARi = p.ld(r + 6), invM = p.ld(r + 7);
       const double f = p.at(PG_CK_F + c), vak = p.at(PG_CK_VA + c);
       const double res = b + R * f + J * vak;
       double fn = f - res * ARi;
@@ -94,9 +98,9 @@ RP_HD int pgs_solve_env(const PgsView p, int maxiter, double tol, double solver_
     // ---- hand joint-limit rows
     for (int i = 0; i < 2 * NL; i++) {
       const int r = PG_LM + 5 * i;
-      const double J = p.at(r);
+      const double J = p.ld(r);
       if (J == 0.0) continue;
-      const double R = p.at(r + 1), b = p.at(r + 2), AR = p.at(r + 3), ARi = p.at(r + 4);
+      const double R = p.ld(r + 1), b = p.ld(r + 2), AR = p.ld(r + 3), ARi = p.ld(r + 4);
       const double f = p.at(PG_LM_F + i);
       const double res = b + R * f + J * va[i * va_stride];
       const double x = f - res * ARi;
@@ -105,34 +109,41 @@ RP_HD int pgs_solve_env(const PgsView p, int maxiter, double tol, double solver_
       if (dl != 0.0) {
         const int h = i / NL, col = i - h * NL;
         const double w = J * dl;
-        for (int j = 0; j < NL; j++) va[(h * NL + j) * va_stride] += p.at(PG_MINV + (h * NL + col) * NL + j) * w;
+        for (int j = 0; j < NL; j++) va[(h * NL + j) * va_stride] += p.ld(PG_MINV + (h * NL + col) * NL + j) * w;
       }
       improvement -= dl * (0.5 * dl * AR + res);
       p.at(PG_LM_F + i) = fn;
     }
-    // ---- contacts
+    // ---- contacts.  The record (read-only but for the force) is loaded up front through ld(): on the device
+    // these are independent read-only loads that go out back to back (one memory latency per contact); read
+    // through at() they would be ordered behind the force stores of the previous contact one by one.
     for (int c = 0; c < ncon; c++) {
       const int q = PG_CON + c * PG_CON_STRIDE;
-      const int h = (int)p.at(q + PC_HAND), ck = (int)p.at(q + PC_CK), dep = (int)p.at(q + PC_DEP);
-      const double mu = p.at(q + PC_MU);
-      double A[9], res[3], f[3], old[3];
-      for (int k = 0; k < 9; k++) A[k] = p.at(q + PC_A + k);
+      const int h = (int)p.ld(q + PC_HAND), ck = (int)p.ld(q + PC_CK), dep = (int)p.ld(q + PC_DEP);
+      const double mu = p.ld(q + PC_MU), invMk = p.ld(q + PC_INVMK);
+      double A[9], Rr[3], br[3], jk[3], res[3], f[3], old[3], jc[3][RP_MAXD];
+      int chain[RP_MAXD];
+      for (int k = 0; k < 9; k++) A[k] = p.ld(q + PC_A + k);
+      for (int r = 0; r < 3; r++) { Rr[r] = p.ld(q + PC_R + r); br[r] = p.ld(q + PC_B + r); jk[r] = p.ld(q + PC_JK + r); }
+      for (int d = 0; d < RP_MAXD; d++) {
+        chain[d] = (int)p.ld(q + PC_CHAIN + d);  // zero-padded past the chain (as are the Jacobian entries)
+        for (int r = 0; r < 3; r++) jc[r][d] = p.ld(q + PC_JC + r * RP_MAXD + d);
+      }
       const double vak = ck >= 0 ? p.at(PG_CK_VA + ck) : 0.0;
       for (int r = 0; r < 3; r++) {
         f[r] = old[r] = p.at(q + PC_F + r);
         double s = 0;
-        for (int d = 0; d <= dep; d++) s += p.at(q + PC_JC + r * RP_MAXD + d) * va[(h * NL + (int)p.at(q + PC_CHAIN + d)) * va_stride];
-        res[r] = p.at(q + PC_B + r) + p.at(q + PC_R + r) * f[r] + s + (ck >= 0 ? p.at(q + PC_JK + r) * vak : 0.0);
+        for (int d = 0; d <= dep; d++) s += jc[r][d] * va[(h * NL + chain[d]) * va_stride];
+        res[r] = br[r] + Rr[r] * f[r] + s + (ck >= 0 ? jk[r] * vak : 0.0);
       }
       const double change = pgs_elliptic_update(A, res, f, mu);
       improvement -= change;
       const double df[3] = {f[0] - old[0], f[1] - old[1], f[2] - old[2]};
       for (int r = 0; r < 3; r++) p.at(q + PC_F + r) = f[r];
       if (df[0] != 0.0 || df[1] != 0.0 || df[2] != 0.0) {
-        if (ck >= 0)
-          p.at(PG_CK_VA + ck) = vak + (p.at(q + PC_JK) * df[0] + p.at(q + PC_JK + 1) * df[1] + p.at(q + PC_JK + 2) * df[2]) * p.at(q + PC_INVMK);
+        if (ck >= 0) p.at(PG_CK_VA + ck) = vak + (jk[0] * df[0] + jk[1] * df[1] + jk[2] * df[2]) * invMk;
         for (int j = 0; j < NL; j++)
-          va[(h * NL + j) * va_stride] += fma(p.at(q + PC_U + 2 * NL + j), df[2], fma(p.at(q + PC_U + NL + j), df[1], p.at(q + PC_U + j) * df[0]));
+          va[(h * NL + j) * va_stride] += fma(p.ld(q + PC_U + 2 * NL + j), df[2], fma(p.ld(q + PC_U + NL + j), df[1], p.ld(q + PC_U + j) * df[0]));
       }
     }
     improvement *= solver_scale;
