@@ -2038,14 +2038,22 @@ cudaError_t rp_launch_order(const int32_t* work, int32_t* order, int n, cudaStre
 // ------------------------------------------------------------------------------------------------
 size_t rp_kernel_smem_bytes() { return kSmemStride * RP_EPB; }
 
+// the opt-in to more than 48 KB of dynamic shared memory is per device
+static int current_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < 64 ? dev : 0;
+}
+
 template <int EPB>
 static cudaError_t launch_hands(const RpKernelArgs& a, cudaStream_t stream) {
-  static bool configured = false;
+  static bool configured[64] = {};
+  const int dev = current_device_slot();
   const size_t smem = kSmemStride * EPB;
-  if (!configured) {
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(rp_step_kernel<2, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[dev] = true;
   }
   rp_step_kernel<2, EPB><<<(a.nenv + EPB - 1) / EPB, 64 * EPB, smem, stream>>>(a);
   return cudaGetLastError();
@@ -2064,12 +2072,13 @@ cudaError_t rp_launch_step(const RpKernelArgs& a, int nhand, cudaStream_t stream
     if (epb != 1 && epb != RP_EPB) return cudaErrorInvalidValue;
     return epb == 1 ? launch_hands<1>(a, stream) : launch_hands<RP_EPB>(a, stream);
   }
-  static bool configured = false;
+  static bool configured[64] = {};
+  const int dev = current_device_slot();
   const size_t smem = kSmemStride;
-  if (!configured) {
+  if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(rp_step_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[dev] = true;
   }
   rp_step_kernel<1, 1><<<a.nenv, 32, smem, stream>>>(a);
   return cudaGetLastError();

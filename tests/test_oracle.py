@@ -160,3 +160,82 @@ def test_midi_messages_of_the_reference_restatement(hands):
     for t in range(45):
         ref2.step(acts[t])
     assert np.array_equal(ref.d.qpos, ref2.d.qpos)
+
+
+def test_pgs_fixed_point_satisfies_the_kkt_conditions(hands):
+    """An implementation-independent property of the solve: run to convergence, the PGS forces must satisfy the
+    optimality conditions of MuJoCo's dual problem min 1/2 f'(A+R)f + f'b over the constraint set — friction-loss
+    rows inside their box with the gradient pointing out of it at an active bound, limit rows f >= 0, g >= 0,
+    f g = 0, elliptic contacts f in the friction cone, g in its dual cone, f . g = 0."""
+    fm, _ = hands
+    om = O.OracleModel(fm, iterations=4000, tolerance=0.0)
+    om.set_option(maxcon=24)
+    d = O.OracleData(om)
+    d.reset()
+    acts = helpers.twinkle_actions()[:, :44]
+    checked = 0
+    for t in range(26):
+        d.control_step(acts[t])
+        if t < 16 or d.ncon == 0:
+            continue
+        d.ctrl[:] = acts[t + 1]
+        d.call("orc_smooth"); d.call("orc_solve_init"); d.call("orc_solve_iterate")
+        typ, eid = d.efc_type(), d.efc_id()
+        AR, b, f, loss = d.efc("efc_AR"), d.efc("efc_b"), d.efc("efc_force"), d.efc("efc_frictionloss")
+        g = AR @ f + b
+        sc = 1e-7 * max(1.0, np.abs(b).max())
+        cons = d.contacts()
+        i = 0
+        while i < len(typ):
+            if typ[i] == 0:      # friction loss: box [-loss, loss]
+                assert abs(f[i]) <= loss[i] + 1e-12
+                if abs(f[i]) < loss[i] - 1e-9:
+                    assert abs(g[i]) < sc
+                else:
+                    assert g[i] * np.sign(f[i]) < sc
+                i += 1
+            elif typ[i] == 1:    # limit: f >= 0 complementary to g >= 0
+                assert f[i] >= 0 and g[i] > -sc and abs(f[i] * g[i]) < sc * max(1.0, f[i])
+                i += 1
+            else:                # elliptic contact, condim 3
+                mu = cons[eid[i]]["mu"]
+                fn, ft = f[i], np.hypot(f[i + 1], f[i + 2])
+                gn, gt = g[i], np.hypot(g[i + 1], g[i + 2])
+                assert fn >= 0 and ft <= mu * fn + 1e-9
+                assert gn > -sc and mu * gt <= gn + 10 * sc
+                assert abs(f[i:i + 3] @ g[i:i + 3]) < 10 * sc * max(1.0, fn)
+                i += 3
+        checked += 1
+        # leave the state as control_step expects it (the next step2 recomputes the solve)
+    assert checked >= 5
+
+
+@pytest.mark.parametrize("key", [40, 42])
+def test_key_equilibrium_under_a_constant_torque_is_the_analytic_one(hands, key):
+    """Closed-form statics of one key (piano_mjcf.py:66-100: hinge about +y at the back edge, spring towards
+    -1 deg, uniform box): with a constant generalized force tau the rest angle solves
+    tau + m g (r_x cos q + r_z sin q) - k (q - q_ref) = 0 (gravity torque about the hinge of the rotated
+    centre of mass); the oracle, stepped to rest, must land on it (no limit active in between)."""
+    fm, om = hands
+    A = fm.arrays
+    dof, body = int(A["key_dofid"][key]), int(A["key_bodyid"][key])
+    jnt = dof  # one hinge per key, joints and dofs share the numbering
+    m, k, qref = A["body_mass"][body], A["jnt_stiffness"][jnt], A["jnt_springref"][jnt]
+    r0 = A["body_ipos"][body] - A["jnt_pos"][jnt]
+    assert np.allclose(A["jnt_axis"][jnt], [0, 1, 0])
+    g = -A["opt_gravity"][2]
+    qmax = fm.key_qmax[key]
+    target = 0.45 * qmax
+    grav = lambda q: m * g * (r0[0] * np.cos(q) + r0[2] * np.sin(q))   # generalized gravity force about +y
+    tau = k * (target - qref) - grav(target)
+    d = O.OracleData(om)
+    d.reset()
+    d.qfrc_applied[dof] = tau
+    for _ in range(800):
+        d.mj_step(np.zeros(44))
+    assert abs(d.qvel[dof]) < 1e-9
+    # the bias force the oracle computes at that angle is minus the analytic gravity torque
+    assert abs(d.qfrc_bias[dof] + grav(d.qpos[dof])) < 1e-12
+    assert abs(d.qpos[dof] - target) < 1e-8
+    # the neighbours are untouched and still resting on their lower limit
+    assert d.qpos[dof - 1] < 0 and d.qpos[dof + 1] < 0
