@@ -239,3 +239,94 @@ def test_key_equilibrium_under_a_constant_torque_is_the_analytic_one(hands, key)
     assert abs(d.qpos[dof] - target) < 1e-8
     # the neighbours are untouched and still resting on their lower limit
     assert d.qpos[dof - 1] < 0 and d.qpos[dof + 1] < 0
+
+
+def _point_box_distance(p, half):
+    q = np.abs(p) - half
+    return np.linalg.norm(np.maximum(q, 0.0)) + min(q.max(), 0.0)   # signed: negative inside
+
+
+def test_capsule_box_contacts_are_geometrically_consistent(hands):
+    """Narrowphase output against brute force, independent of how it was computed: for every capsule / sphere -
+    box pair in contact, (i) the deepest reported distance equals the minimum over the capsule axis of the
+    signed point-box distance minus the radius (dense sampling), (ii) every contact's normal is a unit vector
+    and its position is the mid-point between a point on the box surface and the surface point of a sphere of
+    the capsule's radius centred on the capsule axis, `dist` apart along the normal."""
+    fm, om = hands
+    A = fm.arrays
+    acts = helpers.twinkle_actions()[:, :44]
+    lo, hi = fm.actuator_ctrlrange[:, 0], fm.actuator_ctrlrange[:, 1]
+    rng = np.random.default_rng(4)
+    pairs = contacts = 0
+    for e in range(3):
+        d = O.OracleData(om)
+        d.reset()
+        for t in range(30):
+            d.control_step(np.clip(acts[t] + (rng.normal(0, 0.08, 44) * (hi - lo) / 2 if e else 0), lo, hi))
+            if t < 12:
+                continue
+            by_pair = {}
+            for c in d.contacts():
+                by_pair.setdefault((c["geom1"], c["geom2"]), []).append(c)
+            for (g1, g2), cs in by_pair.items():
+                assert A["geom_type"][g2] == 6 and A["geom_type"][g1] in (2, 3)   # sphere / capsule vs box
+                R2 = d.geom_xmat[g2].reshape(3, 3); p2 = d.geom_xpos[g2]; half = A["geom_size"][g2]
+                R1 = d.geom_xmat[g1].reshape(3, 3); p1 = d.geom_xpos[g1]
+                rad = A["geom_size"][g1][0]
+                hl = A["geom_size"][g1][1] if A["geom_type"][g1] == 3 else 0.0
+                ts = np.linspace(-hl, hl, 4001 if hl > 0 else 1)
+                axis_pts = p1[None, :] + ts[:, None] * R1[:, 2][None, :]
+                local = (axis_pts - p2) @ R2                                  # box frame
+                dmin = min(_point_box_distance(q, half) for q in local) - rad
+                assert abs(min(c["dist"] for c in cs) - dmin) < 2e-7, (t, g1, g2)
+                for c in cs:
+                    n = c["frame"][0]
+                    assert abs(np.linalg.norm(n) - 1) < 1e-12
+                    s1 = c["pos"] - 0.5 * c["dist"] * n      # on the capsule surface
+                    s2 = c["pos"] + 0.5 * c["dist"] * n      # on the box surface
+                    assert abs(_point_box_distance((s2 - p2) @ R2, half)) < 1e-9
+                    centre = s1 - rad * n                    # the sphere this contact was generated from
+                    rel = centre - p1
+                    tt = np.clip(rel @ R1[:, 2], -hl, hl)
+                    assert np.linalg.norm(rel - tt * R1[:, 2]) < 1e-9   # ... sits on the capsule axis segment
+                    contacts += 1
+                pairs += 1
+    assert pairs > 40 and contacts > 60
+
+
+def test_contact_jacobian_matches_finite_differences(hands):
+    """Rows of efc_J for contacts against finite differences of the kinematics: moving dof j by eps displaces the
+    material points of the two bodies at the contact position; (displacement of body 2 - body 1) / eps along
+    the three frame axes is column j of the contact's Jacobian block."""
+    fm, om = hands
+    A = fm.arrays
+    acts = helpers.twinkle_actions()[:, :44]
+    d = O.OracleData(om); d.reset()
+    probe = O.OracleData(om)
+    eps, checked = 1e-7, 0
+    for t in range(26):
+        d.control_step(acts[t])
+        if t < 17 or d.ncon == 0:
+            continue
+        typ, eid, J = d.efc_type(), d.efc_id(), d.efc("efc_J")
+        cons = d.contacts()
+        rows = [i for i in range(len(typ)) if typ[i] == 2][::3]
+        xpos0, xmat0 = d.xpos.copy(), d.xmat.copy()
+        for i in rows[:3]:
+            c = cons[eid[i]]
+            b1, b2 = int(A["geom_bodyid"][c["geom1"]]), int(A["geom_bodyid"][c["geom2"]])
+            loc = [xmat0[b].reshape(3, 3).T @ (c["pos"] - xpos0[b]) for b in (b1, b2)]
+            cols = np.flatnonzero(np.abs(J[i:i + 3]).sum(axis=0))
+            assert len(cols) >= 5
+            for j in cols:
+                probe.qpos[:] = d.qpos
+                probe.qpos[j] += eps
+                probe.call("orc_kinematics")
+                p = [probe.xpos[b] + probe.xmat[b].reshape(3, 3) @ l for b, l in zip((b1, b2), loc)]
+                num = c["frame"] @ ((p[1] - p[0]) / eps)      # both were at c["pos"] before the perturbation
+                assert np.abs(num - J[i:i + 3, j]).max() < 5e-6, (t, i, j, num, J[i:i + 3, j])
+            # a dof outside the chain moves neither body
+            other = [j for j in range(fm.meta["nv"]) if j not in cols][:3]
+            assert np.abs(J[i:i + 3][:, other]).max() == 0
+            checked += 1
+    assert checked >= 8
