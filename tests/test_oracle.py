@@ -330,3 +330,43 @@ def test_contact_jacobian_matches_finite_differences(hands):
             assert np.abs(J[i:i + 3][:, other]).max() == 0
             checked += 1
     assert checked >= 8
+
+
+def test_step_invariants_recomputed_in_numpy(hands):
+    """One mj_step of the oracle re-derived from its own intermediate arrays with dense numpy algebra:
+    actuator forces from the position-actuator model (clamped ctrl, kp (ctrl - length), force range), the
+    dual -> primal map M (qacc - qacc_smooth) = J^T f, the implicit-damping Euler system
+    (M + h D)(v+ - v) / h = qfrc_smooth + qfrc_constraint, and q+ = q + h v+."""
+    fm, om = hands
+    A = fm.arrays
+    h = fm.meta["timestep"]
+    acts = helpers.twinkle_actions()[:, :44]
+    d = O.OracleData(om); d.reset()
+    checked = 0
+    for t in range(24):
+        d.control_step(acts[t])
+        if t < 15:
+            continue
+        q0, v0 = d.qpos.copy(), d.qvel.copy()
+        ctrl = acts[t + 1]
+        d.ctrl[:] = ctrl
+        d.step2()      # d holds a valid step1 for (q0, v0); step2 = actuation .. Euler
+        M = d.M.copy()
+        # actuators: joint / fixed-tendon transmission, gain kp, bias -kp * length
+        length = d.actuator_length.copy()
+        kp = A["actuator_gainprm"]
+        c = np.where(A["actuator_ctrllimited"].astype(bool), np.clip(ctrl, A["actuator_ctrlrange"][:, 0], A["actuator_ctrlrange"][:, 1]), ctrl)
+        force = kp * c + A["actuator_biasprm"][:, 0] + A["actuator_biasprm"][:, 1] * length + A["actuator_biasprm"][:, 2] * d.actuator_velocity
+        force = np.where(A["actuator_forcelimited"].astype(bool), np.clip(force, A["actuator_forcerange"][:, 0], A["actuator_forcerange"][:, 1]), force)
+        # (step2 ends with Euler: actuator_length / velocity still belong to (q0, v0), the state the force was computed from)
+        assert np.abs(force - d.actuator_force).max() < 1e-12
+        J, f = d.efc("efc_J"), d.efc("efc_force")
+        assert np.abs(M @ (d.qacc - d.qacc_smooth) - J.T @ f).max() < 1e-9
+        assert np.abs(J.T @ f - d.qfrc_constraint).max() < 1e-12
+        D = np.diag(A["dof_damping"])
+        lhs = (M + h * D) @ ((d.qvel - v0) / h)
+        assert np.abs(lhs - (d.qfrc_smooth + d.qfrc_constraint)).max() < 1e-8
+        assert np.abs(d.qpos - (q0 + h * d.qvel)).max() < 1e-15
+        d.step1()      # restore the invariant control_step relies on
+        checked += 1
+    assert checked >= 8
