@@ -70,6 +70,8 @@ typedef struct orc_data {
   double *efc_pos, *efc_margin, *efc_frictionloss, *efc_diagApprox, *efc_R, *efc_D, *efc_K, *efc_Bd,
       *efc_imp, *efc_vel, *efc_aref, *efc_b, *efc_force, *efc_AR;
   int *adj, *adj_n; /* adjacency (rows sharing a tree): adj[i*efc_cap + k] */
+  double *scr_MH, *scr_a, *scr_crb, *scr_A, *scr_F, *scr_jar; /* per-step scratch, allocated once: the baseline
+      timing runs one instance per host thread and must not serialise on mmap / munmap of 157 KB blocks */
   int solver_niter;
   double solver_improvement;
   long mac_count;
@@ -180,6 +182,7 @@ orc_data *orc_data_create(const orc_model *o) {
   ALLOC(efc_vel, cap); ALLOC(efc_aref, cap); ALLOC(efc_b, cap); ALLOC(efc_force, cap);
   ALLOC(efc_AR, cap * cap);
   ALLOCI(adj, cap * cap); ALLOCI(adj_n, cap);
+  ALLOC(scr_MH, nv * nv); ALLOC(scr_a, nv); ALLOC(scr_crb, nb * 10); ALLOC(scr_A, nb * 6); ALLOC(scr_F, nb * 6); ALLOC(scr_jar, cap);
   return d;
 }
 void orc_data_destroy(orc_data *d) {
@@ -193,6 +196,7 @@ void orc_data_destroy(orc_data *d) {
   free(d->efc_pos); free(d->efc_margin); free(d->efc_frictionloss); free(d->efc_diagApprox);
   free(d->efc_R); free(d->efc_D); free(d->efc_K); free(d->efc_Bd); free(d->efc_imp); free(d->efc_vel);
   free(d->efc_aref); free(d->efc_b); free(d->efc_force); free(d->efc_AR); free(d->adj); free(d->adj_n);
+  free(d->scr_MH); free(d->scr_a); free(d->scr_crb); free(d->scr_A); free(d->scr_F); free(d->scr_jar);
   free(d);
 }
 
@@ -399,7 +403,8 @@ static void solve_M(const orc_model *o, const double *L, int nv, double *x) {
 void orc_crb(const orc_model *o, orc_data *d) {
   const rp_flat_model *m = &o->m;
   int nv = m->nv, nb = m->nbody;
-  double *crb = (double *)calloc((size_t)nb * 10, sizeof(double));
+  double *crb = d->scr_crb;
+  memset(crb, 0, sizeof(double) * (size_t)nb * 10);
   for (int b = 1; b < nb; b++) body_inertia_world(o, d, b, crb + 10 * b);
   for (int b = nb - 1; b > 0; b--) {
     int p = m->body_parentid[b];
@@ -416,7 +421,6 @@ void orc_crb(const orc_model *o, orc_data *d) {
     }
     d->M[i * nv + i] += m->dof_armature[i];
   }
-  free(crb);
   for (int t = 0; t < o->ntree; t++)
     if (chol_block(d->L, d->M, nv, o->tree_adr[t], o->tree_num[t])) fprintf(stderr, "oracle: M not SPD\n");
 }
@@ -425,8 +429,9 @@ void orc_crb(const orc_model *o, orc_data *d) {
 void orc_velocity(const orc_model *o, orc_data *d) {
   const rp_flat_model *m = &o->m;
   int nv = m->nv, nb = m->nbody;
-  double *A = (double *)calloc((size_t)nb * 6, sizeof(double));
-  double *F = (double *)calloc((size_t)nb * 6, sizeof(double));
+  double *A = d->scr_A, *F = d->scr_F;
+  memset(A, 0, sizeof(double) * (size_t)nb * 6);
+  memset(F, 0, sizeof(double) * (size_t)nb * 6);
   memset(d->V, 0, sizeof(double) * 6 * nb);
   for (int k = 0; k < 3; k++) A[3 + k] = -m->gravity[k];
   for (int b = 1; b < nb; b++) {
@@ -486,7 +491,6 @@ void orc_velocity(const orc_model *o, orc_data *d) {
     d->actuator_length[a] = m->actuator_gear[a] * len;
     d->actuator_velocity[a] = m->actuator_gear[a] * vel;
   }
-  free(A); free(F);
 }
 
 /* ------------------------------------ mj_collision ----------------------------------------- */
@@ -956,7 +960,8 @@ static double row_residual(orc_data *d, int i) {
 void orc_solve_init(const orc_model *o, orc_data *d) {
   const rp_flat_model *m = &o->m;
   int nv = m->nv, nefc = d->nefc;
-  double *jar = (double *)calloc((size_t)nefc + 1, sizeof(double));
+  double *jar = d->scr_jar;
+  memset(jar, 0, sizeof(double) * ((size_t)nefc + 1));
   /* b = J*qacc_smooth - aref */
   for (int i = 0; i < nefc; i++) {
     const double *J = d->efc_J + (size_t)i * nv;
@@ -980,7 +985,6 @@ void orc_solve_init(const orc_model *o, orc_data *d) {
     }
     if (cost > 0) memset(d->efc_force, 0, sizeof(double) * nefc);
   }
-  free(jar);
 }
 void orc_solve_iterate(const orc_model *o, orc_data *d) {
   const rp_flat_model *m = &o->m;
@@ -1103,8 +1107,7 @@ void orc_step2(const orc_model *o, orc_data *d) {
   orc_smooth(o, d);
   orc_solve(o, d);
   /* mj_Euler with implicit joint damping: (M + h*diag(damping)) a = qfrc_smooth + qfrc_constraint */
-  double *a = (double *)malloc(sizeof(double) * nv);
-  double *MH = (double *)malloc(sizeof(double) * nv * nv);
+  double *a = d->scr_a, *MH = d->scr_MH;
   memcpy(MH, d->M, sizeof(double) * nv * nv);
   for (int j = 0; j < nv; j++) { MH[j * nv + j] += h * m->dof_damping[j]; a[j] = d->qfrc_smooth[j] + d->qfrc_constraint[j]; }
   for (int t = 0; t < o->ntree; t++) chol_block(d->LH, MH, nv, o->tree_adr[t], o->tree_num[t]);
@@ -1114,7 +1117,6 @@ void orc_step2(const orc_model *o, orc_data *d) {
     d->qpos[j] += h * d->qvel[j];
     d->qacc_warmstart[j] = d->qacc[j];
   }
-  free(a); free(MH);
 }
 void orc_reset(const orc_model *o, orc_data *d) {
   int nv = o->m.nv;
