@@ -28,33 +28,9 @@
 #define MAXCON RP_MAXCON
 #define RS 27  // row stride of the hand matrices (odd: lane-per-row accesses are bank-conflict free)
 #define H1 (RP_NHMAX - 1)
-// tuning knobs (instruction-cache footprint of the PGS loop vs. per-row overhead)
-#ifndef RP_FR_UNROLL
-#define RP_FR_UNROLL 1  // rolled: the 25-instruction body stays in the L0 instruction cache (measured 27.7 -> 24.6 ms/step)
-#endif
+// tuning knobs (DESIGN.md §5 lists what was measured, including the variants that were removed again)
 #ifndef RP_CH_UNROLL
 #define RP_CH_UNROLL 1
-#endif
-#ifndef RP_EULER_FACTOR
-#define RP_EULER_FACTOR 0  // tree-sparse L^T D L solve for the Euler step: 1.5k instead of 4.3k instructions but serial; measured 23.4 vs 23.0 ms/step
-#endif
-#ifndef RP_SWIZZLE
-#define RP_SWIZZLE 1  // no effect with one environment per block (23.0 vs 23.0 ms/step); 15.50 -> 15.31 with six
-#endif
-#ifndef RP_FR_DEFER
-#define RP_FR_DEFER 0
-#endif
-#ifndef RP_FR_ICLAMP
-#define RP_FR_ICLAMP 0
-#endif
-#ifndef RP_FR_SKIP
-#define RP_FR_SKIP 1  // step only the friction-loss rows whose force changes (bit-identical; see the sweep)
-#endif
-#ifndef RP_FR_ABS
-#define RP_FR_ABS 0
-#endif
-#ifndef RP_FR_CHAIN
-#define RP_FR_CHAIN 0
 #endif
 #ifndef RP_SW_UNROLL
 #define RP_SW_UNROLL 2
@@ -75,21 +51,6 @@
 #ifndef RP_NU
 #define RP_NU 8  // contacts whose M^-1 Jc^T is kept in shared memory (the others walk the kinematic chain)
 #endif
-#ifndef RP_JV_GATHER
-#define RP_JV_GATHER 0
-#endif
-#ifndef RP_CH_PIPE
-#define RP_CH_PIPE 0
-#endif
-#ifndef RP_CH_ACC2
-#define RP_CH_ACC2 0
-#endif
-#ifndef RP_CON_PRE
-#define RP_CON_PRE 1  // residual-independent half of the contact update ahead of the J*v reduction
-#endif
-#ifndef RP_SW_BATCH
-#define RP_SW_BATCH 0  // element updates of a sweep pivot loaded in batches of this size (0: one by one)
-#endif
 #ifndef RP_MINBLOCKS
 #define RP_MINBLOCKS 6
 #endif
@@ -97,7 +58,7 @@
 namespace {
 
 constexpr int kPhaseExtra = ((RP_PHASE_MASK) & 1) + (((RP_PHASE_MASK) >> 1) & 1) + (((RP_PHASE_MASK) >> 2) & 1);
-constexpr int kFrUnroll = RP_FR_UNROLL, kChUnroll = RP_CH_UNROLL, kSwUnroll = RP_SW_UNROLL;
+constexpr int kChUnroll = RP_CH_UNROLL, kSwUnroll = RP_SW_UNROLL;
 
 struct Contact {  // lives in shared memory
   double Jc[3][MAXD];  // hand-chain Jacobian entries by depth (already signed: body2 - body1)
@@ -217,35 +178,6 @@ __device__ __noinline__ void sweep_inverse(double* A, const signed char* anc /*[
     const bool upd = lane < NL && lane != k;  // lane k's own row is rewritten after the updates
     const double t = upd ? rowk[lane] * dinv : 0.0;
     const int depk = dep[k], endk = k + sub[k];
-#if RP_SW_BATCH
-    // Row `lane` changes only if it is an ancestor of k or inside k's subtree (t != 0; the others would
-    // subtract exact zeros).  The element updates of one pivot are independent, but written one by one the
-    // compiler has to assume that the store of element i aliases the loads of element i + 1 and serialises
-    // LDS -> FMA -> STS per element; loading a batch first gives the shared-memory pipe RP_SW_BATCH
-    // independent element updates in flight.  Entries past the end re-load the last valid one and are not stored.
-    if (upd && t != 0.0) {
-      constexpr int B = RP_SW_BATCH;
-#pragma unroll 1
-      for (int d0 = 0; d0 < depk; d0 += B) {
-        int idx[B];
-        double r[B], m[B];
-#pragma unroll
-        for (int u = 0; u < B; u++) idx[u] = anc[k * MAXD + min(d0 + u, depk - 1)];
-#pragma unroll
-        for (int u = 0; u < B; u++) { r[u] = rowk[idx[u]]; m[u] = myrow[idx[u]]; }
-#pragma unroll
-        for (int u = 0; u < B; u++) if (d0 + u < depk) myrow[idx[u]] = m[u] - r[u] * t;
-      }
-#pragma unroll 1
-      for (int i0 = k + 1; i0 < endk; i0 += B) {
-        double r[B], m[B];
-#pragma unroll
-        for (int u = 0; u < B; u++) { const int i = min(i0 + u, endk - 1); r[u] = rowk[i]; m[u] = myrow[i]; }
-#pragma unroll
-        for (int u = 0; u < B; u++) if (i0 + u < endk) myrow[i0 + u] = m[u] - r[u] * t;
-      }
-    }
-#else
     if (upd) {
       for (int d = 0; d < depk; d++) {
         const int i = anc[k * MAXD + d];
@@ -254,67 +186,11 @@ __device__ __noinline__ void sweep_inverse(double* A, const signed char* anc /*[
 #pragma unroll kSwUnroll
       for (int i = k + 1; i < endk; i++) myrow[i] -= rowk[i] * t;
     }
-#endif
     __syncwarp();
     if (upd) { myrow[k] = t; A[k * RS + lane] = t; }
     if (lane == k) A[k * RS + k] = -dinv;
     __syncwarp();
   }
-}
-
-// Solves (M + h*D) x = rhs for one hand with the tree-sparse L^T D L factorisation (the scheme of
-// MuJoCo's mj_factorI / mj_solveLD), in place on the packed rows R[moff[k] + d] = M[k][anc(k, d)],
-// d = 0..dep[k] (d == dep[k]: the diagonal, already including h*damping).  Lane == dof; `xin` is the
-// lane's right-hand side, the return value its solution.  xs: 32 doubles of shared scratch.
-// About 1.5k instructions instead of the 4.3k of a second dense sweep + matrix-vector product.
-__device__ __noinline__ double factor_solve(double* R, const unsigned char* moff, const signed char* anc /*[NL][MAXD]*/,
-                                            const signed char* dep, const signed char* sub, double* xs, double xin, int lane) {
-  const bool hl = lane < NL;
-  const int mydep = hl ? dep[lane] : 0, myoff = hl ? moff[lane] : 0, mysub = hl ? sub[lane] : 0;
-  double* ri = R + myoff;
-  // ---- factorisation, leaves first: for every proper ancestor i of k, L[k][i] = M[k][i] / D[k] and
-  // row i -= L[k][i] * row k (restricted to the ancestors-or-self of i)
-#pragma unroll 1
-  for (int k = NL - 1; k >= 1; k--) {
-    const int depk = dep[k];
-    if (depk == 0) continue;  // a root has nothing above it (warp-uniform)
-    const double* rk = R + moff[k];
-    const bool isanc = hl && lane < k && k < lane + mysub;
-    double t = 0;
-    if (isanc) {
-      t = rk[mydep] / rk[depk];
-      for (int d = 0; d <= mydep; d++) ri[d] -= rk[d] * t;
-    }
-    __syncwarp();
-    if (isanc) R[moff[k] + mydep] = t;
-    __syncwarp();
-  }
-  // ---- x <- L^-T x: descending k, every ancestor i of k takes x[i] -= L[k][i] * x[k]
-  double x = xin;
-#pragma unroll 1
-  for (int k = NL - 1; k >= 1; k--) {
-    if (dep[k] == 0) continue;
-    const double xk = __shfl_sync(FULL, x, k);
-    const bool isanc = hl && lane < k && k < lane + mysub;
-    if (isanc) x -= R[moff[k] + mydep] * xk;
-  }
-  // ---- x <- D^-1 x
-  if (hl) x /= ri[mydep];
-  // ---- x <- L^-1 x: by depth level, x[k] -= sum over ancestors i of L[k][i] * x[i] (all final by then)
-  const int maxd = __reduce_max_sync(FULL, hl ? mydep : 0);
-  xs[lane] = x;
-  __syncwarp();
-#pragma unroll 1
-  for (int lvl = 1; lvl <= maxd; lvl++) {
-    if (hl && mydep == lvl) {
-      double acc = x;
-      for (int d = 0; d < lvl; d++) acc -= ri[d] * xs[anc[lane * MAXD + d]];
-      x = acc;
-      xs[lane] = acc;
-    }
-    __syncwarp();
-  }
-  return x;
 }
 
 }  // namespace
@@ -340,11 +216,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // opaque: keeps the compiler from re-reading S2R in loops
   // warp <-> hand; swizzled by block parity so that the warps of the (usually busier) right hand do not
   // all land on the same two warp schedulers of an SM
-#if RP_SWIZZLE
   const int h = HANDS ? ((tid >> 5) ^ (EPB > 1 ? ((slot >> 1) & 1) : (int)(blockIdx.x & 1))) : 0;
-#else
-  const int h = HANDS ? (tid >> 5) : 0;
-#endif
   // block-wide phase barriers every thread of the block has to pass: one per iteration of the substep loop
   const int nsub_loop = a.mode == RP_MODE_RESET ? 0 : a.nsub;
   const int eidx = (int)blockIdx.x * EPB + slot;
@@ -1315,12 +1187,10 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       while (iter < maxiter) {
         double improvement = iter == 0 ? improvement0 : 0.0;
         if (HANDS) {
-          // ---- friction-loss rows, dof order: every lane evaluates the candidate update of its own
-          // row; lane i commits at step i and broadcasts the force change
+          // ---- friction-loss rows, dof order (row i of the classic sweep: res = b + R f + va_i,
+          // f' = clamp(f - res / AR, +-frictionloss), va += M^-1[:, i] (f' - f), cost change -(f' - f)(0.5 (f' - f) AR + res)).
           const double fbase = fr_b + fr_R * fr_f;  // f only changes at the lane's own commit
           const double fr_lo = -fr_hi;
-          const double* prow = Ah + lc;
-#if RP_FR_SKIP
           // Only rows whose force actually changes are stepped.  Every lane evaluates the update of its own row
           // against the current va; a ballot finds the first row at or after the cursor with a non-zero change,
           // that row commits and broadcasts, and the search resumes behind it.  The rows skipped in between
@@ -1346,112 +1216,6 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
               cursor = i + 1;
             }
           }
-#elif RP_FR_CHAIN
-          // short dependency chain: the force change is clamped directly, dl = clamp(-(fbase + va) / AR,
-          // lo - f, hi - f), so a row costs FMA -> compare/select -> shuffle -> FMA on the critical path
-          const double fq = -(fbase * fr_ARi), dlo = fr_lo - fr_f, dhi = fr_hi - fr_f;
-#pragma unroll kFrUnroll
-          for (int i = 0; i < NL; i++, prow += RS) {
-            const double mrow = *prow;
-            const double d = fma(-va, fr_ARi, fq);
-            const bool plo = d < dlo, phi = d > dhi;
-            double dl = plo ? dlo : d;
-            dl = phi ? dhi : dl;
-            const double dbc = shfl(dl, i);
-            const double res = fbase + va;
-            va -= mrow * dbc;
-            if (lane == i) {
-              improvement -= dl * (0.5 * dl * fr_AR + res);
-              fr_f = phi ? fr_hi : (plo ? fr_lo : fr_f + dl);
-            }
-          }
-#elif RP_FR_ABS
-          // Absolute-force form: lane j tracks g_j, the unclamped minimiser of its own row given the forces of
-          // the rows before it (already updated) and after it (still old).  Committing row i then costs
-          // clamp -> shuffle -> one FMA on the serial chain (the classic form has four more dependent fp64
-          // operations per row); the two matrix-vector products this needs (removing the old forces of the
-          // earlier rows up front, folding the force changes into va afterwards) have no serial dependence.
-          // K_ij = Ah_ij * ARi_j.  Same Gauss-Seidel iterates up to rounding.
-          {
-            double g0 = fr_f - (fbase + va) * fr_ARi, g1 = 0;
-            const double* pr = prow;
-#pragma unroll 2
-            for (int i = 0; i < NL; i += 2, pr += 2 * RS) {
-              const double f0 = shfl(fr_f, i), f1 = shfl(fr_f, i + 1);
-              const double k0 = i < lane ? pr[0] * fr_ARi : 0.0, k1 = i + 1 < lane ? pr[RS] * fr_ARi : 0.0;
-              g0 = fma(-k0, f0, g0);
-              g1 = fma(-k1, f1, g1);
-            }
-            double g = g0 + g1, fx_own = fr_f, g_own = 0;
-            pr = prow;
-#pragma unroll kFrUnroll
-            for (int i = 0; i < NL; i++, pr += RS) {
-              const double k = i < lane ? pr[0] * fr_ARi : 0.0;
-              double fx = g < fr_lo ? fr_lo : g;
-              fx = g > fr_hi ? fr_hi : fx;
-              const double fbc = shfl(fx, i);
-              if (lane == i) { fx_own = fx; g_own = g; }
-              g = fma(k, fbc, g);
-            }
-            const double dl = fx_own - fr_f, res_own = (fr_f - g_own) * fr_AR;
-            improvement -= dl * (0.5 * dl * fr_AR + res_own);
-            fr_f = fx_own;
-            double a0 = 0, a1 = 0;
-            pr = prow;
-#pragma unroll 2
-            for (int i = 0; i < NL; i += 2, pr += 2 * RS) {
-              const double d0 = shfl(dl, i), d1 = shfl(dl, i + 1);
-              a0 = fma(-pr[0], d0, a0);
-              a1 = fma(-pr[RS], d1, a1);
-            }
-            va += a0 + a1;
-          }
-#elif RP_FR_DEFER
-          // the owner lane only records (dl, res) at its commit; the cost change is evaluated once after
-          // the sweep, which keeps three fp64 instructions per row off the 16-lane fp64 pipe
-          double dl_own = 0, res_own = 0;
-#pragma unroll kFrUnroll
-          for (int i = 0; i < NL; i++, prow += RS) {
-            const double mrow = *prow;
-            const double res = fbase + va;
-            const double x = fr_f - res * fr_ARi;
-#if RP_FR_ICLAMP
-            // |x| > hi on the integer pipe (non-negative doubles order like their bit patterns)
-            const unsigned long long xb = (unsigned long long)__double_as_longlong(x);
-            const bool big = (xb & 0x7fffffffffffffffull) > (unsigned long long)__double_as_longlong(fr_hi);
-            const double fx = big ? __longlong_as_double((long long)((xb & 0x8000000000000000ull) | (unsigned long long)__double_as_longlong(fr_hi))) : x;
-#else
-            double fx = x < fr_lo ? fr_lo : x;
-            fx = x > fr_hi ? fr_hi : fx;
-#endif
-            const double dl = fx - fr_f;
-            const double dbc = shfl(dl, i);
-            va -= mrow * dbc;
-            if (lane == i) { dl_own = dl; res_own = res; fr_f = fx; }
-          }
-          improvement -= dl_own * (0.5 * dl_own * fr_AR + res_own);
-#else
-#pragma unroll kFrUnroll
-          for (int i = 0; i < NL; i++, prow += RS) {
-            const double mrow = *prow;
-            const double res = fbase + va;
-            const double x = fr_f - res * fr_ARi;
-#if RP_FR_ICLAMP
-            // symmetric clamp on the integer pipe: |x| > hi compares like the bit patterns (non-negative doubles),
-            // the result takes the sign of x; a DSETP + select pair costs about twice the latency
-            const unsigned long long xb = (unsigned long long)__double_as_longlong(x);
-            const bool big = (xb & 0x7fffffffffffffffull) > (unsigned long long)__double_as_longlong(fr_hi);
-            const double fx = big ? __longlong_as_double((long long)((xb & 0x8000000000000000ull) | (unsigned long long)__double_as_longlong(fr_hi))) : x;
-#else
-            double fx = x < fr_lo ? fr_lo : x;
-            fx = x > fr_hi ? fr_hi : fx;
-#endif
-            const double dl = fx - fr_f;
-            const double dbc = shfl(dl, i);
-            va -= mrow * dbc;
-            if (lane == i) { improvement -= dl * (0.5 * dl * fr_AR + res); fr_f = fx; }
-          }
-#endif
         }
     TICK(8)
         // ---- limit rows of keys that carry contacts (values in shared memory)
@@ -1496,7 +1260,6 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
               const bool anc = lane <= link && link < lane + lsub;
               const double j0 = anc ? cn.Jc[0][ldc] : 0.0, j1 = anc ? cn.Jc[1][ldc] : 0.0, j2 = anc ? cn.Jc[2][ldc] : 0.0;
               double part[3] = {j0 * va, j1 * va, j2 * va};
-#if RP_CON_PRE
               // residual-independent part of the update, issued ahead of the reduction so that it runs in the
               // shadow of the shuffle latency: block loads, ray denominators, the lambda = 0 pass of the QCQP
               double Ab[9], fold[3], rbase[3];
@@ -1510,53 +1273,17 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
               }
               rp::EllPre pre;
               rp::pgs_elliptic_pre(pre, Ab, fold, cmu);
-#endif
-#if RP_JV_GATHER
-              // J*va by gathering the (at most MAXD) chain entries of va with independent shuffles and summing
-              // them redundantly on every lane (Jc[][d] and chain[d] are zero-padded past the chain): one
-              // shuffle latency plus five dependent FMAs instead of five dependent shuffle + add rounds
-              {
-                const unsigned long long c0 = *reinterpret_cast<const unsigned long long*>(cn.chain);
-                const unsigned long long c1 = *reinterpret_cast<const unsigned long long*>(cn.chain + 8);
-                double pa[3] = {0, 0, 0}, pb[3] = {0, 0, 0};
-#pragma unroll
-                for (int d = 0; d < MAXD; d++) {
-                  const int j = (int)((d < 8 ? c0 >> (8 * d) : c1 >> (8 * (d - 8))) & 0xffull);
-                  const double vj = shfl(va, j);
-#pragma unroll
-                  for (int r = 0; r < 3; r++) {
-                    if (d & 1) pb[r] = fma(cn.Jc[r][d], vj, pb[r]); else pa[r] = fma(cn.Jc[r][d], vj, pa[r]);
-                  }
-                }
-#pragma unroll
-                for (int r = 0; r < 3; r++) part[r] = pa[r] + pb[r];
-              }
-#else
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
                 for (int r = 0; r < 3; r++) part[r] += __shfl_xor_sync(FULL, part[r], o);
               }
-#endif
               double res[3], f[3];
               const double vak = sm.vak[key >= 0 ? key : 0];
               const double jkm = key >= 0 ? 1.0 : 0.0;
-#if RP_CON_PRE
               for (int r = 0; r < 3; r++) res[r] = rbase[r] + part[r];
               f[0] = fold[0]; f[1] = fold[1]; f[2] = fold[2];
               const double change = rp::pgs_elliptic_post(pre, Ab, res, f, cmu);
-#else
-#pragma unroll
-              for (int r = 0; r < 3; r++) {
-                f[r] = cn.f[r];
-                res[r] = cn.b[r] + cn.R[r] * f[r] + part[r] + jkm * cn.Jk[r] * vak;
-              }
-              double Ab[9];
-#pragma unroll
-              for (int k = 0; k < 9; k++) Ab[k] = cn.A[k];
-              const double fold[3] = {f[0], f[1], f[2]};
-              const double change = rp::pgs_elliptic_update(Ab, res, f, cn.mu);
-#endif
               const double df[3] = {f[0] - fold[0], f[1] - fold[1], f[2] - fold[2]};
               __syncwarp();
               improvement -= lane == 0 ? change : 0.0;
@@ -1573,44 +1300,12 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
                 // hand side: w = Jc^T df on the chain, va += Minv[:,chain] w
                 const double w = j0 * df[0] + j1 * df[1] + j2 * df[2];
                 double acc = 0;
-#if RP_CH_PIPE
-                // Software-pipelined: the chain indices come as two packed words, then every shuffle and every
-                // M^-1 load is issued before the first FMA (fully unrolled over MAXD, entries past the chain
-                // contribute zero; chain[] is zero-padded so the shuffle source is always a valid lane).  The
-                // rolled loop pays index load -> shuffle -> load -> FMA serially, about 40 cycles per chain dof.
-                {
-                  const unsigned long long c0 = *reinterpret_cast<const unsigned long long*>(cn.chain);
-                  const unsigned long long c1 = *reinterpret_cast<const unsigned long long*>(cn.chain + 8);
-                  double acc1 = 0;
-#pragma unroll
-                  for (int d = 0; d < MAXD; d++) {
-                    const int j = (int)((d < 8 ? c0 >> (8 * d) : c1 >> (8 * (d - 8))) & 0xffull);
-                    const double wj = shfl(w, j);
-                    const double m = Ah[j * RS + lc];
-                    const double t = d <= dep ? wj : 0.0;
-                    if (d & 1) acc1 = fma(-m, t, acc1); else acc = fma(-m, t, acc);
-                  }
-                  acc += acc1;
-                }
-#elif RP_CH_ACC2
-                // two partial sums: halves the serial length of the accumulation (chain[] is zero-padded)
-                double acc2 = 0;
-#pragma unroll 1
-                for (int d = 0; d <= dep; d += 2) {
-                  const int j = cn.chain[d], j2 = cn.chain[d + 1];
-                  const double wj = shfl(w, j), wj2 = shfl(w, j2);
-                  acc -= Ah[j * RS + lc] * wj;
-                  acc2 -= Ah[j2 * RS + lc] * (d + 1 <= dep ? wj2 : 0.0);
-                }
-                acc += acc2;
-#else
 #pragma unroll kChUnroll
                 for (int d = 0; d <= dep; d++) {
                   const int j = cn.chain[d];
                   const double wj = shfl(w, j);
                   acc -= Ah[j * RS + lc] * wj;
                 }
-#endif
                 va += acc;
                 }
               }
@@ -1696,12 +1391,6 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     // Euler with implicit joint damping: (M + h*D) a = qfrc_smooth + qfrc_constraint
     double aeul = 0;
     if (HANDS) {
-#if RP_EULER_FACTOR
-      __syncwarp();
-      if (hl) sm.Mrow[h][moff + ldep] += hstep * dm->link_damping[h][lane];  // the diagonal of this link's packed row
-      __syncwarp();
-      aeul = factor_solve(sm.Mrow[h], sm.moff[h], &sm.anc[h][0][0], sm.dep[h], sm.sub[h], sm.wbuf[h], qfrc_smooth + qfrc_c, lane);
-#else
       double* Aw = sm.A[h];
       __syncwarp();
       for (int idx = lane; idx < NL * RS; idx += 32) Aw[idx] = 0;
@@ -1724,7 +1413,6 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         for (int i = 0; i < NL; i++) acc -= Aw[lane * RS + i] * sm.wbuf[h][i];
         aeul = acc;
       }
-#endif
     }
     // integrate
     if (hl) {

@@ -9,17 +9,6 @@
 #define RP_HD inline
 #endif
 
-#ifndef RP_HINTS
-#define RP_HINTS 0
-#endif
-#if RP_HINTS  // branch layout hints for the contact update (hot path falls through)
-#define RP_LIKELY(x) __builtin_expect(!!(x), 1)
-#define RP_UNLIKELY(x) __builtin_expect(!!(x), 0)
-#else
-#define RP_LIKELY(x) (x)
-#define RP_UNLIKELY(x) (x)
-#endif
-
 #define RP_MINVAL 1e-15
 #define RP_MINIMP 0.0001
 #define RP_MAXIMP 0.9999
@@ -330,7 +319,7 @@ RP_HD void qcqp2_prepare(QcqpPre& q, const double* Ain, const double* d) {
 }
 RP_HD int qcqp2_solve(double* res, const QcqpPre& q, const double* bin, const double* d, double r) {
   const double b1 = bin[0] * d[0], b2 = bin[1] * d[1];
-  if (RP_UNLIKELY(!q.ok)) { res[0] = 0; res[1] = 0; return 0; }
+  if (!q.ok) { res[0] = 0; res[1] = 0; return 0; }
   double la = 0, P11 = q.P11, P22 = q.P22, P12 = q.P12, v1, v2;
   for (int iter = 0;;) {
     v1 = -P11 * b1 - P12 * b2;
@@ -341,9 +330,9 @@ RP_HD int qcqp2_solve(double* res, const QcqpPre& q, const double* bin, const do
     const double delta = -val * rcp(deriv);
     if (delta < 1e-10) break;
     la += delta;
-    if (RP_UNLIKELY(++iter >= 20)) break;
+    if (++iter >= 20) break;
     const double det = (q.A11 + la) * (q.A22 + la) - q.A12 * q.A12;
-    if (RP_UNLIKELY(det < 1e-10)) { res[0] = 0; res[1] = 0; return 0; }
+    if (det < 1e-10) { res[0] = 0; res[1] = 0; return 0; }
     const double detinv = rcp(det);
     P11 = (q.A22 + la) * detinv; P22 = (q.A11 + la) * detinv; P12 = -q.A12 * detinv;
   }
@@ -367,16 +356,16 @@ RP_HD void pgs_elliptic_pre(EllPre& p, const double* A, const double* f, double 
 RP_HD double pgs_elliptic_post(const EllPre& p, const double* A, const double* res, double* f, double mu) {
   const double* old = p.old;
   const double fr[2] = {mu, mu};
-  if (RP_UNLIKELY(p.lowf)) {
+  if (p.lowf) {
     f[0] -= res[0] * p.rA0;
     if (f[0] < 0) f[0] = 0;
     f[1] = f[2] = 0;
-  } else if (RP_LIKELY(p.den_ok)) {
+  } else if (p.den_ok) {
     double x = -dot3(old, res) * p.rden;
     if (f[0] + x * old[0] < 0) x = -1.0;
     for (int r = 0; r < 3; r++) f[r] += x * old[r];
   }
-  if (RP_LIKELY(f[0] >= RP_MINVAL)) {
+  if (f[0] >= RP_MINVAL) {
     double bc[2], vv[2];
     for (int r = 1; r < 3; r++) {
       double t = res[r];
@@ -397,7 +386,7 @@ RP_HD double pgs_elliptic_post(const EllPre& p, const double* A, const double* r
   double Ad[3];
   for (int r = 0; r < 3; r++) Ad[r] = A[3 * r] * dl[0] + A[3 * r + 1] * dl[1] + A[3 * r + 2] * dl[2];
   double change = 0.5 * dot3(dl, Ad) + dot3(dl, res);
-  if (RP_UNLIKELY(change > 1e-10)) { f[0] = old[0]; f[1] = old[1]; f[2] = old[2]; change = 0; }
+  if (change > 1e-10) { f[0] = old[0]; f[1] = old[1]; f[2] = old[2]; change = 0; }
   return change;
 }
 // primal map of an elliptic contact: jar (3) -> force (3)  (mj_constraintUpdate)
