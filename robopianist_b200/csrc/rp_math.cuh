@@ -1,5 +1,6 @@
-// rp_math.cuh — scalar building blocks of the step kernel (host+device so they can be unit-tested
-// on the CPU against the oracle: tests/test_hd_math.py builds csrc/hd_harness.cpp with g++).
+// rp_math.cuh — scalar building blocks of the step kernel (host+device so they can be unit-tested on the
+// CPU: tests/test_hd_math.py builds tests/csrc/hd_*.cpp with g++ and checks them against brute force,
+// MuJoCo's documented formulas and each other).
 #pragma once
 #include <math.h>
 

@@ -59,3 +59,113 @@ def test_absolute_force_friction_sweep_matches_classic():
         assert np.allclose(fx_own, f1, atol=1e-13)
         assert np.allclose(va2, va1, atol=1e-12)
         assert abs(imp1 - imp2) < 1e-12
+
+
+def _hd_geom(tmp_path):
+    import ctypes as C
+    so = tmp_path / "hd_geom.so"
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", f"-I{ROOT / 'robopianist_b200' / 'csrc'}", "-o", str(so),
+                           str(ROOT / "tests" / "csrc" / "hd_geom.cpp")])
+    L = C.CDLL(str(so))
+    dp = C.POINTER(C.c_double)
+    L.hd_sphere_box.restype = C.c_double; L.hd_sphere_box.argtypes = [dp, C.c_double, dp, dp, dp]
+    L.hd_segment_box_closest_t.restype = C.c_double; L.hd_segment_box_closest_t.argtypes = [dp, dp, dp]
+    L.hd_make_frame.argtypes = [dp]
+    L.hd_impedance.restype = C.c_double; L.hd_impedance.argtypes = [dp, C.c_double, C.c_double]
+    L.hd_ref_KB.argtypes = [dp, C.c_double, C.c_double, dp, dp]
+    L.hd_elliptic_primal_force.argtypes = [dp, dp, C.c_double, dp]
+    P = lambda a: a.ctypes.data_as(dp)
+    return L, P
+
+
+def _signed_point_box(p, half):
+    q = np.abs(p) - half
+    return np.linalg.norm(np.maximum(q, 0.0)) + min(q.max(), 0.0)
+
+
+def test_kernel_geometry_helpers_against_brute_force(tmp_path):
+    """The narrowphase building blocks the step kernel is compiled from (sphere_box, segment_box_closest_t,
+    make_frame), host build, against brute force: signed distance, unit normal, mid-point convention, the
+    closest point of a segment to a box by dense sampling, orthonormal right-handed contact frames."""
+    L, P = _hd_geom(tmp_path)
+    rng = np.random.default_rng(0)
+    for _ in range(3000):
+        half = rng.uniform(0.005, 0.08, 3)
+        c = rng.normal(size=3) * 0.08
+        r = rng.uniform(0.004, 0.012)
+        n, p = np.zeros(3), np.zeros(3)
+        dist = L.hd_sphere_box(P(c), r, P(half), P(n), P(p))
+        assert abs(dist - (_signed_point_box(c, half) - r)) < 1e-12
+        assert abs(np.linalg.norm(n) - 1) < 1e-12
+        s_box, s_sph = p + 0.5 * dist * n, p - 0.5 * dist * n
+        assert abs(_signed_point_box(s_box, half)) < 1e-12               # on the box surface
+        assert abs(np.linalg.norm(s_sph - c) - r) < 1e-12                 # on the sphere surface
+        assert np.linalg.norm((s_sph - r * n) - c) < 1e-12                # the normal points from the sphere to the box
+    for _ in range(400):
+        half = rng.uniform(0.005, 0.08, 3)
+        a, b = rng.normal(size=3) * 0.08, rng.normal(size=3) * 0.08
+        t = L.hd_segment_box_closest_t(P(a), P(b), P(half))
+        ts = np.linspace(0, 1, 4001)
+        d = np.array([np.linalg.norm(np.maximum(np.abs(a + u * (b - a)) - half, 0.0)) for u in ts])
+        dt = np.linalg.norm(np.maximum(np.abs(a + t * (b - a)) - half, 0.0))
+        assert 0.0 <= t <= 1.0 and dt <= d.min() + 1e-9
+    for _ in range(500):
+        f = np.zeros(9)
+        v = rng.normal(size=3)
+        f[:3] = v / np.linalg.norm(v)
+        L.hd_make_frame(P(f))
+        F = f.reshape(3, 3)
+        assert np.abs(F @ F.T - np.eye(3)).max() < 1e-12 and abs(np.linalg.det(F) - 1) < 1e-12
+
+
+def test_kernel_constraint_parameters_against_the_documented_formulas(tmp_path):
+    """impedance(), ref_KB() and the elliptic primal map of rp_math.cuh against numpy restatements of MuJoCo's
+    documented formulas (solimp sigmoid d(r); K = 1 / (dmax^2 tc^2 dr^2), B = 2 / (dmax tc), refsafe;
+    constraint-update force of an elliptic cone: zero / quadratic / projected zones)."""
+    L, P = _hd_geom(tmp_path)
+    rng = np.random.default_rng(1)
+
+    def imp_ref(si, pos, margin):
+        d0, d1 = np.clip(si[0], 1e-4, 0.9999), np.clip(si[1], 1e-4, 0.9999)
+        width, mid, power = max(si[2], 0.0), np.clip(si[3], 1e-4, 0.9999), max(si[4], 1.0)
+        if d0 == d1 or width <= 1e-15:
+            return 0.5 * (d0 + d1)
+        x = abs((pos - margin) / width)
+        if x >= 1:
+            return d1
+        if x <= 0:
+            return d0
+        if power == 1:
+            y = x
+        elif x <= mid:
+            y = x ** power / mid ** (power - 1)
+        else:
+            y = 1 - (1 - x) ** power / (1 - mid) ** (power - 1)
+        return d0 + y * (d1 - d0)
+
+    for _ in range(2000):
+        si = np.array([rng.uniform(0.3, 0.95), rng.uniform(0.9, 0.999), rng.choice([1e-4, 1e-3, 5e-3]), rng.uniform(0.2, 0.8), rng.choice([1.0, 2.0, 3.0])])
+        pos = rng.normal() * 3e-3
+        assert abs(L.hd_impedance(P(si), pos, 0.0) - imp_ref(si, pos, 0.0)) < 1e-12
+    K, B = np.zeros(1), np.zeros(1)
+    for _ in range(500):
+        sr = np.array([rng.choice([0.005, 0.01, 0.02, 0.05]), rng.uniform(0.5, 1.5)])
+        dmax, h = rng.uniform(0.9, 0.999), 0.005
+        L.hd_ref_KB(P(sr), dmax, h, P(K), P(B))
+        tc = max(sr[0], 2 * h)
+        assert abs(K[0] - 1 / (dmax ** 2 * tc ** 2 * sr[1] ** 2)) < 1e-6 * K[0] and abs(B[0] - 2 / (dmax * tc)) < 1e-9 * B[0]
+    f = np.zeros(3)
+    zones = set()
+    for _ in range(3000):
+        jar = rng.normal(size=3) * np.array([1.0, 2.0, 2.0])
+        D = 1.0 / rng.uniform(1e-3, 1e-1, 3); D[2] = D[1]
+        mu = rng.uniform(0.3, 1.5)
+        L.hd_elliptic_primal_force(P(jar), P(D), mu, P(f))
+        N, T = jar[0] * mu, mu * np.hypot(jar[1], jar[2])
+        if N >= mu * T:                       # separating inside the dual cone: no force
+            assert (f == 0).all(); zones.add(0)
+        elif mu * N + T <= 0:                 # inside the cone: plain quadratic
+            assert np.allclose(f, -D * jar, rtol=1e-12); zones.add(1)
+        else:                                 # in between: the force lies on the cone surface
+            assert f[0] > 0 and abs(np.hypot(f[1], f[2]) - mu * f[0]) < 1e-9 * max(1.0, f[0]); zones.add(2)
+    assert zones == {0, 1, 2}
