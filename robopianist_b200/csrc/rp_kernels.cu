@@ -48,6 +48,9 @@
 #ifndef RP_PHASE_MASK
 #define RP_PHASE_MASK 0  // extra block-wide phase barriers per substep (RP_EPB > 1): 1 before collision, 2 before PGS, 4 after PGS
 #endif
+#ifndef RP_MINV_LDL
+#define RP_MINV_LDL 0  // EXPERIMENTAL: M^-1 through the sparse L^T D L factorisation (see ldl_inverse); not measured yet
+#endif
 #ifndef RP_NU
 #define RP_NU 8  // contacts whose M^-1 Jc^T is kept in shared memory (the others walk the kinematic chain)
 #endif
@@ -116,6 +119,75 @@ struct Smem {
   } u;
   int ncon, nraw, overflow, pad;
 };
+
+#if RP_MINV_LDL
+// EXPERIMENTAL (round-2 candidate, not measured yet): A <- -(M + diag(extra))^-1 from
+// the packed rows of M through the tree-sparse L^T D L factorisation (the scheme of MuJoCo's mj_factorI /
+// mj_solveLD) instead of 26 dependent sweep pivots.  Factorisation: leaves first, the ancestors of k update
+// their packed rows in parallel.  Then all 26 unit right-hand sides at once: lane j owns column j of A and
+// runs both triangular solves in gather form (x_i -= sum over the subtree / the ancestors), reading the
+// factor through broadcast loads — no shuffles, no barriers, every load independent of the lane's stores.
+// F: 160 + 32 doubles of scratch (factor, then 1/D).  Validated on the host in numpy against inv(M) on the
+// real hand tree (4e-16 relative); columns agree with the sweep up to rounding, symmetric up to rounding.
+__device__ __noinline__ void ldl_inverse(double* A, const double* Mrow, double extra, double* F, const unsigned char* moff,
+                                         const signed char* anc /*[NL][MAXD]*/, const signed char* dep, const signed char* sub,
+                                         int lane) {
+  const bool hl = lane < NL;
+  const int mydep = hl ? dep[lane] : 0, myoff = hl ? moff[lane] : 0, mysub = hl ? sub[lane] : 0;
+  double* Dinv = F + 160;
+  if (hl) {
+    for (int d = 0; d < mydep; d++) F[myoff + d] = Mrow[myoff + d];
+    F[myoff + mydep] = Mrow[myoff + mydep] + extra;
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int k = NL - 1; k >= 0; k--) {
+    const int depk = dep[k];
+    const double* rk = F + moff[k];
+    const double dinv = rp::rcp(rk[depk]);
+    if (depk > 0) {  // warp-uniform
+      const bool isanc = hl && lane < k && k < lane + mysub;
+      double t = 0;
+      if (isanc) {
+        t = rk[mydep] * dinv;
+        double r[MAXD], m[MAXD];
+#pragma unroll
+        for (int d = 0; d < MAXD; d++) { const int dd = d <= mydep ? d : mydep; r[d] = rk[dd]; m[d] = F[myoff + dd]; }
+#pragma unroll
+        for (int d = 0; d < MAXD; d++) if (d <= mydep) F[myoff + d] = m[d] - r[d] * t;
+      }
+      __syncwarp();
+      if (isanc) F[moff[k] + mydep] = t;  // L[k][lane]
+    }
+    if (lane == 0) Dinv[k] = dinv;
+    __syncwarp();
+  }
+  if (hl) {
+    double* x = A + lane;  // column `lane`, element i at x[i * RS]
+    for (int i = 0; i < NL; i++) x[i * RS] = i == lane ? -1.0 : 0.0;  // right-hand side -e_lane: the result is -M^-1
+    // x <- L^-T x: x_i -= sum over the proper subtree of i of L[k][i] x_k (those are final: descending i)
+#pragma unroll 1
+    for (int i = NL - 1; i >= 0; i--) {
+      const int di = dep[i], end = i + sub[i];
+      double acc = x[i * RS];
+#pragma unroll 4
+      for (int k = i + 1; k < end; k++) acc -= F[moff[k] + di] * x[k * RS];
+      x[i * RS] = acc;
+    }
+    // x <- L^-1 D^-1 x: x_k = x_k / D_k - sum over the proper ancestors i of k of L[k][i] x_i (final: ascending k)
+#pragma unroll 1
+    for (int k = 0; k < NL; k++) {
+      const int dk = dep[k];
+      const double* lk = F + moff[k];
+      double acc = x[k * RS] * Dinv[k];  // the D^-1 scaling folded into the read of the lane's own entry
+#pragma unroll 4
+      for (int d = 0; d < dk; d++) acc -= lk[d] * x[anc[k * MAXD + d] * RS];
+      x[k * RS] = acc;
+    }
+  }
+  __syncwarp();
+}
+#endif
 
 constexpr size_t kSmemStride = (sizeof(Smem) + 15) / 16 * 16;  // per-environment shared memory (RP_EPB > 1: slot stride)
 
@@ -522,7 +594,11 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       }
     TICK(1)
       // ---------------------------------------------------------------- invert M (symmetric sweep): A = -M^-1
+#if RP_MINV_LDL
+      ldl_inverse(Aw, sm.Mrow[h], 0.0, &sm.u.acc[h][0][0], sm.moff[h], &sm.anc[h][0][0], sm.dep[h], sm.sub[h], lane);
+#else
       sweep_inverse(Aw, &sm.anc[h][0][0], sm.dep[h], sm.sub[h], lane);
+#endif
       if (a.dbg && sub == 0 && h == 0) {
         double* dbg = a.dbg + (size_t)env * RP_DBG_STRIDE;
         for (int i = 0; i < NL; i++) if (hl) dbg[RP_DBG_MINV + i * NL + lane] = -Aw[i * RS + lane];
@@ -1407,7 +1483,12 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       }
       __syncwarp();
       // a = (M + h*D)^-1 rhs: sweep (A = -inverse), then one row-times-vector per lane
+#if RP_MINV_LDL
+      ldl_inverse(Aw, sm.Mrow[h], hl ? hstep * dm->link_damping[h][lane] : 0.0, &sm.u.acc[h][0][0], sm.moff[h], &sm.anc[h][0][0],
+                  sm.dep[h], sm.sub[h], lane);
+#else
       sweep_inverse(Aw, &sm.anc[h][0][0], sm.dep[h], sm.sub[h], lane);
+#endif
       if (hl) {
         double acc = 0;
         for (int i = 0; i < NL; i++) acc -= Aw[lane * RS + i] * sm.wbuf[h][i];
