@@ -208,7 +208,7 @@ def test_ldl_inverse_scheme_against_numpy(tmp_path):
         sub8 = sub.astype(np.int8)
         off = 0
         for j in range(NL):
-            moff[j] = off; off += dep[j] + 1
+            moff[j] = off; off += int(dep[j]) + 1
         assert off <= 160
         Mrow = np.zeros(160)
         for k in range(NL):
