@@ -79,7 +79,9 @@ typedef struct rp_task {
   int32_t disable_fingering_reward;
   int32_t disable_forearm_reward;
   int32_t reward_type;        /* self-actuated: 0 = negative L2, 1 = negative xent */
-  int32_t reserved;
+  int32_t ot_fingering_reward; /* with disable_fingering_reward: add the optimal-transport fingering term in its
+                               * place, as PianoWithShadowHands._set_rewards does (piano_with_shadow_hands.py:130-141,
+                               * 333-369); 0 = no fingering term at all */
   double energy_penalty_coef;
   const uint8_t *goal;        /* [T, 89] */
   const int8_t *fingering;    /* [T, 88] finger id 0..9 per goal key, -1 none */

@@ -4,7 +4,7 @@ Follows, line by line, the reference's Python:
   composer.Environment.step order: before_step -> n_sub x (physics.step,
   Piano.after_substep) -> after_step -> observables -> reward -> termination;
   robopianist/suite/tasks/piano_with_shadow_hands.py:176-220 (before/after_step, termination),
-  :251-331 (rewards), :371-412 (goal / fingering state), robopianist/models/piano/piano.py:178-192
+  :251-369 (rewards, incl. the optimal-transport fingering reward), :371-412 (goal / fingering state), robopianist/models/piano/piano.py:178-192
   (key state), robopianist/models/piano/midi_module.py:40-98 (MIDI messages per substep, record_midi=True),
   robopianist/suite/tasks/self_actuated_piano.py:38-57,143-243,
   dm_control.utils.rewards.tolerance (gaussian sigmoid, value_at_margin=0.1).
@@ -44,7 +44,7 @@ class RefEnv:
 
     def __init__(self, fm, goal, fingering, kind=0, n_steps_lookahead=1, wrong_press_termination=False,
                  disable_fingering_reward=False, disable_forearm_reward=False, energy_penalty_coef=5e-3,
-                 reward_type=0, maxcon=24, iterations=None, tolerance_=None):
+                 reward_type=0, maxcon=24, iterations=None, tolerance_=None, ot_fingering_reward=False):
         self.fm, self.kind = fm, kind
         self.goal = np.asarray(goal, np.float64)
         self.fingering = np.asarray(fingering)
@@ -53,6 +53,7 @@ class RefEnv:
         self.disable_fingering_reward = disable_fingering_reward
         self.disable_forearm_reward = disable_forearm_reward
         self.energy_coef, self.reward_type = energy_penalty_coef, reward_type
+        self.ot_fingering_reward = ot_fingering_reward and disable_fingering_reward and kind == 0
         self.om = O.OracleModel(fm, iterations, tolerance_)
         self.om.set_option(maxcon=maxcon)
         self.d = O.OracleData(self.om)
@@ -183,6 +184,27 @@ class RefEnv:
                         kp[0] += 0.35 * fm.geom_size[g, 0]
                         dists.append(np.linalg.norm(kp - d.site_xpos[hand * 5 + fi]))
                 terms["fingering_reward"] = float(tolerance(np.array(dists), (0, 0.01), 0.1).mean()) if dists else 0.0
+            elif self.ot_fingering_reward:
+                # _compute_ot_fingering_reward (piano_with_shadow_hands.py:333-369): left-hand fingertips first
+                from scipy.optimize import linear_sum_assignment
+                keys_to_press = np.flatnonzero(goal_current[:-1])
+                if keys_to_press.shape[0] == 0:
+                    terms["ot_fingering_reward"] = 1.0
+                else:
+                    tips = [d.site_xpos[5 + i].copy() for i in range(5)] + [d.site_xpos[i].copy() for i in range(5)]
+                    key_pos = []
+                    for k in keys_to_press:
+                        g = fm.key_geomid[k]
+                        kp = d.geom_xpos[g].copy()
+                        kp[-1] += 0.5 * fm.geom_size[g, 2]
+                        kp[0] += 0.35 * fm.geom_size[g, 0]
+                        key_pos.append(kp)
+                    dist = np.full((len(tips), len(key_pos)), 100.0)
+                    for i, f in enumerate(tips):
+                        for j, kpos in enumerate(key_pos):
+                            dist[i, j] = np.linalg.norm(kpos - f)
+                    ri, ci = linear_sum_assignment(dist)
+                    terms["ot_fingering_reward"] = float(np.mean(tolerance(dist[ri, ci], (0, 0.01), 0.1)))
             if not self.disable_forearm_reward:
                 terms["forearm_reward"] = 0.5  # hands cannot touch each other with disable_hand_collisions=True
             reward = sum(terms.values())

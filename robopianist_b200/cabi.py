@@ -55,7 +55,7 @@ class RpTask(C.Structure):
     _fields_ = [
         ("kind", C.c_int32), ("n_steps", C.c_int32), ("n_steps_lookahead", C.c_int32),
         ("wrong_press_termination", C.c_int32), ("disable_fingering_reward", C.c_int32),
-        ("disable_forearm_reward", C.c_int32), ("reward_type", C.c_int32), ("reserved", C.c_int32),
+        ("disable_forearm_reward", C.c_int32), ("reward_type", C.c_int32), ("ot_fingering_reward", C.c_int32),
         ("energy_penalty_coef", C.c_double),
         ("goal", C.POINTER(C.c_uint8)), ("fingering", C.POINTER(C.c_int8)),
     ]
@@ -91,7 +91,7 @@ def pack_model(fm, iterations=None, tolerance=None):
 def pack_task(kind: int, goal: np.ndarray, fingering: np.ndarray, n_steps_lookahead: int = 1,
               wrong_press_termination: bool = False, disable_fingering_reward: bool = False,
               disable_forearm_reward: bool = False, energy_penalty_coef: float = 5e-3,
-              reward_type: int = 0):
+              reward_type: int = 0, ot_fingering_reward: bool = False):
     t = RpTask()
     goal = np.ascontiguousarray(goal, np.uint8)
     fingering = np.ascontiguousarray(fingering, np.int8)
@@ -101,6 +101,7 @@ def pack_task(kind: int, goal: np.ndarray, fingering: np.ndarray, n_steps_lookah
     t.disable_fingering_reward = int(disable_fingering_reward)
     t.disable_forearm_reward = int(disable_forearm_reward)
     t.reward_type = int(reward_type)
+    t.ot_fingering_reward = int(ot_fingering_reward)
     t.energy_penalty_coef = float(energy_penalty_coef)
     t.goal = goal.ctypes.data_as(C.POINTER(C.c_uint8))
     t.fingering = fingering.ctypes.data_as(C.POINTER(C.c_int8))

@@ -41,6 +41,7 @@ struct rp_batch {
   uint8_t* activation;
   double* metrics;  // [N][RP_METRICS_STRIDE] musical metrics accumulators (see rp_get_metrics)
   uint32_t* midi_events;  // [N][midi_cap], allocated by rp_midi_enable
+  double* ot_scratch;     // [N][RP_OT_SCRATCH_DOUBLES], only for tasks with the optimal-transport fingering reward
   int32_t* midi_count;
   int midi_cap;
   // staging for rp_step_host
@@ -288,6 +289,7 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
   d.wrong_press_termination = task->wrong_press_termination;
   d.disable_fingering_reward = task->disable_fingering_reward;
   d.disable_forearm_reward = task->disable_forearm_reward;
+  d.ot_fingering = task->disable_fingering_reward && task->ot_fingering_reward && task->kind == 0;
   d.reward_type = task->reward_type;
   d.energy_coef = task->energy_penalty_coef;
   if (task->kind == 0) {
@@ -342,6 +344,7 @@ extern "C" rp_batch* rp_batch_create(const rp_model* model, int nenv, int device
   chk(dalloc(&b->diag, N * 3)); chk(dalloc(&b->activation, N * RP_NK));
   chk(dalloc(&b->metrics, N * RP_METRICS_STRIDE));
   chk(dalloc(&b->work, N)); chk(dalloc(&b->order, N));
+  if (model->dm.ot_fingering) chk(dalloc(&b->ot_scratch, N * RP_OT_SCRATCH_DOUBLES));
   size_t out_doubles = N * (model->obs_dim + 2 + 5) + (N + 7) / 8 + 8;
   chk(cudaMallocHost((void**)&b->h_action, sizeof(double) * N * model->act_dim));
   chk(cudaMallocHost((void**)&b->h_out, sizeof(double) * out_doubles));
@@ -361,7 +364,7 @@ extern "C" int rp_batch_destroy(rp_batch* b) {
   cudaFree(b->qpos); cudaFree(b->qvel); cudaFree(b->qacc_ws); cudaFree(b->ctrl); cudaFree(b->sustain);
   cudaFree(b->act_force); cudaFree(b->site_xpos); cudaFree(b->t_idx); cudaFree(b->step_type_state);
   cudaFree(b->diag); cudaFree(b->activation); cudaFree(b->metrics); cudaFree(b->work); cudaFree(b->order); cudaFree(b->dbg); cudaFree(b->d_action); cudaFree(b->d_out);
-  cudaFree(b->midi_events); cudaFree(b->midi_count);
+  cudaFree(b->midi_events); cudaFree(b->midi_count); cudaFree(b->ot_scratch);
   cudaFreeHost(b->h_action); cudaFreeHost(b->h_out);
   delete b;
   return 0;
@@ -412,6 +415,11 @@ extern "C" int rp_step(rp_batch* b, const double* action_dev, double* obs_dev, d
   a.action = action_dev; a.obs = obs_dev; a.reward = reward_dev; a.discount = discount_dev;
   a.step_type = step_type_dev; a.reward_terms = reward_terms_dev;
   if (launch(b, a)) return 1;
+  if (b->model->dm.ot_fingering && (reward_dev || reward_terms_dev)) {
+    CUDA_OK(rp_launch_ot_fingering(b->d_dm, b->nenv, b->t_idx, b->qpos, b->model->nv, b->site_xpos, b->d_goal, reward_dev,
+                                   reward_terms_dev, b->ot_scratch, b->stream));
+    b->launches++;
+  }
   // more environments than resident slots: sort the next launch longest-expected-first
   if (b->nenv >= 2048 && b->model->nhand > 0) {
     CUDA_OK(rp_launch_order(b->work, b->order, b->nenv, b->stream));

@@ -421,4 +421,81 @@ RP_HD void mix_params(const double* solref1, const double* solimp1, const double
   *mu = prio1 == prio2 ? fmax(fr1[0], fr2[0]) : (prio1 > prio2 ? fr1[0] : fr2[0]);
 }
 
+
+// dm_control.utils.rewards.tolerance(x, bounds=(lo, hi), margin, sigmoid="gaussian", value_at_margin=0.1)
+RP_HD double tolerance_gaussian(double x, double lo, double hi, double margin) {
+  if (x >= lo && x <= hi) return 1.0;
+  const double dd = (x < lo ? lo - x : x - hi) / margin;
+  const double sc = sqrt(-2 * log(0.1));
+  return exp(-0.5 * (dd * sc) * (dd * sc));
+}
+
+// Rectangular linear sum assignment for nr <= nc: the shortest-augmenting-path algorithm scipy's
+// linear_sum_assignment runs (Crouse 2016; rectangular_lsap: rows taken in order, the unvisited columns
+// scanned from the last to the first, ties resolved towards a column that is still free), restated so that
+// the optimal-transport fingering reward (piano_with_shadow_hands.py:333-369) picks the same pairs.
+// cost: row-major [nr][nc]; col4row [nr] out.  wd: nr + 2 nc doubles, wi: 4 nc + nr ints of scratch.
+RP_HD void lsa_rect(int nr, int nc, const double* cost, int* col4row, double* wd, int* wi) {
+  double *u = wd, *v = wd + nr, *spc = wd + nr + nc;
+  int *path = wi, *row4col = wi + nc, *remaining = wi + 2 * nc, *SC = wi + 3 * nc, *SR = wi + 4 * nc;
+  for (int i = 0; i < nr; i++) { u[i] = 0; col4row[i] = -1; }
+  for (int j = 0; j < nc; j++) { v[j] = 0; row4col[j] = -1; path[j] = -1; }
+  for (int cur = 0; cur < nr; cur++) {
+    double minVal = 0;
+    int num_remaining = nc, i = cur, sink = -1;
+    for (int it = 0; it < nc; it++) { remaining[it] = nc - it - 1; SC[it] = 0; spc[it] = HUGE_VAL; }
+    for (int r = 0; r < nr; r++) SR[r] = 0;
+    while (sink == -1) {
+      int index = -1;
+      double lowest = HUGE_VAL;
+      SR[i] = 1;
+      for (int it = 0; it < num_remaining; it++) {
+        const int j = remaining[it];
+        const double r = minVal + cost[i * nc + j] - u[i] - v[j];
+        if (r < spc[j]) { path[j] = i; spc[j] = r; }
+        if (spc[j] < lowest || (spc[j] == lowest && row4col[j] == -1)) { lowest = spc[j]; index = it; }
+      }
+      minVal = lowest;
+      if (index < 0) return;  // infeasible (non-finite costs): leaves col4row of the remaining rows at -1
+      const int j = remaining[index];
+      if (row4col[j] == -1) sink = j; else i = row4col[j];
+      SC[j] = 1;
+      remaining[index] = remaining[--num_remaining];
+    }
+    u[cur] += minVal;
+    for (int r = 0; r < nr; r++) if (SR[r] && r != cur) u[r] += minVal - spc[col4row[r]];
+    for (int j = 0; j < nc; j++) if (SC[j]) v[j] -= minVal - spc[j];
+    int j = sink;
+    while (true) {
+      const int r = path[j];
+      row4col[j] = r;
+      const int t = col4row[r]; col4row[r] = j; j = t;
+      if (r == cur) break;
+    }
+  }
+}
+
+// _compute_ot_fingering_reward (piano_with_shadow_hands.py:333-369): fingertip[10][3] (left hand first, as the
+// reference stacks them), keypos[K][3] in ascending key order; distance matrix [10][K], assignment, mean of
+// tolerance(d, (0, 0.01), margin 0.1, gaussian) over the min(10, K) assigned pairs; 1 if nothing is to be
+// pressed.  scipy transposes a tall matrix (K < 10) before solving: so does this.
+// wd: 10 K + (10 + 2 max(10, K)) doubles, wi: 4 max(10, K) + 2 * 10 ints.
+RP_HD double ot_fingering_reward(const double* fingertip, const double* keypos, int K, double* wd, int* wi) {
+  if (K <= 0) return 1.0;
+  const bool tall = K < 10;
+  const int nr = tall ? K : 10, nc = tall ? 10 : K;
+  double* cost = wd;
+  for (int f = 0; f < 10; f++)
+    for (int k = 0; k < K; k++) {
+      const double dx = keypos[3 * k] - fingertip[3 * f], dy = keypos[3 * k + 1] - fingertip[3 * f + 1], dz = keypos[3 * k + 2] - fingertip[3 * f + 2];
+      const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+      if (tall) cost[k * 10 + f] = dist; else cost[f * K + k] = dist;
+    }
+  int* col4row = wi;
+  lsa_rect(nr, nc, cost, col4row, wd + 10 * K, wi + 10);
+  double sum = 0;
+  for (int r = 0; r < nr; r++) sum += tolerance_gaussian(cost[r * nc + col4row[r]], 0.0, 0.01, 0.1);
+  return sum / nr;
+}
+
 }  // namespace rp

@@ -27,7 +27,7 @@ struct RpGeomParams {  // contact-relevant geom fields
 
 struct RpDevModel {
   // ---- options ----
-  int nhand, nu, nsub, iterations, task_kind, nkey_act, pad0, pad1;
+  int nhand, nu, nsub, iterations, task_kind, nkey_act, ot_fingering, pad1;
   double h, tol, impratio, solver_scale;  // solver_scale = 1/(meaninertia*max(1,nv))
   double gravity[3];
   // ---- keys ----

@@ -138,11 +138,9 @@ class BatchedPianoEnv:
         self.goal_table, self.fingering_table = goal, fing
         self.n_steps_lookahead = L
         has_fingering = bool((fing >= 0).any())
+        # piano_with_shadow_hands.py:109-111: no fingering in the song disables the fingering reward; whenever it is
+        # disabled the task adds the optimal-transport fingering reward in its place (:130-141, :333-369)
         self.disable_fingering_reward = bool(kw["disable_fingering_reward"]) or not has_fingering
-        if hands and not kw["disable_fingering_reward"] and not has_fingering:
-            raise NotImplementedError(
-                "songs without fingering use the optimal-transport fingering reward "
-                "(piano_with_shadow_hands.py:333-369): not implemented; pass disable_fingering_reward=True")
         self.disable_forearm_reward = bool(kw["disable_forearm_reward"])
         self.flat = cache.load_scene(task, gravity_compensation=bool(kw["gravity_compensation"]),
                                      physics_timestep=float(kw["physics_timestep"]),
@@ -153,7 +151,8 @@ class BatchedPianoEnv:
             n_steps_lookahead=L, wrong_press_termination=bool(kw["wrong_press_termination"]),
             disable_fingering_reward=self.disable_fingering_reward,
             disable_forearm_reward=bool(kw["disable_forearm_reward"]),
-            energy_penalty_coef=float(kw["energy_penalty_coef"]), reward_type=reward_type)
+            energy_penalty_coef=float(kw["energy_penalty_coef"]), reward_type=reward_type,
+            ot_fingering_reward=hands and self.disable_fingering_reward)
         self.num_envs, self.device = int(num_envs), torch.device("cuda", device)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -329,9 +328,10 @@ class PianoEnv:
         obs, rew, dis, st, terms = b.step_host(action[None])
         self._sustain = float(action[-1])
         names = _TERM_NAMES if b._hands else ("key_press_reward",)
-        enabled = [n for n in names if not (n == "fingering_reward" and b.disable_fingering_reward)
-                   and not (n == "forearm_reward" and b.disable_forearm_reward)]
-        self.task.reward_fn.reward_terms = {n: float(terms[0][names.index(n)]) for n in enabled}
+        enabled = [n for n in names if not (n == "forearm_reward" and b.disable_forearm_reward)]
+        # the fourth slot carries the fingering reward or, when that one is disabled, the optimal-transport one
+        rename = {"fingering_reward": "ot_fingering_reward"} if b.disable_fingering_reward else {}
+        self.task.reward_fn.reward_terms = {rename.get(n, n): float(terms[0][names.index(n)]) for n in enabled}
         step_type = StepType(int(st[0]))
         if step_type == StepType.LAST:
             self._reset_next = True

@@ -223,3 +223,43 @@ def test_ldl_inverse_scheme_against_numpy(tmp_path):
             X = -A[:NL * RS].reshape(NL, RS)[:, :NL]
             ref = np.linalg.inv(M + np.diag(extra))
             assert np.abs(X - ref).max() < 1e-14 * np.abs(ref).max()
+
+
+def test_assignment_solver_and_ot_reward_against_scipy(tmp_path):
+    """lsa_rect / ot_fingering_reward of rp_math.cuh (host build) against scipy.optimize.linear_sum_assignment,
+    which the reference calls (piano_with_shadow_hands.py:358): same pairs on continuous costs, same pairs on
+    integer costs with many ties (the scan order and tie rule are restated), and the reward of
+    _compute_ot_fingering_reward for 0..88 keys to press."""
+    import ctypes as C
+    from scipy.optimize import linear_sum_assignment
+    sys_path_oracle = str(ROOT)
+    import sys
+    sys.path.insert(0, sys_path_oracle)
+    from oracle.task_ref import tolerance
+    so = tmp_path / "hd_ot.so"
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", f"-I{ROOT / 'robopianist_b200' / 'csrc'}", "-o", str(so),
+                           str(ROOT / "tests" / "csrc" / "hd_ot.cpp")])
+    L = C.CDLL(str(so))
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.hd_ot_reward.restype = C.c_double
+    rng = np.random.default_rng(0)
+    for trial in range(600):
+        nr = int(rng.integers(1, 11)); nc = int(rng.integers(nr, 40))
+        cost = rng.uniform(0, 1, (nr, nc)) if trial % 2 == 0 else rng.integers(0, 4, (nr, nc)).astype(float)
+        cost = np.ascontiguousarray(cost)
+        col = np.zeros(nr, np.int32)
+        L.hd_lsa(nr, nc, cost.ctypes.data_as(dp), col.ctypes.data_as(ip))
+        r, c = linear_sum_assignment(cost)
+        assert (r == np.arange(nr)).all() and (c == col).all(), (trial, c, col)
+    for trial in range(300):
+        K = int(rng.integers(0, 14)) if trial % 10 else 88
+        fingers = rng.normal(size=(10, 3)) * 0.05
+        keys = fingers[rng.integers(0, 10, K)] + rng.normal(size=(K, 3)) * rng.choice([0.002, 0.02, 0.2]) if K else np.zeros((0, 3))
+        got = L.hd_ot_reward(np.ascontiguousarray(fingers).ctypes.data_as(dp), np.ascontiguousarray(keys.reshape(-1)).ctypes.data_as(dp) if K else None, K)
+        if K == 0:
+            assert got == 1.0
+            continue
+        dist = np.linalg.norm(keys[None, :, :] - fingers[:, None, :], axis=2)
+        ri, ci = linear_sum_assignment(dist)
+        ref = float(np.mean(tolerance(dist[ri, ci], (0, 0.01), 0.1)))
+        assert abs(got - ref) < 1e-14, (trial, K, got, ref)

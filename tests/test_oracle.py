@@ -370,3 +370,34 @@ def test_step_invariants_recomputed_in_numpy(hands):
         d.step1()      # restore the invariant control_step relies on
         checked += 1
     assert checked >= 8
+
+
+def test_ot_fingering_reward_of_the_reference_restatement(hands):
+    """piano_with_shadow_hands.py:130-141: with the fingering reward disabled (or no fingering in the song) the task
+    adds the optimal-transport fingering reward; RefEnv(ot_fingering_reward=True) restates it with scipy's
+    linear_sum_assignment, as the reference does: term in (0, 1], exactly 1 when no key is to be pressed, part of
+    the reward, and not larger than the assignment-free upper bound (every key matched to its nearest fingertip)."""
+    fm, _ = hands
+    goal, fing = helpers.song_tables("TwinkleTwinkleRousseau")
+    ref = task_ref.RefEnv(fm, goal, -np.ones_like(fing), disable_fingering_reward=True, ot_fingering_reward=True)
+    ref.reset()
+    acts = helpers.twinkle_actions()
+    saw_one = saw_less = 0
+    for t in range(40):
+        gprev = ref.goal_state[0].copy()
+        st, rew, disc, obs = ref.step(acts[t])
+        terms = ref.reward_terms
+        assert set(terms) == {"key_press_reward", "sustain_reward", "energy_reward", "ot_fingering_reward", "forearm_reward"}
+        assert abs(rew - sum(terms.values())) < 1e-12
+        r = terms["ot_fingering_reward"]
+        keys = np.flatnonzero(gprev[:-1])
+        if keys.size == 0:
+            assert r == 1.0; saw_one += 1
+        else:
+            assert 0.0 < r <= 1.0; saw_less += r < 1.0
+            d = ref.d
+            kp = np.array([d.geom_xpos[fm.key_geomid[k]] + [0.35 * fm.geom_size[fm.key_geomid[k], 0], 0, 0.5 * fm.geom_size[fm.key_geomid[k], 2]] for k in keys])
+            nearest = np.linalg.norm(kp[:, None, :] - d.site_xpos[None, :10, :], axis=2).min(axis=1)
+            assert r <= float(np.mean(task_ref.tolerance(nearest, (0, 0.01), 0.1))) + 1e-12
+    assert saw_one > 0 and saw_less > 0
+    assert obs.shape == (88 + 1 + 52 + 2 * 89,)   # no fingering observable
