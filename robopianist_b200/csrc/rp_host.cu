@@ -11,6 +11,7 @@
 
 #include "../../include/roboplay.h"
 #include "rp_kernels.h"
+#include "rp_task.cuh"
 #include "rp_math.cuh"
 
 static thread_local std::string g_err;
@@ -544,6 +545,13 @@ extern "C" int rp_get_midi(rp_batch* b, uint32_t* events, int32_t* counts) {
   if (events) CUDA_OK(cudaMemcpy(events, b->midi_events, sizeof(uint32_t) * (size_t)b->nenv * b->midi_cap, cudaMemcpyDeviceToHost));
   if (counts) CUDA_OK(cudaMemcpy(counts, b->midi_count, sizeof(int32_t) * (size_t)b->nenv, cudaMemcpyDeviceToHost));
   return 0;
+}
+
+// Debug hook (not part of the public header): the per-environment body of rp_ot_fingering_kernel run on the
+// host for one environment — lets the CPU tests check the wrapper's indexing without a GPU.
+extern "C" double rp_debug_ot_fingering_host(const rp_model* m, int t, const double* qpos, const double* site_xpos) {
+  std::vector<double> scratch(RP_OT_SCRATCH_DOUBLES);
+  return rp::ot_fingering_env(&m->dm, t, qpos, site_xpos, m->goal.data(), scratch.data());
 }
 
 extern "C" int64_t rp_launch_count(const rp_batch* b) { return b->launches; }

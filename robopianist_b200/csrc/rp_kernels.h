@@ -60,9 +60,7 @@ struct RpKernelArgs {
 size_t rp_kernel_smem_bytes();
 cudaError_t rp_launch_step(const RpKernelArgs& a, int nhand, cudaStream_t stream, int block_envs);
 cudaError_t rp_launch_order(const int32_t* work, int32_t* order, int n, cudaStream_t stream);
-// optimal-transport fingering reward (rp_task_kernels.cu); per-environment scratch: fingertips 30, key positions
-// 3*88, cost matrix + solver doubles 10*88 + 10 + 2*88, solver integers (4*88 + 20) / 2
-#define RP_OT_SCRATCH_DOUBLES (30 + 3 * RP_NK + 10 * RP_NK + 10 + 2 * RP_NK + (4 * RP_NK + 20 + 1) / 2)
+// optimal-transport fingering reward (rp_task_kernels.cu; per-environment scratch: RP_OT_SCRATCH_DOUBLES of rp_task.cuh)
 cudaError_t rp_launch_ot_fingering(const RpDevModel* dm, int nenv, const int32_t* t_idx, const double* qpos, int nvtot,
                                    const double* site_xpos, const uint8_t* goal, double* reward, double* reward_terms,
                                    double* scratch, cudaStream_t stream);

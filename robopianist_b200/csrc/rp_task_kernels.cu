@@ -13,7 +13,7 @@
 #include <stdint.h>
 
 #include "rp_kernels.h"
-#include "rp_math.cuh"
+#include "rp_task.cuh"
 
 namespace {
 __global__ void rp_ot_fingering_kernel(const RpDevModel* __restrict__ dm, int nenv, const int32_t* __restrict__ t_idx,
@@ -23,35 +23,8 @@ __global__ void rp_ot_fingering_kernel(const RpDevModel* __restrict__ dm, int ne
   if (env >= nenv) return;
   const int t = t_idx[env];
   if (t == 0) return;  // FIRST step of an episode: no reward
-  const uint8_t* gcur = goal + (size_t)min(t - 1, dm->T - 1) * RP_GOAL_DIM_;
-  double* wd = scratch + (size_t)env * RP_OT_SCRATCH_DOUBLES;
-  double* tips = wd;
-  double* keyp = wd + 30;
-  const double* sx = site_xpos + (size_t)env * 2 * RP_NSITE * 3;  // [hand][site][3], right hand first
-  for (int f = 0; f < 2 * RP_NSITE; f++) {
-    const int src = (1 - f / RP_NSITE) * RP_NSITE + f % RP_NSITE;
-    for (int c = 0; c < 3; c++) tips[3 * f + c] = sx[3 * src + c];
-  }
-  int K = 0;
-  for (int k = 0; k < RP_NK; k++) {
-    if (!gcur[k]) continue;
-    // key geom centre in the world: body origin rotated about the hinge by the key's angle after this step
-    const double q = qpos[(size_t)env * nvtot + k];
-    double sn, cs;
-    sincos(q, &sn, &cs);
-    const double ax[3] = {dm->key_axis[k][0], dm->key_axis[k][1], dm->key_axis[k][2]};
-    const double v[3] = {-dm->key_jpos[k][0], -dm->key_jpos[k][1], -dm->key_jpos[k][2]};
-    double axv[3];
-    rp::cross3(axv, ax, v);
-    const double ad = rp::dot3(ax, v) * (1 - cs);
-    for (int c = 0; c < 3; c++) keyp[3 * K + c] = dm->key_pos[k][c] + dm->key_jpos[k][c] + (v[c] * cs + axv[c] * sn + ax[c] * ad);
-    keyp[3 * K + 2] += 0.5 * dm->key_half[k][2];
-    keyp[3 * K + 0] += 0.35 * dm->key_half[k][0];
-    K++;
-  }
-  double* work = keyp + 3 * RP_NK;
-  int* wi = reinterpret_cast<int*>(work + 10 * RP_NK + 10 + 2 * RP_NK);
-  const double r = rp::ot_fingering_reward(tips, keyp, K, work, wi);
+  const double r = rp::ot_fingering_env(dm, t, qpos + (size_t)env * nvtot, site_xpos + (size_t)env * 2 * RP_NSITE * 3, goal,
+                                        scratch + (size_t)env * RP_OT_SCRATCH_DOUBLES);
   if (reward_terms) reward_terms[(size_t)env * 5 + 3] = r;
   if (reward) reward[env] += r;
 }

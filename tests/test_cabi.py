@@ -39,3 +39,38 @@ def test_product_does_not_import_oracle():
     for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.h")) + list(pkg.rglob("*.cuh")):
         txt = p.read_text()
         assert "oracle" not in txt.replace("CPU oracle (oracle/)", "").replace("the oracle", "").lower() or p.name in ("compile.py",), p
+
+
+def test_ot_fingering_wrapper_on_the_host_matches_the_reference_logic():
+    """The per-environment body of rp_ot_fingering_kernel (csrc/rp_task.cuh: which goal row, fingertip stacking,
+    key poses from the key angles, scratch layout) run on the host through a debug entry of the library, fed
+    with the oracle's post-step positions and fingertip sites: equals the optimal-transport term the restated
+    reference task computes for the same step (piano_with_shadow_hands.py:333-369)."""
+    import ctypes as C
+    import sys
+    sys.path.insert(0, str(ROOT / "tests"))
+    import numpy as np
+    import helpers
+    from oracle import task_ref
+    from robopianist_b200.scene import cache
+    fm = cache.load_scene(gravity_compensation=True)
+    L = native.lib()
+    L.rp_debug_ot_fingering_host.restype = C.c_double
+    L.rp_debug_ot_fingering_host.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    dp = C.POINTER(C.c_double)
+    for song, steps in (("TwinkleTwinkleRousseau", 45), ("CMajorScaleTwoHands", 25)):
+        goal, fing = helpers.song_tables(song)
+        model = native.Model(fm, goal, fing, kind=0, disable_fingering_reward=True, ot_fingering_reward=True)
+        ref = task_ref.RefEnv(fm, goal, fing, disable_fingering_reward=True, ot_fingering_reward=True)
+        ref.reset()
+        acts = helpers.twinkle_actions()
+        partial = 0
+        for t in range(steps):
+            ref.step(acts[t])
+            q = np.ascontiguousarray(ref.d.qpos, np.float64)
+            sx = np.ascontiguousarray(ref.d.site_xpos[:10], np.float64)
+            got = L.rp_debug_ot_fingering_host(model.ptr, ref.t_idx, q.ctypes.data_as(dp), sx.ctypes.data_as(dp))
+            want = ref.reward_terms["ot_fingering_reward"]
+            assert abs(got - want) < 1e-12, (song, t, got, want)
+            partial += 0.0 < want < 1.0
+        assert partial > 5
