@@ -351,7 +351,11 @@ extern "C" rp_batch* rp_batch_create(const rp_model* model, int nenv, int device
   chk(cudaMallocHost((void**)&b->h_out, sizeof(double) * out_doubles));
   chk(dalloc(&b->d_action, N * model->act_dim));
   chk(dalloc(&b->d_out, out_doubles));
-  if (e != cudaSuccess) { fail(std::string("allocation failed: ") + cudaGetErrorString(e)); delete b; return nullptr; }
+  if (e != cudaSuccess) {  // release whatever was allocated before the failure
+    fail(std::string("allocation failed: ") + cudaGetErrorString(e));
+    rp_batch_destroy(b);
+    return nullptr;
+  }
   // step_type_state starts as MID so the first rp_step without rp_reset still steps
   std::vector<int32_t> mid(N, RP_STEP_MID_);
   cudaMemcpy(b->step_type_state, mid.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice);
