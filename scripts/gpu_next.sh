@@ -1,6 +1,10 @@
 #!/bin/bash
 # First GPU session of the next round: confirm the shipped build, then measure the prepared experiments.
-#   here (no GPU):  scripts/build_variants.sh base:"" ldl:"-DRP_MINV_LDL=1"
+#   here (no GPU):  scripts/build_variants.sh base:"" ldl:"-DRP_MINV_LDL=1" \
+#                       pgsbar:"-DRP_PHASE_EVERY=100 -DRP_PHASE_MASK=2" ldlpgsbar:"-DRP_MINV_LDL=1 -DRP_PHASE_EVERY=100 -DRP_PHASE_MASK=2"
+#   (ldl: M^-1 through the sparse factorisation, prepared and host-checked, never run on a GPU;
+#    pgsbar: the phase barrier moved from the top of the substep to the entry of the solver — untested idea:
+#    fast environments would overlap their next setup with the slow ones' sweeps)
 #   on the GPU box: bash scripts/gpu_next.sh [tag]
 TAG=${1:-r02a}
 OUT=gpurun_out/$TAG
