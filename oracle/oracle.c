@@ -810,6 +810,10 @@ void orc_make_constraint(const orc_model *o, orc_data *d) {
     /* R[i+2] = R[i+1]*mu^2/friction_t2^2; condim 3 uses the geom sliding friction for both
      * tangents (mjContact.friction[0] == friction[1]), so the factor is 1 */
     d->efc_R[i + 2] = d->efc_R[i + 1];
+    /* friction coefficient of the regularised cone (mj_makeImpedance: contact.mu = friction[0]*sqrt(R[i+1]/R[i])):
+     * with R_t = R_n/impratio the primal map of mj_constraintUpdate works in the space where the cone is regular;
+     * the dual solver (PGS) keeps using contact.friction */
+    con->mu = con->friction[0] * sqrt(d->efc_R[i + 1] / d->efc_R[i]);
   }
   for (int i = 0; i < nefc; i++) {
     d->efc_D[i] = 1 / d->efc_R[i];
@@ -1202,12 +1206,12 @@ int *orc_iptr(orc_data *d, const char *name) {
   if (!strcmp(name, "efc_id")) return d->efc_id;
   return NULL;
 }
-/* contact i -> out[0..] = dist, pos(3), frame(9), geom1, geom2, key, mu */
+/* contact i -> out[0..] = dist, pos(3), frame(9), geom1, geom2, key, mu (regularised cone), friction[0] */
 void orc_contact_get(orc_data *d, int i, double *out) {
   orc_contact *c = &d->con[i];
   out[0] = c->dist;
   memcpy(out + 1, c->pos, 3 * sizeof(double));
   memcpy(out + 4, c->frame, 9 * sizeof(double));
-  out[13] = c->geom1; out[14] = c->geom2; out[15] = c->key; out[16] = c->mu;
+  out[13] = c->geom1; out[14] = c->geom2; out[15] = c->key; out[16] = c->mu; out[17] = c->friction[0];
 }
 long orc_mac_count(orc_data *d) { return d->mac_count; }

@@ -177,10 +177,10 @@ class OracleData:
 
     def contacts(self):
         out = []
-        buf = (C.c_double * 17)()
+        buf = (C.c_double * 18)()
         for i in range(self.ncon):
             lib().orc_contact_get(self.ptr, i, buf)
             a = np.array(buf[:])
             out.append(dict(dist=a[0], pos=a[1:4], frame=a[4:13].reshape(3, 3), geom1=int(a[13]),
-                            geom2=int(a[14]), key=int(a[15]), mu=a[16]))
+                            geom2=int(a[14]), key=int(a[15]), mu=a[16], friction=a[17]))
         return out

@@ -973,7 +973,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       if (rowt && r == 0) {
         Contact& cn = sm.u.con[c];
         double jar[3] = {cn.f[0], cn.f[1], cn.f[2]}, D[3] = {1.0 / cn.R[0], 1.0 / cn.R[1], 1.0 / cn.R[2]};
-        rp::elliptic_primal_force(jar, D, cn.mu, cn.f);
+        rp::elliptic_primal_force(jar, D, cn.mu * sqrt(cn.R[1] / cn.R[0]), cn.mu, cn.f);
       }
       env_sync<NW, EPB>(bar_id);
     } else
@@ -1091,7 +1091,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
           jar[r] = s3 - cn.aref[r];
           D[r] = 1.0 / cn.R[r];
         }
-        rp::elliptic_primal_force(jar, D, cn.mu, cn.f);
+        rp::elliptic_primal_force(jar, D, cn.mu * sqrt(cn.R[1] / cn.R[0]), cn.mu, cn.f);
       }
       __syncwarp();
     }

@@ -390,9 +390,10 @@ RP_HD double pgs_elliptic_post(const EllPre& p, const double* A, const double* r
   if (change > 1e-10) { f[0] = old[0]; f[1] = old[1]; f[2] = old[2]; change = 0; }
   return change;
 }
-// primal map of an elliptic contact: jar (3) -> force (3)  (mj_constraintUpdate)
-RP_HD void elliptic_primal_force(const double* jar, const double* D, double mu, double* force) {
-  double U0 = jar[0] * mu, U1 = jar[1] * mu, U2 = jar[2] * mu;
+// primal map of an elliptic contact: jar (3) -> force (3)  (mj_constraintUpdate).  mu is the friction coefficient of
+// the regularised cone, friction[0] * sqrt(R_t / R_n) (mj_makeImpedance), fr the contact's own friction coefficient.
+RP_HD void elliptic_primal_force(const double* jar, const double* D, double mu, double fr, double* force) {
+  double U0 = jar[0] * mu, U1 = jar[1] * fr, U2 = jar[2] * fr;
   double N = U0, T = sqrt(U1 * U1 + U2 * U2);
   if ((N >= mu * T) || (T <= 0 && N >= 0)) {
     force[0] = force[1] = force[2] = 0;
@@ -402,8 +403,8 @@ RP_HD void elliptic_primal_force(const double* jar, const double* D, double mu, 
     double Dm = D[0] / (mu * mu * (1 + mu * mu));
     double NmT = N - mu * T;
     force[0] = -Dm * NmT * mu;
-    force[1] = -force[0] / T * U1 * mu;
-    force[2] = -force[0] / T * U2 * mu;
+    force[1] = -force[0] / T * U1 * fr;
+    force[2] = -force[0] / T * U2 * fr;
   }
 }
 // geom-pair parameter mixing (mj_contactParam)

@@ -7,5 +7,5 @@ double hd_point_box_d2(const double* c, const double* s) { return rp::point_box_
 void hd_make_frame(double* frame) { rp::make_frame(frame); }
 double hd_impedance(const double* solimp, double pos, double margin) { return rp::impedance(solimp, pos, margin); }
 void hd_ref_KB(const double* solref, double dmax, double h, double* K, double* B) { rp::ref_KB(solref, dmax, h, K, B); }
-void hd_elliptic_primal_force(const double* jar, const double* D, double mu, double* f) { rp::elliptic_primal_force(jar, D, mu, f); }
+void hd_elliptic_primal_force(const double* jar, const double* D, double mu, double fr, double* f) { rp::elliptic_primal_force(jar, D, mu, fr, f); }
 }

@@ -73,7 +73,7 @@ def _hd_geom(tmp_path):
     L.hd_make_frame.argtypes = [dp]
     L.hd_impedance.restype = C.c_double; L.hd_impedance.argtypes = [dp, C.c_double, C.c_double]
     L.hd_ref_KB.argtypes = [dp, C.c_double, C.c_double, dp, dp]
-    L.hd_elliptic_primal_force.argtypes = [dp, dp, C.c_double, dp]
+    L.hd_elliptic_primal_force.argtypes = [dp, dp, C.c_double, C.c_double, dp]
     P = lambda a: a.ctypes.data_as(dp)
     return L, P
 
@@ -158,16 +158,27 @@ def test_kernel_constraint_parameters_against_the_documented_formulas(tmp_path):
     zones = set()
     for _ in range(3000):
         jar = rng.normal(size=3) * np.array([1.0, 2.0, 2.0])
-        D = 1.0 / rng.uniform(1e-3, 1e-1, 3); D[2] = D[1]
-        mu = rng.uniform(0.3, 1.5)
-        L.hd_elliptic_primal_force(P(jar), P(D), mu, P(f))
-        N, T = jar[0] * mu, mu * np.hypot(jar[1], jar[2])
-        if N >= mu * T:                       # separating inside the dual cone: no force
+        impratio = rng.choice([1.0, 10.0, 3.0])
+        Rn = rng.uniform(1e-3, 1e-1)
+        D = np.array([1.0 / Rn, impratio / Rn, impratio / Rn])
+        fr = rng.uniform(0.3, 1.5)
+        mu = fr * np.sqrt((1 / D[1]) / (1 / D[0]))   # mj_makeImpedance: friction[0] * sqrt(R_t / R_n)
+        L.hd_elliptic_primal_force(P(jar), P(D), mu, fr, P(f))
+        N, T = jar[0] * mu, fr * np.hypot(jar[1], jar[2])
+        if N >= mu * T:                       # jar inside the dual of the friction cone: no force
             assert (f == 0).all(); zones.add(0)
-        elif mu * N + T <= 0:                 # inside the cone: plain quadratic
+            assert jar[0] >= fr * np.hypot(jar[1], jar[2]) * (1 - 1e-12)
+        elif mu * N + T <= 0:                 # the unconstrained minimiser -D jar is inside the friction cone
             assert np.allclose(f, -D * jar, rtol=1e-12); zones.add(1)
-        else:                                 # in between: the force lies on the cone surface
-            assert f[0] > 0 and abs(np.hypot(f[1], f[2]) - mu * f[0]) < 1e-9 * max(1.0, f[0]); zones.add(2)
+            assert np.hypot(f[1], f[2]) <= fr * f[0] * (1 + 1e-9)
+        else:                                 # in between: the force lies on the surface of the friction cone
+            assert f[0] > 0 and abs(np.hypot(f[1], f[2]) - fr * f[0]) < 1e-9 * max(1.0, f[0]); zones.add(2)
+            # ... and is the minimiser of 0.5 (f - f*)' R (f - f*) over the cone surface, f* = -D jar (KKT: gradient
+            # along the surface vanishes), which is what makes the map continuous across the zone borders
+            fs = -D * jar
+            t = f[1:] / np.hypot(f[1], f[2])
+            g = (f - fs) / D                  # gradient R (f - f*)
+            assert abs(g[0] + fr * (g[1:] @ t)) < 1e-7 * (abs(g).max() + 1e-12)
     assert zones == {0, 1, 2}
 
 

@@ -198,7 +198,7 @@ def test_pgs_fixed_point_satisfies_the_kkt_conditions(hands):
                 assert f[i] >= 0 and g[i] > -sc and abs(f[i] * g[i]) < sc * max(1.0, f[i])
                 i += 1
             else:                # elliptic contact, condim 3
-                mu = cons[eid[i]]["mu"]
+                mu = cons[eid[i]]["friction"]   # the dual solver works on the contact's own friction cone
                 fn, ft = f[i], np.hypot(f[i + 1], f[i + 2])
                 gn, gt = g[i], np.hypot(g[i + 1], g[i + 2])
                 assert fn >= 0 and ft <= mu * fn + 1e-9
@@ -401,3 +401,71 @@ def test_ot_fingering_reward_of_the_reference_restatement(hands):
             assert r <= float(np.mean(task_ref.tolerance(nearest, (0, 0.01), 0.1))) + 1e-12
     assert saw_one > 0 and saw_less > 0
     assert obs.shape == (88 + 1 + 52 + 2 * 89,)   # no fingering observable
+
+
+def test_warm_start_uses_the_regularised_cone_and_the_fixed_point_does_not_care(hands):
+    """mj_makeImpedance gives the friction rows of an elliptic contact R_t = R_n / impratio and the primal map of
+    mj_constraintUpdate the friction coefficient of the *regularised* cone, friction * sqrt(R_t / R_n); the dual
+    solver keeps the contact's own friction.  (1) The oracle's warm-start forces are the numpy restatement of that
+    map and differ from the un-regularised variant (impratio = 10 here) on sliding contacts; (2) every warm-start
+    force lies in the friction cone; (3) the converged PGS forces do not depend on the starting point."""
+    import ctypes as C
+    fm, _ = hands
+    om = O.OracleModel(fm, iterations=6000, tolerance=0.0)
+    om.set_option(maxcon=24)
+    d = O.OracleData(om)
+    d.reset()
+    acts = helpers.twinkle_actions()[:, :44]
+    nv = om.nv
+
+    def primal(jar, D, mu, fr):
+        N, T = jar[0] * mu, fr * np.hypot(jar[1], jar[2])
+        if N >= mu * T or (T <= 0 and N >= 0):
+            return np.zeros(3)
+        if mu * N + T <= 0 or (T <= 0 and N < 0):
+            return -D * jar
+        f0 = -D[0] / (mu * mu * (1 + mu * mu)) * (N - mu * T) * mu
+        return np.array([f0, -f0 / T * jar[1] * fr * fr, -f0 / T * jar[2] * fr * fr])
+
+    differs = middle = checked = 0
+    for t in range(40):
+        d.control_step(acts[t])
+        if d.ncon == 0:
+            continue
+        d.ctrl[:] = acts[t + 1]
+        d.call("orc_smooth"); d.call("orc_solve_init")
+        typ, eid = d.efc_type(), d.efc_id()
+        J, aref, R, f_ws = d.efc("efc_J"), d.efc("efc_aref"), d.efc("efc_R"), d.efc("efc_force")
+        jar = J @ d.qacc_warmstart - aref
+        cons = d.contacts()
+        kept = np.abs(f_ws).max() > 0          # the warm start is dropped as a whole when its dual cost is positive
+        i = 0
+        while i < len(typ):
+            if typ[i] != 2:
+                i += 1
+                continue
+            fr = cons[eid[i]]["friction"]
+            assert abs(R[i + 1] * fm.meta["impratio"] - R[i]) < 1e-12 * R[i]
+            mu = fr * np.sqrt(R[i + 1] / R[i])
+            assert abs(cons[eid[i]]["mu"] - mu) < 1e-15
+            want = primal(jar[i:i + 3], 1 / R[i:i + 3], mu, fr)
+            other = primal(jar[i:i + 3], 1 / R[i:i + 3], fr, fr)
+            if kept:
+                assert np.allclose(f_ws[i:i + 3], want, rtol=1e-10, atol=1e-12)
+                assert np.hypot(want[1], want[2]) <= fr * want[0] * (1 + 1e-9) + 1e-12
+                if want[0] > 0 and abs(np.hypot(want[1], want[2]) - fr * want[0]) < 1e-9 * want[0]:
+                    middle += 1
+                differs += int(not np.allclose(want, other, rtol=1e-6, atol=1e-9))
+            i += 3
+        if checked < 4:
+            # converged forces from the warm start and from zero
+            d.call("orc_solve_iterate")
+            f_a = d.efc("efc_force")
+            d.call("orc_smooth"); d.call("orc_solve_init")
+            p = O.lib().orc_ptr(d.ptr, b"efc_force")
+            np.ctypeslib.as_array(p, shape=(d.nefc,))[:] = 0
+            d.call("orc_solve_iterate")
+            f_b = d.efc("efc_force")
+            assert np.abs(f_a - f_b).max() < 1e-6 * max(1.0, np.abs(f_a).max())
+            checked += 1
+    assert checked == 4 and differs > 0 and middle > 0

@@ -108,7 +108,7 @@ def build_problem(fm, od, off, size):
         P[q + off["C_HAND"]] = h
         P[q + off["C_CK"]] = ckeys.index(k) if k >= 0 else -1
         P[q + off["C_DEP"]] = len(chain) - 1
-        P[q + off["C_MU"]] = con["mu"]
+        P[q + off["C_MU"]] = con["friction"]
         P[q + off["C_INVMK"]] = 1.0 / M[k, k] if k >= 0 else 0.0
         for r in range(3):
             P[q + off["C_JK"] + r] = J[i + r, k] if k >= 0 else 0.0
