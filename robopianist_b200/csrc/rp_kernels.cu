@@ -48,9 +48,6 @@
 #ifndef RP_PHASE_MASK
 #define RP_PHASE_MASK 0  // extra block-wide phase barriers per substep (RP_EPB > 1): 1 before collision, 2 before PGS, 4 after PGS
 #endif
-#ifndef RP_MINV_LDL
-#define RP_MINV_LDL 0  // EXPERIMENTAL: M^-1 through the sparse L^T D L factorisation (see ldl_inverse); not measured yet
-#endif
 #ifndef RP_NU
 #define RP_NU 8  // contacts whose M^-1 Jc^T is kept in shared memory (the others walk the kinematic chain)
 #endif
@@ -67,9 +64,10 @@ struct Contact {  // lives in shared memory
   double Jc[3][MAXD];  // hand-chain Jacobian entries by depth (already signed: body2 - body1)
   double Jk[3];        // key dof entry
   double A[9];         // 3x3 block of AR (R on the diagonal)
-  double R[3], b[3], f[3], aref[3];
+  double R[3], b[3], f[3];
   double mu, invMk;
-  int hand, link, key, dep;  // key = -1: piano base (static)
+  rp::EllInv inv;            // sweep-invariant part of the elliptic block update (1/A00, friction block at lambda = 0, ...)
+  int hand, link, key, dep;  // key = -1: piano base (static); dep: chain depth, bit 8: friction block regular (qcqp ok)
   signed char chain[16];     // dof (lane) at depth d of the hand chain
 };
 struct CKey {  // limit row of a key that is coupled to a hand through a contact
@@ -120,75 +118,6 @@ struct Smem {
   int ncon, nraw, overflow, pad;
 };
 
-#if RP_MINV_LDL
-// EXPERIMENTAL (round-2 candidate, not measured yet): A <- -(M + diag(extra))^-1 from
-// the packed rows of M through the tree-sparse L^T D L factorisation (the scheme of MuJoCo's mj_factorI /
-// mj_solveLD) instead of 26 dependent sweep pivots.  Factorisation: leaves first, the ancestors of k update
-// their packed rows in parallel.  Then all 26 unit right-hand sides at once: lane j owns column j of A and
-// runs both triangular solves in gather form (x_i -= sum over the subtree / the ancestors), reading the
-// factor through broadcast loads — no shuffles, no barriers, every load independent of the lane's stores.
-// F: 160 + 32 doubles of scratch (factor, then 1/D).  Validated on the host in numpy against inv(M) on the
-// real hand tree (4e-16 relative); columns agree with the sweep up to rounding, symmetric up to rounding.
-__device__ __noinline__ void ldl_inverse(double* A, const double* Mrow, double extra, double* F, const unsigned char* moff,
-                                         const signed char* anc /*[NL][MAXD]*/, const signed char* dep, const signed char* sub,
-                                         int lane) {
-  const bool hl = lane < NL;
-  const int mydep = hl ? dep[lane] : 0, myoff = hl ? moff[lane] : 0, mysub = hl ? sub[lane] : 0;
-  double* Dinv = F + 160;
-  if (hl) {
-    for (int d = 0; d < mydep; d++) F[myoff + d] = Mrow[myoff + d];
-    F[myoff + mydep] = Mrow[myoff + mydep] + extra;
-  }
-  __syncwarp();
-#pragma unroll 1
-  for (int k = NL - 1; k >= 0; k--) {
-    const int depk = dep[k];
-    const double* rk = F + moff[k];
-    const double dinv = rp::rcp(rk[depk]);
-    if (depk > 0) {  // warp-uniform
-      const bool isanc = hl && lane < k && k < lane + mysub;
-      double t = 0;
-      if (isanc) {
-        t = rk[mydep] * dinv;
-        double r[MAXD], m[MAXD];
-#pragma unroll
-        for (int d = 0; d < MAXD; d++) { const int dd = d <= mydep ? d : mydep; r[d] = rk[dd]; m[d] = F[myoff + dd]; }
-#pragma unroll
-        for (int d = 0; d < MAXD; d++) if (d <= mydep) F[myoff + d] = m[d] - r[d] * t;
-      }
-      __syncwarp();
-      if (isanc) F[moff[k] + mydep] = t;  // L[k][lane]
-    }
-    if (lane == 0) Dinv[k] = dinv;
-    __syncwarp();
-  }
-  if (hl) {
-    double* x = A + lane;  // column `lane`, element i at x[i * RS]
-    for (int i = 0; i < NL; i++) x[i * RS] = i == lane ? -1.0 : 0.0;  // right-hand side -e_lane: the result is -M^-1
-    // x <- L^-T x: x_i -= sum over the proper subtree of i of L[k][i] x_k (those are final: descending i)
-#pragma unroll 1
-    for (int i = NL - 1; i >= 0; i--) {
-      const int di = dep[i], end = i + sub[i];
-      double acc = x[i * RS];
-#pragma unroll 4
-      for (int k = i + 1; k < end; k++) acc -= F[moff[k] + di] * x[k * RS];
-      x[i * RS] = acc;
-    }
-    // x <- L^-1 D^-1 x: x_k = x_k / D_k - sum over the proper ancestors i of k of L[k][i] x_i (final: ascending k)
-#pragma unroll 1
-    for (int k = 0; k < NL; k++) {
-      const int dk = dep[k];
-      const double* lk = F + moff[k];
-      double acc = x[k * RS] * Dinv[k];  // the D^-1 scaling folded into the read of the lane's own entry
-#pragma unroll 4
-      for (int d = 0; d < dk; d++) acc -= lk[d] * x[anc[k * MAXD + d] * RS];
-      x[k * RS] = acc;
-    }
-  }
-  __syncwarp();
-}
-#endif
-
 constexpr size_t kSmemStride = (sizeof(Smem) + 15) / 16 * 16;  // per-environment shared memory (RP_EPB > 1: slot stride)
 
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
@@ -205,6 +134,12 @@ __device__ __forceinline__ void env_sync(int bar_id) {
   if (NW == 1) __syncwarp();
   else if (EPB == 1) __syncthreads();
   else { __syncwarp(); asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory"); }
+}
+// the two warps of one environment, on the environment's named barrier (also when the block holds a single
+// environment: pgs_solve is one function shared by every launch shape, which keeps their results bit-identical)
+__device__ __forceinline__ void hand_pair_sync(int bar_id) {
+  __syncwarp();
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
 }
 __device__ __forceinline__ void rotq(double* r, const double* q, const double* v) {
   double m[9];
@@ -263,6 +198,235 @@ __device__ __noinline__ void sweep_inverse(double* A, const signed char* anc /*[
     if (lane == k) A[k * RS + k] = -dinv;
     __syncwarp();
   }
+}
+
+#ifndef RP_FR_SEQ
+#define RP_FR_SEQ 12  // friction-loss rows: at least this many changing rows at the start of a sweep -> plain row-by-row sweep
+#endif
+#ifdef RP_PROFILE
+#define PTICK(i) { const long long tn = clock64(); tacc[i] += tn - *tlast; *tlast = tn; }
+#else
+#define PTICK(i)
+#endif
+
+struct PgsLane { double fr_f, lm_f, va; };
+
+// Projected Gauss-Seidel over the rows of one hand (one warp; lane == dof), MuJoCo's row order inside a sweep:
+// friction-loss dofs, joint limits (keys, then hand joints), contacts.  The two hands are independent islands
+// unless they touch the same key, so each warp sweeps the rows of its own hand and the rows of a key are handled
+// by the warp of the hand touching it.  If some key carries contacts of both hands (shared_key) the key rows go to
+// warp 0 and the contact rows are stepped in global order with an environment barrier per row.  One environment
+// barrier per sweep for MuJoCo's global convergence test.  A function of its own (not inlined, not a template: one
+// body for every launch shape) so that the hot loop gets a register allocation that does not have to carry the
+// lane state of the whole step.
+// Cost changes are accumulated warp-uniformly in row order (the committing lane broadcasts its term), the order
+// mj_solPGS adds them in.  Returns the number of sweeps; forces / va through io.
+__device__ __noinline__ int pgs_solve(Smem* smp, const int h, const int bar_id, const int ncon, const int maxiter, const double tol,
+                                      const double scale, const double improvement0, const double fr_R, const double fr_b,
+                                      const double fr_AR, const double fr_hi, const double lm_J, const double lm_R,
+                                      const double lm_b, const double lm_AR, const unsigned lm_mask, const int lsub,
+                                      const int ldc, PgsLane* io
+#ifdef RP_PROFILE
+                                      , long long* tacc, long long* tlast
+#endif
+) {
+  Smem& sm = *smp;
+  int lane;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+  const bool hl = lane < NL;
+  const int lc = hl ? lane : 0;
+  const double* const Ah = sm.A[h];
+  const double* const pcol = Ah + lc;
+  double fr_f = io->fr_f, lm_f = io->lm_f, va = io->va;
+  const int nck = sm.nck, shared_key = sm.shared_key, nmine = sm.nhc[h];
+  const double fr_ARi = 1.0 / fr_AR, lm_ARi = ((lm_mask >> lane) & 1u) ? 1.0 / lm_AR : 0.0;
+  const double fr_lo = -fr_hi;
+  // limit rows of the coupled keys this warp sweeps; an inactive row keeps its zero force (it never moves anything)
+  unsigned ckmask = 0;
+  for (int c = 0; c < nck; c++) {
+    const bool mine = shared_key ? (h == 0) : (sm.ckown[c] == h);
+    if (mine && sm.ck[c].active) ckmask |= 1u << c;
+  }
+  const signed char* const hlist = sm.hlist[h];
+  Contact* const con = sm.u.con;
+  const int ntrip = shared_key ? ncon : nmine;
+  const double imp0 = warp_sum(improvement0);
+  int iter = 0;
+  while (iter < maxiter) {
+    double improvement = iter == 0 ? imp0 : 0.0;
+    // ---- friction-loss rows, dof order (row i of the classic sweep: res = b + R f + va_i,
+    // f' = clamp(f - res / AR, +-frictionloss), va += M^-1[:, i] (f' - f), cost change (f' - f)(0.5 (f' - f) AR + res)).
+    // Every lane evaluates the update of its own row against the current va.  Few changing rows (most rows sit at
+    // +-frictionloss while the hand moves): a ballot finds the first row at or after the cursor whose force changes,
+    // that row commits and broadcasts, the search resumes behind it — the rows skipped in between would have
+    // committed a change of exactly zero at their turn, so the iterates are those of the row-by-row sweep.  Many
+    // changing rows (a hand at rest: stiction, nothing saturated): the plain row-by-row sweep, whose serial step is
+    // shorter (no ballot / find-first / dependent column load).
+    {
+      const double fbase = fr_b + fr_R * fr_f;  // f only changes at the lane's own commit
+      double res = fbase + va;
+      double x = fr_f - res * fr_ARi;
+      double fx = x < fr_lo ? fr_lo : x;
+      fx = x > fr_hi ? fr_hi : fx;
+      unsigned m = __ballot_sync(FULL, hl && fx != fr_f);
+      if (__popc(m) >= RP_FR_SEQ) {
+#pragma unroll 2
+        for (int i = 0; i < NL; i++) {
+          const double dl = fx - fr_f;
+          const double imp = dl * (0.5 * dl * fr_AR + res);
+          const double dbc = shfl(dl, i), ibc = shfl(imp, i);
+          va -= pcol[i * RS] * dbc;
+          improvement -= ibc;
+          if (lane == i) fr_f = fx;
+          res = fbase + va;
+          x = fr_f - res * fr_ARi;
+          fx = x < fr_lo ? fr_lo : x;
+          fx = x > fr_hi ? fr_hi : fx;
+          fx = lane <= i ? fr_f : fx;  // rows already visited (and the lanes without a row) stay put
+        }
+      } else {
+        while (m != 0u) {
+          const int i = __ffs(m) - 1;
+          const double dl = fx - fr_f;
+          const double imp = dl * (0.5 * dl * fr_AR + res);
+          const double dbc = shfl(dl, i), ibc = shfl(imp, i);
+          va -= pcol[i * RS] * dbc;
+          improvement -= ibc;
+          if (lane == i) fr_f = fx;
+          res = fbase + va;
+          x = fr_f - res * fr_ARi;
+          fx = x < fr_lo ? fr_lo : x;
+          fx = x > fr_hi ? fr_hi : fx;
+          m = __ballot_sync(FULL, hl && lane > i && fx != fr_f);
+        }
+      }
+    }
+    PTICK(8)
+    // ---- limit rows of keys that carry contacts (values in shared memory, every lane computes the same)
+    for (unsigned mm = ckmask; mm; mm &= mm - 1) {
+      CKey& ck = sm.ck[__ffs(mm) - 1];
+      const int key = ck.key;
+      const double vak = sm.vak[key], f = ck.f;
+      const double res = ck.b + ck.R * f + ck.J * vak;
+      double fn = f - res * ck.ARi;
+      fn = fn < 0 ? 0.0 : fn;
+      const double dl = fn - f;
+      __syncwarp();
+      improvement -= dl * (0.5 * dl * ck.AR + res);
+      ck.f = fn;  // every lane stores the same value
+      sm.vak[key] = vak + ck.J * dl * ck.invM;
+      __syncwarp();
+    }
+    if (shared_key) hand_pair_sync(bar_id);
+    // ---- hand limit rows
+    {
+      const double lbase = lm_b + lm_R * lm_f;
+      for (unsigned m2 = lm_mask; m2; m2 &= m2 - 1) {
+        const int i = __ffs(m2) - 1;
+        const double res = lbase + lm_J * va;
+        const double x = lm_f - res * lm_ARi;
+        const double fn = x < 0 ? 0.0 : x;
+        const double dl = fn - lm_f;
+        const double imp = dl * (0.5 * dl * lm_AR + res);
+        const double dbc = shfl(lm_J * dl, i), ibc = shfl(imp, i);
+        va -= Ah[i * RS + lc] * dbc;
+        improvement -= ibc;
+        if (lane == i) lm_f = fn;
+      }
+    }
+    PTICK(9)
+    // ---- contacts of this hand, sorted order.  The per-lane Jacobian entries of the next contact are fetched while
+    // the current one is being updated; the block of the current one arrives in the shadow of the J*v reduction.
+    if (ntrip > 0) {
+      int c = shared_key ? 0 : hlist[0];
+      double j0, j1, j2;
+      {
+        const Contact& q = con[c];
+        const int link = q.link;
+        const bool anc = lane <= link && link < lane + lsub;
+        j0 = anc ? q.Jc[0][ldc] : 0.0; j1 = anc ? q.Jc[1][ldc] : 0.0; j2 = anc ? q.Jc[2][ldc] : 0.0;
+      }
+      for (int ci = 0; ci < ntrip; ci++) {
+        Contact& cn = con[c];
+        const int cnext = ci + 1 < ntrip ? (shared_key ? ci + 1 : (int)hlist[ci + 1]) : c;
+        double n0, n1, n2;
+        {
+          const Contact& q = con[cnext];
+          const int link = q.link;
+          const bool anc = lane <= link && link < lane + lsub;
+          n0 = anc ? q.Jc[0][ldc] : 0.0; n1 = anc ? q.Jc[1][ldc] : 0.0; n2 = anc ? q.Jc[2][ldc] : 0.0;
+        }
+        if (!shared_key || cn.hand == h) {
+          double p0 = j0 * va, p1 = j1 * va, p2 = j2 * va;
+          const int key = cn.key, depq = cn.dep;
+          double Ab[9], fold[3], rbase[3];
+#pragma unroll
+          for (int k = 0; k < 9; k++) Ab[k] = cn.A[k];
+          const double cmu = cn.mu;
+          const rp::EllInv inv = cn.inv;
+          const double vak = sm.vak[key >= 0 ? key : 0], jkm0 = key >= 0 ? 1.0 : 0.0;
+          const double jk0 = cn.Jk[0], jk1 = cn.Jk[1], jk2 = cn.Jk[2], invMk = cn.invMk;
+#pragma unroll
+          for (int r = 0; r < 3; r++) { fold[r] = cn.f[r]; rbase[r] = cn.b[r] + cn.R[r] * fold[r] + jkm0 * cn.Jk[r] * vak; }
+#if RP_NU > 0
+          double u0 = 0, u1 = 0, u2 = 0;
+          if (c < RP_NU) { const double* Uc = &sm.v.U[c][0][lc]; u0 = Uc[0]; u1 = Uc[NL]; u2 = Uc[2 * NL]; }
+#endif
+          int den_ok;
+          const double rden = rp::pgs_elliptic_ray(Ab, fold, &den_ok);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            p0 += __shfl_xor_sync(FULL, p0, o);
+            p1 += __shfl_xor_sync(FULL, p1, o);
+            p2 += __shfl_xor_sync(FULL, p2, o);
+          }
+          PTICK(16)
+          const double res[3] = {rbase[0] + p0, rbase[1] + p1, rbase[2] + p2};
+          double f[3] = {fold[0], fold[1], fold[2]};
+          const double change = rp::pgs_elliptic_apply(inv, depq >> 8, rden, den_ok, Ab, res, f, cmu);
+          const double df0 = f[0] - fold[0], df1 = f[1] - fold[1], df2 = f[2] - fold[2];
+          PTICK(17)
+          __syncwarp();
+          improvement -= change;
+          cn.f[0] = f[0]; cn.f[1] = f[1]; cn.f[2] = f[2];  // identical on every lane
+          if (df0 != 0.0 || df1 != 0.0 || df2 != 0.0) {  // warp-uniform; an unchanged force moves nothing
+            if (key >= 0) sm.vak[key] = vak + (jk0 * df0 + jk1 * df1 + jk2 * df2) * invMk;
+#if RP_NU > 0
+            if (c < RP_NU) {
+              va += fma(u2, df2, fma(u1, df1, u0 * df0));
+            } else
+#endif
+            {
+              // hand side: w = Jc^T df on the chain, va += Minv[:,chain] w
+              const double w = j0 * df0 + j1 * df1 + j2 * df2;
+              const int dep = depq & 0xff;
+              double acc = 0;
+#pragma unroll 1
+              for (int d = 0; d <= dep; d++) {
+                const int j = cn.chain[d];
+                const double wj = shfl(w, j);
+                acc -= Ah[j * RS + lc] * wj;
+              }
+              va += acc;
+            }
+          }
+          __syncwarp();
+          PTICK(18)
+        }
+        if (shared_key) hand_pair_sync(bar_id);
+        c = cnext; j0 = n0; j1 = n1; j2 = n2;
+      }
+    }
+    PTICK(10)
+    if (lane == 0) sm.red[iter & 1][h][1] = improvement;
+    hand_pair_sync(bar_id);
+    PTICK(11)
+    improvement = (sm.red[iter & 1][0][1] + sm.red[iter & 1][H1][1]) * scale;
+    iter++;
+    if (improvement < tol) break;
+  }
+  io->fr_f = fr_f; io->lm_f = lm_f; io->va = va;
+  return iter;
 }
 
 }  // namespace
@@ -414,7 +578,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
   const double tol = a.tolerance >= 0 ? a.tolerance : dm->tol;
 
 #ifdef RP_PROFILE
-  long long tacc[16] = {0}, tlast = clock64();
+  long long tacc[RP_DBG_NPROF] = {0}, tlast = clock64();
 #define TICK(i) { const long long tn = clock64(); tacc[i] += tn - tlast; tlast = tn; }
 #else
 #define TICK(i)
@@ -594,11 +758,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       }
     TICK(1)
       // ---------------------------------------------------------------- invert M (symmetric sweep): A = -M^-1
-#if RP_MINV_LDL
-      ldl_inverse(Aw, sm.Mrow[h], 0.0, &sm.u.acc[h][0][0], sm.moff[h], &sm.anc[h][0][0], sm.dep[h], sm.sub[h], lane);
-#else
       sweep_inverse(Aw, &sm.anc[h][0][0], sm.dep[h], sm.sub[h], lane);
-#endif
       if (a.dbg && sub == 0 && h == 0) {
         double* dbg = a.dbg + (size_t)env * RP_DBG_STRIDE;
         for (int i = 0; i < NL; i++) if (hl) dbg[RP_DBG_MINV + i * NL + lane] = -Aw[i * RS + lane];
@@ -856,9 +1016,10 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     // NOTE: on overflow the kept subset depends on atomic order; the flag marks the env invalid.
     const int ncon = nraw;
     ncon_last = ncon;
-    // ---- contact rows (rank-sorted into con[]).  Up to 21 contacts: one thread per (contact, frame row),
-    // spread over both warps, which cuts the serial length of this stage ~3x; more: one lane per contact.
-    if (HANDS && ncon > 0 && 3 * ncon <= KT) {
+    // ---- contact rows (rank-sorted into con[]): one thread per (contact, frame row), spread over both warps
+    // (RP_MAXCON = 21 contacts = 63 rows)
+    static_assert(!HANDS || 3 * MAXCON <= KT, "one thread per contact row");
+    if (HANDS && ncon > 0) {
       if (tid < nraw) {
         const unsigned mykey = sm.u.raw[tid].sortkey;
         int rank = 0;
@@ -881,7 +1042,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         ch = rc.hand; c_geom = rc.geom; c_key = rc.key;
       }
       env_sync<NW, EPB>(bar_id);
-      double u[MAXD], arefr = 0;
+      double u[MAXD], arefr = 0, mu_row = 0;
       int link = 0, dep = 0;
       if (rowt) {
         Contact& cn = sm.u.con[c];
@@ -927,12 +1088,12 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         const double diag = dm->link_body_invw[ch][link] + (c_key >= 0 ? dm->key_body_invw[c_key] : 0.0);
         const double Rn = fmax(RP_MINVAL, (1 - imp) * diag / imp);
         cn.R[r] = r == 0 ? Rn : Rn / fmax(RP_MINVAL, dm->impratio);
+        mu_row = mu;
         // row velocity -> reference acceleration
         double sv = 0;
         for (int d = 0; d <= dep; d++) sv += jrow[d] * sm.v.pre.vh[ch][sm.anc[ch][link][d]];
         if (c_key >= 0) sv += jk * sm.v.pre.vk[c_key];
         arefr = r == 0 ? -B * sv - K * imp * (c_dist - incl) : -B * sv;
-        cn.aref[r] = arefr;
         // u = Minv_chain Jc_r^T (kept in registers for the A block)
 #pragma unroll 1
         for (int d = 0; d <= dep; d++) {
@@ -942,7 +1103,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
           u[d] = s2;
         }
         if (r == 0) {
-          cn.hand = ch; cn.link = link; cn.key = c_key; cn.dep = dep; cn.mu = mu;
+          cn.hand = ch; cn.link = link; cn.key = c_key; cn.mu = mu;
           cn.invMk = c_key >= 0 ? 1.0 / dm->key_M[c_key] : 0.0;
           for (int d = 0; d < 16; d++) cn.chain[d] = (signed char)(d <= dep ? sm.anc[ch][link][d] : 0);
         }
@@ -975,125 +1136,16 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         double jar[3] = {cn.f[0], cn.f[1], cn.f[2]}, D[3] = {1.0 / cn.R[0], 1.0 / cn.R[1], 1.0 / cn.R[2]};
         rp::elliptic_primal_force(jar, D, cn.mu * sqrt(cn.R[1] / cn.R[0]), cn.mu, cn.f);
       }
+      if (rowt && r == 1) {  // what the Gauss-Seidel update of this block needs in every sweep but that never changes
+        Contact& cn = sm.u.con[c];
+        double Ab[9];
+        for (int k = 0; k < 9; k++) Ab[k] = cn.A[k];
+        rp::EllInv q;
+        const int qok = rp::pgs_elliptic_invariants(q, Ab, mu_row);
+        cn.inv = q;
+        cn.dep = dep | (qok << 8);
+      }
       env_sync<NW, EPB>(bar_id);
-    } else
-    if (HANDS && h == 0 && ncon > 0) {  // > 21 contacts: warp 0, lane c builds contact c
-      int myrank = -1;
-      if (lane < nraw) {
-        const unsigned mykey = sm.u.raw[lane].sortkey;
-        myrank = 0;
-        for (int j = 0; j < nraw; j++) myrank += (sm.u.raw[j].sortkey < mykey) ? 1 : 0;
-      }
-      // contact geometry is first moved to registers: raw[] and con[] share the same shared memory
-      double c_dist = 0, c_pos[3] = {0, 0, 0}, c_frame[9];
-      int c_hand = 0, c_geom = 0, c_key = -1;
-      if (lane < ncon) {
-        RawContact rc = sm.u.raw[lane];
-        c_dist = rc.dist;
-        for (int k = 0; k < 3; k++) { c_pos[k] = rc.pos[k]; c_frame[k] = rc.n[k]; }
-        const double nn = sqrt(rp::dot3(c_frame, c_frame));
-        for (int k = 0; k < 3; k++) c_frame[k] /= nn;
-        rp::make_frame(c_frame);
-        c_hand = rc.hand; c_geom = rc.geom; c_key = rc.key;
-      }
-      __syncwarp();
-      if (lane < ncon) {
-        Contact& cn = sm.u.con[myrank];
-        const int ch = c_hand, link = dm->geom_link[ch][c_geom];
-        cn.hand = ch; cn.link = link; cn.key = c_key;
-        // mixed parameters
-        const RpGeomParams& g1 = dm->geom_gp[ch][c_geom];
-        const RpGeomParams& g2 = c_key < 0 ? dm->base_gp : dm->key_gp[c_key];
-        double solref[2], solimp[5], mu;
-        rp::mix_params(g1.solref, g1.solimp, g1.friction, g1.solmix, g1.priority, g2.solref, g2.solimp, g2.friction,
-                       g2.solmix, g2.priority, solref, solimp, &mu);
-        const double margin = fmax(g1.margin, g2.margin), gap = fmax(g1.gap, g2.gap), incl = margin - gap;
-        cn.mu = mu;
-        // Jacobian: rows = frame directions, body2 (key) minus body1 (hand link)
-        const int dep = sm.dep[ch][link];
-        cn.dep = dep;
-        for (int d = 0; d < 16; d++) cn.chain[d] = (signed char)(d <= dep ? sm.anc[ch][link][d] : 0);
-        const double* Ac = sm.A[ch];
-        for (int r = 0; r < 3; r++) {
-          const double* dir = c_frame + 3 * r;
-          for (int d = 0; d < MAXD; d++) {
-            double v = 0;
-            if (d <= dep) {
-              const int j = sm.anc[ch][link][d];
-              const double* S = sm.v.pre.S[ch][j];
-              double wxp[3];
-              rp::cross3(wxp, S, c_pos);
-              v = -(dir[0] * (S[3] + wxp[0]) + dir[1] * (S[4] + wxp[1]) + dir[2] * (S[5] + wxp[2]));
-            }
-            cn.Jc[r][d] = v;
-          }
-          double jk = 0;
-          if (c_key >= 0) {
-            double ax[3] = {dm->key_axis[c_key][0], dm->key_axis[c_key][1], dm->key_axis[c_key][2]};
-            double an[3] = {dm->key_pos[c_key][0] + dm->key_jpos[c_key][0], dm->key_pos[c_key][1] + dm->key_jpos[c_key][1],
-                            dm->key_pos[c_key][2] + dm->key_jpos[c_key][2]};
-            double lin[3], wxp[3];
-            rp::cross3(lin, an, ax);  // S_lin = anchor x axis
-            rp::cross3(wxp, ax, c_pos);
-            jk = dir[0] * (lin[0] + wxp[0]) + dir[1] * (lin[1] + wxp[1]) + dir[2] * (lin[2] + wxp[2]);
-          }
-          cn.Jk[r] = jk;
-        }
-        cn.invMk = c_key >= 0 ? 1.0 / dm->key_M[c_key] : 0.0;
-        // impedance / regularisation
-        const double imp = rp::impedance(solimp, c_dist, incl);
-        double K, B;
-        rp::ref_KB(solref, solimp[1], hstep, &K, &B);
-        const double diag = dm->link_body_invw[ch][link] + (c_key >= 0 ? dm->key_body_invw[c_key] : 0.0);
-        const double Rn = fmax(RP_MINVAL, (1 - imp) * diag / imp);
-        cn.R[0] = Rn;
-        cn.R[1] = Rn / fmax(RP_MINVAL, dm->impratio);
-        cn.R[2] = cn.R[1];
-        // velocities, aref, b, block A
-        double vel[3];
-        for (int r = 0; r < 3; r++) {
-          double sv = 0;
-          for (int d = 0; d <= dep; d++) sv += cn.Jc[r][d] * sm.v.pre.vh[ch][sm.anc[ch][link][d]];
-          if (c_key >= 0) sv += cn.Jk[r] * sm.v.pre.vk[c_key];
-          vel[r] = sv;
-        }
-        cn.aref[0] = -B * vel[0] - K * imp * (c_dist - incl);
-        cn.aref[1] = -B * vel[1];
-        cn.aref[2] = -B * vel[2];
-        // A = Jc Minv_chain Jc^T + Jk Jk^T / Mk + R
-        double u[3][MAXD];
-        for (int r = 0; r < 3; r++)
-          for (int d = 0; d <= dep; d++) {
-            const int jd = sm.anc[ch][link][d];
-            double s2 = 0;
-            for (int e = 0; e <= dep; e++) s2 -= Ac[jd * RS + sm.anc[ch][link][e]] * cn.Jc[r][e];
-            u[r][d] = s2;
-          }
-        for (int r = 0; r < 3; r++)
-          for (int s2 = 0; s2 < 3; s2++) {
-            double v = 0;
-            for (int d = 0; d <= dep; d++) v += cn.Jc[s2][d] * u[r][d];
-            v += cn.Jk[r] * cn.Jk[s2] * cn.invMk;
-            if (r == s2) v += cn.R[r];
-            cn.A[3 * s2 + r] = v;
-          }
-        // b = J qacc_smooth - aref; warm-start force from qacc_warmstart through the primal map
-        double jar[3], D[3];
-        for (int r = 0; r < 3; r++) {
-          double s2 = 0, s3 = 0;
-          for (int d = 0; d <= dep; d++) {
-            const int j = sm.anc[ch][link][d];
-            s2 += cn.Jc[r][d] * sm.wbuf[ch][j];
-            s3 += cn.Jc[r][d] * sm.v.pre.wsb[ch][j];
-          }
-          if (c_key >= 0) { s2 += cn.Jk[r] * sm.vak[c_key]; s3 += cn.Jk[r] * sm.kfc[c_key]; }
-          cn.b[r] = s2 - cn.aref[r];
-          jar[r] = s3 - cn.aref[r];
-          D[r] = 1.0 / cn.R[r];
-        }
-        rp::elliptic_primal_force(jar, D, cn.mu * sqrt(cn.R[1] / cn.R[0]), cn.mu, cn.f);
-      }
-      __syncwarp();
     }
     if (HANDS && h == 0 && ncon > 0) {
       // coupled keys, per-hand contact lists, cross-hand key sharing (sorted order: same key => adjacent)
@@ -1149,7 +1201,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         const int c = sm.hlist[h][ci];
         if (c < RP_NU) {  // warp-uniform
           const Contact& cn = sm.u.con[c];
-          const int dep = cn.dep;
+          const int dep = cn.dep & 0xff;
           double u0 = 0, u1 = 0, u2 = 0;
 #pragma unroll 1
           for (int d = 0; d <= dep; d++) {
@@ -1257,148 +1309,20 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     // hand touching it.  If some key carries contacts of both hands (shared_key) the key rows go to
     // warp 0 and the contact rows are stepped in global order with a block barrier per row.
     int iter = 0;
-    {
-      const double fr_ARi = 1.0 / fr_AR, lm_ARi = lm_on ? 1.0 / lm_AR : 0.0;
-      const double fr_hi = fr_on ? fr_loss : 0.0;
-      while (iter < maxiter) {
-        double improvement = iter == 0 ? improvement0 : 0.0;
-        if (HANDS) {
-          // ---- friction-loss rows, dof order (row i of the classic sweep: res = b + R f + va_i,
-          // f' = clamp(f - res / AR, +-frictionloss), va += M^-1[:, i] (f' - f), cost change -(f' - f)(0.5 (f' - f) AR + res)).
-          const double fbase = fr_b + fr_R * fr_f;  // f only changes at the lane's own commit
-          const double fr_lo = -fr_hi;
-          // Only rows whose force actually changes are stepped.  Every lane evaluates the update of its own row
-          // against the current va; a ballot finds the first row at or after the cursor with a non-zero change,
-          // that row commits and broadcasts, and the search resumes behind it.  The rows skipped in between
-          // would have committed a change of exactly zero at their turn (nothing moved since their candidate
-          // was evaluated), so the iterates are bit-identical to the row-by-row sweep.  In the bench workload
-          // 86 % of the friction-loss updates are such no-ops (rows saturated at +-frictionloss): a sweep costs
-          // ~4 serial steps per hand instead of 26.
-          {
-            const double* const pcol = Ah + lc;
-            int cursor = 0;
-            while (true) {
-              const double res = fbase + va;
-              const double x = fr_f - res * fr_ARi;
-              double fx = x < fr_lo ? fr_lo : x;
-              fx = x > fr_hi ? fr_hi : fx;
-              const unsigned m = __ballot_sync(FULL, hl && lane >= cursor && fx != fr_f);
-              if (m == 0u) break;
-              const int i = __ffs(m) - 1;
-              const double dl = fx - fr_f;
-              const double dbc = shfl(dl, i);
-              va -= pcol[i * RS] * dbc;
-              if (lane == i) { improvement -= dl * (0.5 * dl * fr_AR + res); fr_f = fx; }
-              cursor = i + 1;
-            }
-          }
-        }
-    TICK(8)
-        // ---- limit rows of keys that carry contacts (values in shared memory)
-        for (int c = 0; c < nck; c++) {
-          const bool mine = (!HANDS || shared_key) ? (h == 0) : (sm.ckown[c] == h);
-          if (mine) {
-            CKey& ck = sm.ck[c];
-            const double vak = sm.vak[ck.key], f = ck.f;
-            const double res = ck.b + ck.R * f + ck.J * vak;
-            double fn = f - res * ck.ARi;
-            fn = (fn < 0 || !ck.active) ? 0.0 : fn;
-            const double dl = fn - f;
-            __syncwarp();
-            improvement -= lane == 0 ? dl * (0.5 * dl * ck.AR + res) : 0.0;
-            ck.f = fn;                                    // every lane stores the same value
-            sm.vak[ck.key] = vak + ck.J * dl * ck.invM;
-            __syncwarp();
-          }
-        }
-        if (HANDS && shared_key) env_sync<NW, EPB>(bar_id);
-        if (HANDS) {
-          // ---- hand limit rows
-          const double lbase = lm_b + lm_R * lm_f;
-          for (unsigned m = lm_mask; m; m &= m - 1) {
-            const int i = __ffs(m) - 1;
-            const double res = lbase + lm_J * va;
-            const double x = lm_f - res * lm_ARi;
-            const double fn = x < 0 ? 0.0 : x;
-            const double dl = fn - lm_f;
-            const double dbc = shfl(lm_J * dl, i);
-            va -= Ah[i * RS + lc] * dbc;
-            if (lane == i) { improvement -= dl * (0.5 * dl * lm_AR + res); lm_f = fn; }
-          }
-    TICK(9)
-          // ---- contacts of this hand, sorted order
-          const int ntrip = shared_key ? ncon : nmine;
-          for (int ci = 0; ci < ntrip; ci++) {
-            const int c = shared_key ? ci : sm.hlist[h][ci];
-            Contact& cn = sm.u.con[c];
-            if (!shared_key || cn.hand == h) {
-              const int link = cn.link, key = cn.key, dep = cn.dep;
-              const bool anc = lane <= link && link < lane + lsub;
-              const double j0 = anc ? cn.Jc[0][ldc] : 0.0, j1 = anc ? cn.Jc[1][ldc] : 0.0, j2 = anc ? cn.Jc[2][ldc] : 0.0;
-              double part[3] = {j0 * va, j1 * va, j2 * va};
-              // residual-independent part of the update, issued ahead of the reduction so that it runs in the
-              // shadow of the shuffle latency: block loads, ray denominators, the lambda = 0 pass of the QCQP
-              double Ab[9], fold[3], rbase[3];
-#pragma unroll
-              for (int k = 0; k < 9; k++) Ab[k] = cn.A[k];
-              const double cmu = cn.mu;
-              {
-                const double vak0 = sm.vak[key >= 0 ? key : 0], jkm0 = key >= 0 ? 1.0 : 0.0;
-#pragma unroll
-                for (int r = 0; r < 3; r++) { fold[r] = cn.f[r]; rbase[r] = cn.b[r] + cn.R[r] * fold[r] + jkm0 * cn.Jk[r] * vak0; }
-              }
-              rp::EllPre pre;
-              rp::pgs_elliptic_pre(pre, Ab, fold, cmu);
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int r = 0; r < 3; r++) part[r] += __shfl_xor_sync(FULL, part[r], o);
-              }
-              double res[3], f[3];
-              const double vak = sm.vak[key >= 0 ? key : 0];
-              const double jkm = key >= 0 ? 1.0 : 0.0;
-              for (int r = 0; r < 3; r++) res[r] = rbase[r] + part[r];
-              f[0] = fold[0]; f[1] = fold[1]; f[2] = fold[2];
-              const double change = rp::pgs_elliptic_post(pre, Ab, res, f, cmu);
-              const double df[3] = {f[0] - fold[0], f[1] - fold[1], f[2] - fold[2]};
-              __syncwarp();
-              improvement -= lane == 0 ? change : 0.0;
-              cn.f[0] = f[0]; cn.f[1] = f[1]; cn.f[2] = f[2];  // identical on every lane
-              if (df[0] != 0.0 || df[1] != 0.0 || df[2] != 0.0) {  // warp-uniform; an unchanged force moves nothing
-                if (key >= 0) sm.vak[key] = vak + (cn.Jk[0] * df[0] + cn.Jk[1] * df[1] + cn.Jk[2] * df[2]) * cn.invMk;
-#if RP_NU > 0
-                if (c < RP_NU) {
-                  const double* Uc = &sm.v.U[c][0][lc];
-                  va += fma(Uc[2 * NL], df[2], fma(Uc[NL], df[1], Uc[0] * df[0]));
-                } else
+    if (HANDS) {
+      PgsLane io = {fr_f, lm_f, va};
+      iter = pgs_solve(&sm, h, bar_id, ncon, maxiter, tol, dm->solver_scale, improvement0, fr_R, fr_b, fr_AR,
+                            fr_on ? fr_loss : 0.0, lm_J, lm_R, lm_b, lm_AR, lm_mask, lsub, ldc, &io
+#ifdef RP_PROFILE
+                            , tacc, &tlast
 #endif
-                {
-                // hand side: w = Jc^T df on the chain, va += Minv[:,chain] w
-                const double w = j0 * df[0] + j1 * df[1] + j2 * df[2];
-                double acc = 0;
-#pragma unroll kChUnroll
-                for (int d = 0; d <= dep; d++) {
-                  const int j = cn.chain[d];
-                  const double wj = shfl(w, j);
-                  acc -= Ah[j * RS + lc] * wj;
-                }
-                va += acc;
-                }
-              }
-              __syncwarp();
-            }
-            if (shared_key) env_sync<NW, EPB>(bar_id);
-          }
-        }
-    TICK(10)
-        improvement = warp_sum(improvement);
-        if (HANDS) {
-          if (lane == 0) sm.red[iter & 1][h][1] = improvement;
-          env_sync<NW, EPB>(bar_id);
-          TICK(11)
-          improvement = sm.red[iter & 1][0][1] + sm.red[iter & 1][H1][1];
-        }
-        improvement *= dm->solver_scale;
+      );
+      fr_f = io.fr_f; lm_f = io.lm_f; va = io.va;
+    } else {
+      // keys only: every limit row is a 1 x 1 island solved in closed form above; the sweeps only run the
+      // convergence test (the first one sees the improvement of the closed-form updates)
+      while (iter < maxiter) {
+        double improvement = warp_sum(iter == 0 ? improvement0 : 0.0) * dm->solver_scale;
         iter++;
         if (improvement < tol) break;
       }
@@ -1460,7 +1384,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         double* o = dbg + RP_DBG_CONTACTS + tid * 16;
         o[0] = cn.key; o[1] = cn.hand; o[2] = cn.link; o[3] = cn.f[0]; o[4] = cn.f[1]; o[5] = cn.f[2];
         o[6] = cn.b[0]; o[7] = cn.b[1]; o[8] = cn.b[2]; o[9] = cn.R[0]; o[10] = cn.A[0]; o[11] = cn.A[4]; o[12] = cn.A[1];
-        o[13] = cn.aref[0]; o[14] = cn.mu; o[15] = cn.Jk[0];
+        o[13] = 0; o[14] = cn.mu; o[15] = cn.Jk[0];
       }
     }
     TICK(13)
@@ -1483,12 +1407,8 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       }
       __syncwarp();
       // a = (M + h*D)^-1 rhs: sweep (A = -inverse), then one row-times-vector per lane
-#if RP_MINV_LDL
-      ldl_inverse(Aw, sm.Mrow[h], hl ? hstep * dm->link_damping[h][lane] : 0.0, &sm.u.acc[h][0][0], sm.moff[h], &sm.anc[h][0][0],
-                  sm.dep[h], sm.sub[h], lane);
-#else
       sweep_inverse(Aw, &sm.anc[h][0][0], sm.dep[h], sm.sub[h], lane);
-#endif
+      TICK(14)
       if (hl) {
         double acc = 0;
         for (int i = 0; i < NL; i++) acc -= Aw[lane * RS + i] * sm.wbuf[h][i];
@@ -1533,6 +1453,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       }
     }
     env_sync<NW, EPB>(bar_id);
+    TICK(15)
   }  // substeps
 
   // ------------------------------------------------------------------ store state
@@ -1566,8 +1487,8 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     }
   }
 #ifdef RP_PROFILE
-  TICK(15)
-  if (a.dbg && lane == 0) for (int i = 0; i < 16; i++) a.dbg[(size_t)env * RP_DBG_STRIDE + RP_DBG_PROFILE + h * 16 + i] = (double)tacc[i];
+  TICK(19)
+  if (a.dbg && lane == 0) for (int i = 0; i < RP_DBG_NPROF; i++) a.dbg[(size_t)env * RP_DBG_STRIDE + RP_DBG_PROFILE + h * RP_DBG_NPROF + i] = (double)tacc[i];
 #endif
   if (a.mode == RP_MODE_PHYSICS) return;
 

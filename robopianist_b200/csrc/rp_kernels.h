@@ -24,8 +24,9 @@ enum { RP_STEP_FIRST_ = 0, RP_STEP_MID_ = 1, RP_STEP_LAST_ = 2 };
 #define RP_DBG_CONTACTS 656   // 24 x 16
 #define RP_DBG_M 1040         // 26 x 26 (hand 0)
 #define RP_DBG_MINV 1716      // 26 x 26 (hand 0)
-#define RP_DBG_PROFILE 2392      // 2 x 16 phase cycle counters (RP_PROFILE builds)
-#define RP_DBG_STRIDE 2432
+#define RP_DBG_PROFILE 2392      // 2 x 24 phase cycle counters (RP_PROFILE builds)
+#define RP_DBG_NPROF 24
+#define RP_DBG_STRIDE 2448
 
 struct RpKernelArgs {
   const RpDevModel* dm;

@@ -390,6 +390,85 @@ RP_HD double pgs_elliptic_post(const EllPre& p, const double* A, const double* r
   if (change > 1e-10) { f[0] = old[0]; f[1] = old[1]; f[2] = old[2]; change = 0; }
   return change;
 }
+// ---- Three-way split used by the step kernel's solver (pgs_solve): (1) what depends only on the block A and the
+// friction coefficient is evaluated once per substep and kept with the contact (EllInv: 1/A00, the scaled
+// friction block and its inverse at lambda = 0, 1/mu^2); (2) what depends on the force of the previous sweep but not
+// on the residual (the ray denominator) runs in the shadow of the J*v reduction; (3) the residual-dependent rest.
+// Same operations in the same order as pgs_elliptic_update: the results are bit-identical (tests/test_hd_math.py).
+struct EllInv { double rA0, A11, A22, A12, P11, P22, P12, imu2; };
+RP_HD int pgs_elliptic_invariants(EllInv& q, const double* A, double mu) {  // returns the "friction block regular" flag
+  q.rA0 = rcp(A[0]);
+  const double Ac[4] = {A[4], A[5], A[7], A[8]}, fr[2] = {mu, mu};
+  QcqpPre t;
+  qcqp2_prepare(t, Ac, fr);
+  q.A11 = t.A11; q.A22 = t.A22; q.A12 = t.A12; q.P11 = t.P11; q.P22 = t.P22; q.P12 = t.P12;
+  q.imu2 = rcp(fr[0] * fr[0]);
+  return t.ok;
+}
+RP_HD double pgs_elliptic_ray(const double* A, const double* f, int* den_ok) {  // 1 / (f' A f), valid when *den_ok
+  double v1[3];
+  for (int r = 0; r < 3; r++) v1[r] = A[3 * r] * f[0] + A[3 * r + 1] * f[1] + A[3 * r + 2] * f[2];
+  const double denom = dot3(f, v1);
+  *den_ok = denom >= RP_MINVAL;
+  return rcp(denom);
+}
+RP_HD double pgs_elliptic_apply(const EllInv& q, int qok, double rden, int den_ok, const double* A, const double* res,
+                                double* f, double mu) {
+  const double old[3] = {f[0], f[1], f[2]};
+  if (old[0] < RP_MINVAL) {
+    f[0] -= res[0] * q.rA0;
+    if (f[0] < 0) f[0] = 0;
+    f[1] = f[2] = 0;
+  } else if (den_ok) {
+    double x = -dot3(old, res) * rden;
+    if (f[0] + x * old[0] < 0) x = -1.0;
+    for (int r = 0; r < 3; r++) f[r] += x * old[r];
+  }
+  if (f[0] >= RP_MINVAL) {
+    double bc[2], vv[2] = {0, 0};
+    for (int r = 1; r < 3; r++) {
+      double t = res[r];
+      for (int s = 1; s < 3; s++) t -= A[3 * r + s] * old[s];
+      t += A[3 * r] * (f[0] - old[0]);
+      bc[r - 1] = t;
+    }
+    // mju_QCQP2 from its second pass on (the lambda = 0 inverse comes with the contact)
+    int flg = 0;
+    if (qok) {
+      const double b1 = bc[0] * mu, b2 = bc[1] * mu, rr = f[0] * f[0];
+      double la = 0, P11 = q.P11, P22 = q.P22, P12 = q.P12, v1, v2;
+      int okl = 1;
+      for (int iter = 0;;) {
+        v1 = -P11 * b1 - P12 * b2;
+        v2 = -P12 * b1 - P22 * b2;
+        const double val = v1 * v1 + v2 * v2 - rr;
+        if (val < 1e-10) break;
+        const double deriv = -2 * (P11 * v1 * v1 + 2 * P12 * v1 * v2 + P22 * v2 * v2);
+        const double delta = -val * rcp(deriv);
+        if (delta < 1e-10) break;
+        la += delta;
+        if (++iter >= 20) break;
+        const double det = (q.A11 + la) * (q.A22 + la) - q.A12 * q.A12;
+        if (det < 1e-10) { okl = 0; break; }
+        const double detinv = rcp(det);
+        P11 = (q.A22 + la) * detinv; P22 = (q.A11 + la) * detinv; P12 = -q.A12 * detinv;
+      }
+      if (okl) { vv[0] = v1 * mu; vv[1] = v2 * mu; flg = la != 0; }
+    }
+    if (flg) {
+      double s = vv[0] * vv[0] * q.imu2 + vv[1] * vv[1] * q.imu2;
+      s = sqrt(f[0] * f[0] * rcp(fmax(RP_MINVAL, s)));
+      vv[0] *= s; vv[1] *= s;
+    }
+    f[1] = vv[0]; f[2] = vv[1];
+  }
+  const double dl[3] = {f[0] - old[0], f[1] - old[1], f[2] - old[2]};
+  double Ad[3];
+  for (int r = 0; r < 3; r++) Ad[r] = A[3 * r] * dl[0] + A[3 * r + 1] * dl[1] + A[3 * r + 2] * dl[2];
+  double change = 0.5 * dot3(dl, Ad) + dot3(dl, res);
+  if (change > 1e-10) { f[0] = old[0]; f[1] = old[1]; f[2] = old[2]; change = 0; }
+  return change;
+}
 // primal map of an elliptic contact: jar (3) -> force (3)  (mj_constraintUpdate).  mu is the friction coefficient of
 // the regularised cone, friction[0] * sqrt(R_t / R_n) (mj_makeImpedance), fr the contact's own friction coefficient.
 RP_HD void elliptic_primal_force(const double* jar, const double* D, double mu, double fr, double* force) {

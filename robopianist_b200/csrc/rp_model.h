@@ -16,7 +16,7 @@
 #define RP_NAH 24     // actuators per hand, max
 #define RP_NSITE 5    // fingertip sites per hand
 #ifndef RP_MAXCON
-#define RP_MAXCON 24  // contact capacity per environment (shared memory: 480 B each)
+#define RP_MAXCON 21  // contact capacity per environment (shared memory: 584 B each; 3 x 21 rows = one thread per row)
 #endif
 #define RP_NPIANO 89  // piano boxes: index 0 = base, 1 + k = key k (MuJoCo body order)
 

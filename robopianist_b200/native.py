@@ -68,7 +68,6 @@ def lib():
         L.rp_launch_count.restype = C.c_int64
         L.rp_launch_count.argtypes = [vp]
         L.rp_debug_enable.argtypes = [vp, C.c_int]
-        L.rp_debug_pgs_solve.argtypes = [dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_float), C.c_int]
         L.rp_debug_read.argtypes = [vp, dp]
         _LIB = L
     return _LIB
@@ -241,15 +240,3 @@ class Batch:
         out = np.empty((self.nenv, stride))
         _check(lib().rp_debug_read(self.ptr, _dp(out)))
         return out
-
-
-def debug_pgs_solve(P, maxiter, tol, scale, repeat=1, staged=False):
-    """EXPERIMENTAL (csrc/rp_pgs_kernel.cu): solve the structure-of-arrays constraint problems P [PG_SIZE, nenv]
-    with the lane == environment Gauss-Seidel kernel; P is overwritten with the solution.  Returns the mean
-    kernel time in ms.  Not used by the step path."""
-    P = np.ascontiguousarray(P, np.float64)
-    ms = C.c_float(0)
-    rc = lib().rp_debug_pgs_solve(_dp(P), P.shape[1], int(maxiter), float(tol), float(scale), int(repeat), C.byref(ms), int(staged))
-    if rc:
-        raise NativeError(f"rp_debug_pgs_solve failed ({rc})")
-    return P, float(ms.value)

@@ -18,6 +18,10 @@ int main() {
     double c1 = rp::pgs_elliptic_update(A, res, f1, mu);
     rp::EllPre p; rp::pgs_elliptic_pre(p, A, f2, mu);
     double c2 = rp::pgs_elliptic_post(p, A, res, f2, mu);
+    double f3[3] = {f[0], f[1], f[2]};
+    rp::EllInv q; int qok = rp::pgs_elliptic_invariants(q, A, mu); int dok; double rden = rp::pgs_elliptic_ray(A, f3, &dok);
+    double c3 = rp::pgs_elliptic_apply(q, qok, rden, dok, A, res, f3, mu);
+    if (memcmp(f1, f3, sizeof f1) || memcmp(&c1, &c3, 8)) { if (bad < 5) printf("mismatch3 t=%d %g %g | %g %g %g | %g %g %g\n", t, c1, c3, f1[0], f1[1], f1[2], f3[0], f3[1], f3[2]); bad++; }
     if (memcmp(f1, f2, sizeof f1) || memcmp(&c1, &c2, 8)) { if (bad < 5) printf("mismatch t=%d %g %g | %g %g %g | %g %g %g\n", t, c1, c2, f1[0], f1[1], f1[2], f2[0], f2[1], f2[2]); bad++; }
     if (f1[0] > 0) nz++;
     if (f1[0] > 0 && fabs(f1[1]*f1[1] + f1[2]*f1[2] - mu*mu*f1[0]*f1[0]) < 1e-9) slide++;

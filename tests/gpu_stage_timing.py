@@ -1,14 +1,16 @@
 """Per-phase cycle counts of the step kernel (needs a build with -DRP_PROFILE; ROBOPLAY_LIB selects it).
-usage: python tests/gpu_stage_timing.py [N] [noise]"""
+usage: python tests/gpu_stage_timing.py [N] [step] [noise]   -- bench workload, measured at control step `step`."""
 import sys
 from pathlib import Path
 import numpy as np, torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1])); sys.path.insert(0, str(Path(__file__).resolve().parent))
 import helpers
-names = ["kin+RNE+CRB", "M scatter", "sweep M^-1", "act/smooth/rows/keys", "barrier waits (setup)", "collision", "contact setup (warp0)",
-         "warm start + cost", "pgs: friction", "pgs: key+limit rows", "pgs: contacts", "pgs: iteration barrier", "(unused)", "dual->primal", "Euler sweep", "integrate+store"]
+names = ["kinematics", "RNE+CRB+M scatter", "sweep M^-1", "act/smooth/rows/keys", "barrier waits (setup)", "collision", "contact setup",
+         "warm start + cost", "pgs: friction", "pgs: key+limit rows", "pgs: contacts tail", "pgs: iteration barrier", "after pgs", "dual->primal",
+         "Euler sweep", "integrate+sync", "pgs contact: load+pre+reduce", "pgs contact: post", "pgs contact: commit", "store"]
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 888
-noise = float(sys.argv[2]) if len(sys.argv) > 2 else 0.05
+step = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+noise = float(sys.argv[3]) if len(sys.argv) > 3 else 0.05
 fm, model, b = helpers.make_native("piano_with_shadow_hands", nenv=N)
 acts = helpers.twinkle_actions()
 lo = np.concatenate([fm.actuator_ctrlrange[:, 0], [0.0]]); hi = np.concatenate([fm.actuator_ctrlrange[:, 1], [1.0]])
@@ -18,17 +20,22 @@ b.reset(None, obs.data_ptr())
 def act(t):
     a = np.tile(acts[t], (N, 1)) + rng.normal(0, noise, (N, 45)) * (hi - lo) / 2
     return torch.tensor(np.clip(a, lo, hi), dtype=torch.float64, device="cuda")
-for t in range(20):
+for t in range(step):
     b.step(act(t).data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
 b.debug_enable(True)
-b.step(act(20).data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a = act(step)
+e0.record()
+b.step(a.data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
+e1.record()
 torch.cuda.synchronize()
 d = b.debug_read()
 dg = b.get_diag()
-print("envs", N, "niter(last substep) mean", dg["niter"].mean(), "ncon mean", dg["ncon"].mean())
+NP = 24
+print("envs", N, "step", step, "ms", e0.elapsed_time(e1), "niter(last substep) mean", dg["niter"].mean(), "ncon mean", dg["ncon"].mean(), "ncon max", dg["ncon"].max())
 for w in range(2):
-    t = d[:, 2392 + 16 * w: 2392 + 16 * w + 16].mean(axis=0)
+    t = d[:, 2392 + NP * w: 2392 + NP * w + NP].mean(axis=0) / 10.0
     tot = t.sum()
-    print(f"--- warp {w}: total {tot/1e6:.3f} Mcycles per env-step (= {tot/1.965e6:.3f} ms at 1.965 GHz)")
+    print(f"--- warp {w}: total {tot/1e3:.1f} kcycles per env-substep (= {tot/1.965e3:.1f} us at 1.965 GHz)")
     for n, v in zip(names, t):
-        if v > 0: print(f"  {n:28s} {v/1e3:9.1f} kcycles {100*v/tot:5.1f}%")
+        if v > 0: print(f"  {n:30s} {v/1e3:9.2f} kcycles {100*v/tot:5.1f}%")

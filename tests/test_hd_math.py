@@ -182,60 +182,6 @@ def test_kernel_constraint_parameters_against_the_documented_formulas(tmp_path):
     assert zones == {0, 1, 2}
 
 
-def test_ldl_inverse_scheme_against_numpy(tmp_path):
-    """The tree-sparse L^T D L route to M^-1 (experimental RP_MINV_LDL path of the step kernel; host emulation in
-    tests/csrc/hd_ldl.cpp, same packed layout and loop structure) on the real hand trees and mass matrices:
-    -(M + diag(extra))^-1 to rounding."""
-    import ctypes as C
-    import sys
-    sys.path.insert(0, str(ROOT / "tests"))
-    import helpers
-    from oracle import oracle as O
-    from robopianist_b200.scene import cache
-    so = tmp_path / "hd_ldl.so"
-    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-o", str(so), str(ROOT / "tests" / "csrc" / "hd_ldl.cpp")])
-    L = C.CDLL(str(so))
-    fm = cache.load_scene(gravity_compensation=True)
-    om = O.OracleModel(fm); om.set_option(maxcon=24)
-    d = O.OracleData(om); d.reset()
-    acts = helpers.twinkle_actions()[:, :44]
-    for t in range(15):
-        d.control_step(acts[t])
-    NK, NL, MAXD, RS = 88, 26, 10, 27
-    par = fm.arrays["dof_parentid"]
-    for h in range(2):
-        base = NK + NL * h
-        M = d.M[base:base + NL, base:base + NL].copy()
-        parent = [int(par[base + j]) - base if par[base + j] >= base else -1 for j in range(NL)]
-        anc = np.zeros((NL, MAXD), np.int8); dep = np.zeros(32, np.int8); sub = np.ones(32, np.int32); moff = np.zeros(32, np.uint8)
-        for j in range(NL):
-            c, p = [], j
-            while p >= 0:
-                c.append(p); p = parent[p]
-            c = c[::-1]; dep[j] = len(c) - 1; anc[j, :len(c)] = c
-        for j in range(NL - 1, -1, -1):
-            if parent[j] >= 0:
-                sub[parent[j]] += sub[j]
-        sub8 = sub.astype(np.int8)
-        off = 0
-        for j in range(NL):
-            moff[j] = off; off += int(dep[j]) + 1
-        assert off <= 160
-        Mrow = np.zeros(160)
-        for k in range(NL):
-            for dd in range(dep[k] + 1):
-                Mrow[moff[k] + dd] = M[k, anc[k, dd]]
-        for extra in (np.zeros(NL), 0.005 * fm.arrays["dof_damping"][base:base + NL]):
-            A = np.zeros(NL * RS + 8)
-            dp = C.POINTER(C.c_double)
-            L.ldl_host(A.ctypes.data_as(dp), Mrow.ctypes.data_as(dp), np.ascontiguousarray(extra).ctypes.data_as(dp),
-                       moff.ctypes.data_as(C.POINTER(C.c_ubyte)), anc.ctypes.data_as(C.POINTER(C.c_byte)),
-                       dep.ctypes.data_as(C.POINTER(C.c_byte)), sub8.ctypes.data_as(C.POINTER(C.c_byte)))
-            X = -A[:NL * RS].reshape(NL, RS)[:, :NL]
-            ref = np.linalg.inv(M + np.diag(extra))
-            assert np.abs(X - ref).max() < 1e-14 * np.abs(ref).max()
-
-
 def test_assignment_solver_and_ot_reward_against_scipy(tmp_path):
     """lsa_rect / ot_fingering_reward of rp_math.cuh (host build) against scipy.optimize.linear_sum_assignment,
     which the reference calls (piano_with_shadow_hands.py:358): same pairs on continuous costs, same pairs on
