@@ -220,6 +220,24 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
       d.link_subtree[h][l] += 1;
       if (d.link_parent[h][l] >= 0) d.link_subtree[h][d.link_parent[h][l]] += d.link_subtree[h][l];
     }
+    {  // sweep schedule: pivots are taken leaves first (k = NL-1 .. 0); runs are stored in pivot order k = 0 .. NL-1
+      int np = 0;
+      for (int k = 0; k < RP_NL; k++) {
+        d.sw_off[h][k] = np;
+        int S[RP_NL], n = 0;
+        for (int dd = 0; dd < d.link_depth[h][k]; dd++) S[n++] = d.link_anc[h][k][dd];
+        for (int i = k + 1; i < k + d.link_subtree[h][k]; i++) S[n++] = i;
+        for (int a = 0; a < n; a++)
+          for (int b2 = a; b2 < n; b2++) {
+            if (np >= RP_SW_MAXPAIRS) return bad("sweep schedule too long");
+            d.sw_pairs[h][np++] = (uint16_t)(S[a] * 32 + S[b2]);
+          }
+      }
+      d.sw_off[h][RP_NL] = np;
+      if (np > RP_SW_NPAIRS_SMEM) return bad("sweep schedule exceeds the kernel's shared-memory copy");
+      if (h > 0 && (memcmp(d.sw_off[h], d.sw_off[0], sizeof(d.sw_off[0])) || memcmp(d.sw_pairs[h], d.sw_pairs[0], sizeof(uint16_t) * np)))
+        return bad("the hands must have the same kinematic tree (one sweep schedule is shared)");
+    }
     {
       int nchild[RP_NL] = {0};
       for (int l = 0; l < RP_NL; l++) {

@@ -32,9 +32,6 @@
 #ifndef RP_CH_UNROLL
 #define RP_CH_UNROLL 1
 #endif
-#ifndef RP_SW_UNROLL
-#define RP_SW_UNROLL 2
-#endif
 #ifndef RP_EPB
 #define RP_EPB RP_BLOCK_ENVS  // environments per thread block of the phase-locked variant (see rp_step_kernel)
 #endif
@@ -58,7 +55,7 @@
 namespace {
 
 constexpr int kPhaseExtra = ((RP_PHASE_MASK) & 1) + (((RP_PHASE_MASK) >> 1) & 1) + (((RP_PHASE_MASK) >> 2) & 1);
-constexpr int kChUnroll = RP_CH_UNROLL, kSwUnroll = RP_SW_UNROLL;
+constexpr int kChUnroll = RP_CH_UNROLL;
 
 struct Contact {  // lives in shared memory
   double Jc[3][MAXD];  // hand-chain Jacobian entries by depth (already signed: body2 - body1)
@@ -119,6 +116,10 @@ struct Smem {
 };
 
 constexpr size_t kSmemStride = (sizeof(Smem) + 15) / 16 * 16;  // per-environment shared memory (RP_EPB > 1: slot stride)
+// block-shared copy of the sweep schedule (the two hands have the same tree: one copy, checked on the host),
+// placed behind the environment slots of the hands kernels
+struct SweepSched { int off[32]; uint16_t pairs[RP_SW_NPAIRS_SMEM]; };
+constexpr size_t kSchedBytes = (sizeof(SweepSched) + 15) / 16 * 16;
 
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
 __device__ __forceinline__ double warp_sum(double v) {
@@ -169,33 +170,39 @@ struct KeyRow {  // active limit row of a key (at most one side can be active)
   int active;
 };
 
-// In-place symmetric sweep of one hand matrix: afterwards A = -M^-1 (callers fold the sign into
-// their multiply-adds).  Lane j owns row j (== column j; the sweep keeps the matrix symmetric).
-// Pivots run leaves first (k = NL-1 .. 0): at that point row k is non-zero only at the ancestors
-// of k and inside its subtree, so a pivot touches depth_k + subtree_k rows instead of 26 (290 row
-// updates per hand instead of 676), and the loops stay rolled: a few hundred bytes of code instead
-// of the 230 KB of a register-resident unrolled elimination (the kernel is instruction-fetch bound).
-__device__ __noinline__ void sweep_inverse(double* A, const signed char* anc /*[NL][MAXD]*/, const signed char* dep,
-                                           const signed char* sub, int lane) {
-  double* myrow = A + (lane < NL ? lane : 0) * RS;
+// In-place symmetric sweep of one hand matrix: afterwards A = -M^-1 (callers fold the sign into their
+// multiply-adds).  Pivots run leaves first (k = NL-1 .. 0): at that point row k is non-zero only at the ancestors
+// of k and inside its subtree (its support S_k), so the rank-one update of pivot k touches |S_k|^2 elements instead
+// of 25^2.  The element updates of one pivot are independent of each other: they are spread over the 32 lanes from a
+// precomputed schedule (RpDevModel::sw_pairs, one entry per element j <= i, mirrored on store), 2-20 independent
+// load / multiply-add / store groups per lane and pivot instead of one lane walking a row element by element
+// through shared memory (r01: 16 % of the step's warp time, 1100 cycles per pivot).
+__device__ __noinline__ void sweep_inverse(double* A, const SweepSched* __restrict__ sched, int lane) {
+  const uint16_t* const pairs = sched->pairs;
+  const int* const off = sched->off;
+  int pend = off[NL];
 #pragma unroll 1
   for (int k = NL - 1; k >= 0; k--) {
     const double* rowk = A + k * RS;
-    const double dinv = 1.0 / rowk[k];
-    const bool upd = lane < NL && lane != k;  // lane k's own row is rewritten after the updates
-    const double t = upd ? rowk[lane] * dinv : 0.0;
-    const int depk = dep[k], endk = k + sub[k];
-    if (upd) {
-      for (int d = 0; d < depk; d++) {
-        const int i = anc[k * MAXD + d];
-        myrow[i] -= rowk[i] * t;
-      }
-#pragma unroll kSwUnroll
-      for (int i = k + 1; i < endk; i++) myrow[i] -= rowk[i] * t;
+    const int pbeg = off[k];
+    const double dinv = rp::rcp(rowk[k]);
+#pragma unroll 2
+    for (int p = pbeg + lane; p < pend; p += 32) {
+      const unsigned e = pairs[p];
+      const int j = e >> 5, i = e & 31;
+      const double t = rowk[j] * dinv;
+      const double v = fma(-rowk[i], t, A[j * RS + i]);
+      A[j * RS + i] = v;
+      A[i * RS + j] = v;
     }
+    pend = pbeg;
     __syncwarp();
-    if (upd) { myrow[k] = t; A[k * RS + lane] = t; }
-    if (lane == k) A[k * RS + k] = -dinv;
+    if (lane < NL) {  // row / column k (zero outside the support: the scaled value is zero there as well)
+      const double t = rowk[lane] * dinv;
+      const double w = lane == k ? -dinv : t;
+      A[lane * RS + k] = w;
+      if (lane != k) A[k * RS + lane] = w;
+    }
     __syncwarp();
   }
 }
@@ -447,6 +454,14 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw + (size_t)slot * kSmemStride);
   const int bar_id = slot + 1;
   const RpDevModel* __restrict__ dm = a.dm;
+  const SweepSched* const sched = reinterpret_cast<const SweepSched*>(smem_raw + (size_t)EPB * kSmemStride);
+  if (HANDS) {  // every thread of the block, before any early exit
+    SweepSched* w = reinterpret_cast<SweepSched*>(smem_raw + (size_t)EPB * kSmemStride);
+    const int np = dm->sw_off[0][NL];
+    for (int i = (int)threadIdx.x; i <= NL; i += KT * EPB) w->off[i] = dm->sw_off[0][i];
+    for (int i = (int)threadIdx.x; i < np; i += KT * EPB) w->pairs[i] = dm->sw_pairs[0][i];
+    __syncthreads();
+  }
   const int tid = (int)threadIdx.x - slot * KT;
   int lane;
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // opaque: keeps the compiler from re-reading S2R in loops
@@ -758,7 +773,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       }
     TICK(1)
       // ---------------------------------------------------------------- invert M (symmetric sweep): A = -M^-1
-      sweep_inverse(Aw, &sm.anc[h][0][0], sm.dep[h], sm.sub[h], lane);
+      sweep_inverse(Aw, sched, lane);
       if (a.dbg && sub == 0 && h == 0) {
         double* dbg = a.dbg + (size_t)env * RP_DBG_STRIDE;
         for (int i = 0; i < NL; i++) if (hl) dbg[RP_DBG_MINV + i * NL + lane] = -Aw[i * RS + lane];
@@ -1407,7 +1422,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       }
       __syncwarp();
       // a = (M + h*D)^-1 rhs: sweep (A = -inverse), then one row-times-vector per lane
-      sweep_inverse(Aw, &sm.anc[h][0][0], sm.dep[h], sm.sub[h], lane);
+      sweep_inverse(Aw, sched, lane);
       TICK(14)
       if (hl) {
         double acc = 0;
@@ -1726,7 +1741,7 @@ cudaError_t rp_launch_order(const int32_t* work, int32_t* order, int n, cudaStre
 }
 
 // ------------------------------------------------------------------------------------------------
-size_t rp_kernel_smem_bytes() { return kSmemStride * RP_EPB; }
+size_t rp_kernel_smem_bytes() { return kSmemStride * RP_EPB + kSchedBytes; }
 
 // the opt-in to more than 48 KB of dynamic shared memory is per device
 static int current_device_slot() {
@@ -1739,7 +1754,7 @@ template <int EPB>
 static cudaError_t launch_hands(const RpKernelArgs& a, cudaStream_t stream) {
   static bool configured[64] = {};
   const int dev = current_device_slot();
-  const size_t smem = kSmemStride * EPB;
+  const size_t smem = kSmemStride * EPB + kSchedBytes;
   if (!configured[dev]) {
     cudaError_t e = cudaFuncSetAttribute(rp_step_kernel<2, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

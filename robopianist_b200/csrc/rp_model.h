@@ -18,6 +18,8 @@
 #ifndef RP_MAXCON
 #define RP_MAXCON 21  // contact capacity per environment (shared memory: 584 B each; 3 x 21 rows = one thread per row)
 #endif
+#define RP_SW_MAXPAIRS 4096  // element updates of one symmetric sweep of a hand matrix (pairs j <= i of every pivot's support)
+#define RP_SW_NPAIRS_SMEM 2048  // ... of which the kernel keeps a block-shared copy (Shadow Hand: 1996)
 #define RP_NPIANO 89  // piano boxes: index 0 = base, 1 + k = key k (MuJoCo body order)
 
 struct RpGeomParams {  // contact-relevant geom fields
@@ -53,6 +55,11 @@ struct RpDevModel {
   int link_nchild_slots[RP_NHMAX][RP_MAXD + 1];  // max #children of any link at depth d
   int link_childrank[RP_NHMAX][RP_NL];           // rank among siblings
   int maxdepth[RP_NHMAX];
+  // schedule of the tree-sparse symmetric sweep (M -> -M^-1): pivot k (leaves first) touches the elements (j, i),
+  // j <= i, of its support S_k = ancestors(k) + proper subtree(k); entries j * 32 + i, pivot k's run at
+  // [sw_off[k], sw_off[k + 1])
+  uint16_t sw_pairs[RP_NHMAX][RP_SW_MAXPAIRS];
+  int sw_off[RP_NHMAX][RP_NL + 1];
   double link_pos[RP_NHMAX][RP_NL][3], link_quat[RP_NHMAX][RP_NL][4];
   double link_jpos[RP_NHMAX][RP_NL][3], link_jaxis[RP_NHMAX][RP_NL][3];
   double link_ipos[RP_NHMAX][RP_NL][3], link_iquat[RP_NHMAX][RP_NL][4];
