@@ -73,6 +73,10 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
   if (m->nkey != RP_NK) { fail("model must have 88 keys"); return nullptr; }
   if (m->nhand != 0 && m->nhand != 2) { fail("nhand must be 0 or 2"); return nullptr; }
   if (m->nv != RP_NK + m->nhand * RP_NL) { fail("unexpected nv (need 88 + nhand*26)"); return nullptr; }
+  if (!task->goal || !task->fingering) { fail("task goal / fingering tables must not be null"); return nullptr; }
+  if (task->n_steps < 1) { fail("task n_steps must be >= 1"); return nullptr; }
+  if (task->n_steps_lookahead < 0 || task->n_steps_lookahead > 1024) { fail("task n_steps_lookahead out of range [0, 1024]"); return nullptr; }
+  if (task->kind != 0 && task->kind != 1) { fail("task kind must be 0 (piano_with_shadow_hands) or 1 (self_actuated_piano)"); return nullptr; }
   rp_model* M = new rp_model();
   RpDevModel& d = M->dm;
   memset(&d, 0, sizeof(d));

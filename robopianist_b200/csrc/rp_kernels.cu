@@ -207,9 +207,6 @@ __device__ __noinline__ void sweep_inverse(double* A, const SweepSched* __restri
   }
 }
 
-#ifndef RP_FR_SEQ
-#define RP_FR_SEQ 12  // friction-loss rows: at least this many changing rows at the start of a sweep -> plain row-by-row sweep
-#endif
 #ifdef RP_PROFILE
 #define PTICK(i) { const long long tn = clock64(); tacc[i] += tn - *tlast; *tlast = tn; }
 #else
@@ -266,9 +263,9 @@ __device__ __noinline__ int pgs_solve(Smem* smp, const int h, const int bar_id, 
     // Every lane evaluates the update of its own row against the current va.  Few changing rows (most rows sit at
     // +-frictionloss while the hand moves): a ballot finds the first row at or after the cursor whose force changes,
     // that row commits and broadcasts, the search resumes behind it — the rows skipped in between would have
-    // committed a change of exactly zero at their turn, so the iterates are those of the row-by-row sweep.  Many
-    // changing rows (a hand at rest: stiction, nothing saturated): the plain row-by-row sweep, whose serial step is
-    // shorter (no ballot / find-first / dependent column load).
+    // committed a change of exactly zero at their turn, so the iterates are those of the row-by-row sweep.  (A plain
+    // row-by-row loop for sweeps in which most rows change — a hand at rest, nothing saturated — was measured and is
+    // slower at every switch-over threshold: 18.2 ms per step always on, 14.83 never, r02g.)
     {
       const double fbase = fr_b + fr_R * fr_f;  // f only changes at the lane's own commit
       double res = fbase + va;
@@ -276,22 +273,7 @@ __device__ __noinline__ int pgs_solve(Smem* smp, const int h, const int bar_id, 
       double fx = x < fr_lo ? fr_lo : x;
       fx = x > fr_hi ? fr_hi : fx;
       unsigned m = __ballot_sync(FULL, hl && fx != fr_f);
-      if (__popc(m) >= RP_FR_SEQ) {
-#pragma unroll 2
-        for (int i = 0; i < NL; i++) {
-          const double dl = fx - fr_f;
-          const double imp = dl * (0.5 * dl * fr_AR + res);
-          const double dbc = shfl(dl, i), ibc = shfl(imp, i);
-          va -= pcol[i * RS] * dbc;
-          improvement -= ibc;
-          if (lane == i) fr_f = fx;
-          res = fbase + va;
-          x = fr_f - res * fr_ARi;
-          fx = x < fr_lo ? fr_lo : x;
-          fx = x > fr_hi ? fr_hi : fx;
-          fx = lane <= i ? fr_f : fx;  // rows already visited (and the lanes without a row) stay put
-        }
-      } else {
+      {
         while (m != 0u) {
           const int i = __ffs(m) - 1;
           const double dl = fx - fr_f;

@@ -98,6 +98,52 @@ def _unsupported(kw: Mapping[str, Any]):
             "task_kwargs=dict(disable_hand_collisions=True)")
 
 
+def derive_task_config(midi, hands: bool, kw: Mapping[str, Any]):
+    """What the task constructor derives from the song and its kwargs (piano_with_shadow_hands.py:98-141), as plain
+    host data — no device needed: trimmed song, note trajectory, goal / fingering tables, lookahead, and which of
+    the fingering rewards is active."""
+    control_timestep = float(kw["control_timestep"])
+    if kw["trim_silence"]:
+        midi = midi.trim_silence()
+    L = int(kw["n_steps_lookahead"])
+    if kw["n_seconds_lookahead"] is not None:  # piano_with_shadow_hands.py:103-106
+        L = int(np.ceil(kw["n_seconds_lookahead"] / control_timestep))
+    traj = trajectory.NoteTrajectory.from_seq(midi, control_timestep)
+    if kw["initial_buffer_time"]:
+        traj = traj.add_initial_buffer_time(kw["initial_buffer_time"])
+    # MidiFile.has_fingering (music/midi_file.py; sequence.py restates it): more than one distinct `part` among the
+    # notes and at least one non-zero — `Note.part` defaults to 0, so a plain .mid has none.  Evaluated after
+    # trim_silence, like the reference (piano_with_shadow_hands.py:100-111).  No fingering in the song disables the
+    # fingering reward (and drops the `fingering` observable); whenever it is disabled the task adds the
+    # optimal-transport fingering reward in its place (:130-141, :333-369).
+    disable_fingering = bool(kw["disable_fingering_reward"]) or not midi.has_fingering()
+    return dict(midi=midi, trajectory=traj, goal=traj.goal_table(), fingering=traj.fingering_table(),
+                n_steps_lookahead=L, control_timestep=control_timestep, disable_fingering_reward=disable_fingering,
+                ot_fingering_reward=bool(hands and disable_fingering))
+
+
+def obs_layout(hands: bool, n_steps_lookahead: int, disable_fingering_reward: bool):
+    """Observation name -> slice of the flat observation row (SURVEY.md App. A order)."""
+    L, nl = n_steps_lookahead, 26
+    out, off = collections.OrderedDict(), 0
+
+    def add(name, n):
+        nonlocal off
+        out[name] = slice(off, off + n)
+        off += n
+
+    if hands:
+        add("piano/state", 88); add("piano/sustain_state", 1)
+        add("rh_shadow_hand/joints_pos", nl); add("lh_shadow_hand/joints_pos", nl)
+        add("goal", (L + 1) * 89)
+        if not disable_fingering_reward:
+            add("fingering", 10)
+    else:
+        add("piano/activation", 88); add("piano/sustain_activation", 1)
+        add("goal", (L + 1) * 89)
+    return out
+
+
 class BatchedPianoEnv:
     """N independent PianoWithShadowHands (or SelfActuatedPiano) environments on one GPU.
 
@@ -122,25 +168,15 @@ class BatchedPianoEnv:
             raise native.NativeError("BatchedPianoEnv needs a CUDA device (there is no CPU path)")
         self.torch = torch
         self.task_name = task
-        self.control_timestep = float(kw["control_timestep"])
-        if kw["trim_silence"]:
-            midi = midi.trim_silence()
-        self.midi = midi
-        L = int(kw["n_steps_lookahead"])
-        if kw["n_seconds_lookahead"] is not None:  # piano_with_shadow_hands.py:103-106
-            L = int(np.ceil(kw["n_seconds_lookahead"] / self.control_timestep))
-        traj = trajectory.NoteTrajectory.from_seq(midi, self.control_timestep)
-        if kw["initial_buffer_time"]:
-            traj = traj.add_initial_buffer_time(kw["initial_buffer_time"])
-        self.trajectory = traj
+        cfg = derive_task_config(midi, hands, kw)
+        self.control_timestep = cfg["control_timestep"]
+        midi = self.midi = cfg["midi"]
+        traj = self.trajectory = cfg["trajectory"]
         self._notes, self._sustains = traj.notes, traj.sustains
-        goal, fing = traj.goal_table(), traj.fingering_table()
+        goal, fing = cfg["goal"], cfg["fingering"]
         self.goal_table, self.fingering_table = goal, fing
-        self.n_steps_lookahead = L
-        has_fingering = bool((fing >= 0).any())
-        # piano_with_shadow_hands.py:109-111: no fingering in the song disables the fingering reward; whenever it is
-        # disabled the task adds the optimal-transport fingering reward in its place (:130-141, :333-369)
-        self.disable_fingering_reward = bool(kw["disable_fingering_reward"]) or not has_fingering
+        L = self.n_steps_lookahead = cfg["n_steps_lookahead"]
+        self.disable_fingering_reward = cfg["disable_fingering_reward"]
         self.disable_forearm_reward = bool(kw["disable_forearm_reward"])
         self.flat = cache.load_scene(task, gravity_compensation=bool(kw["gravity_compensation"]),
                                      physics_timestep=float(kw["physics_timestep"]),
@@ -152,7 +188,7 @@ class BatchedPianoEnv:
             disable_fingering_reward=self.disable_fingering_reward,
             disable_forearm_reward=bool(kw["disable_forearm_reward"]),
             energy_penalty_coef=float(kw["energy_penalty_coef"]), reward_type=reward_type,
-            ot_fingering_reward=hands and self.disable_fingering_reward)
+            ot_fingering_reward=cfg["ot_fingering_reward"])
         self.num_envs, self.device = int(num_envs), torch.device("cuda", device)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -168,23 +204,8 @@ class BatchedPianoEnv:
 
     # ------------------------------------------------------------------ specs
     def _obs_layout(self):
-        L, nl = self.n_steps_lookahead, 26
-        out, off = collections.OrderedDict(), 0
-
-        def add(name, n):
-            nonlocal off
-            out[name] = slice(off, off + n)
-            off += n
-
-        if self._hands:
-            add("piano/state", 88); add("piano/sustain_state", 1)
-            add("rh_shadow_hand/joints_pos", nl); add("lh_shadow_hand/joints_pos", nl)
-            add("goal", (L + 1) * 89)
-            if not self.disable_fingering_reward:
-                add("fingering", 10)
-        else:
-            add("piano/activation", 88); add("piano/sustain_activation", 1)
-            add("goal", (L + 1) * 89)
+        out = obs_layout(self._hands, self.n_steps_lookahead, self.disable_fingering_reward)
+        off = next(reversed(out.values())).stop
         assert off == self.model.obs_dim, (off, self.model.obs_dim)
         return out
 
@@ -203,6 +224,10 @@ class BatchedPianoEnv:
         self.batch.reset(None if mask is None else mask.data_ptr(), self.obs.data_ptr())
         if mask is None:
             self.reward.zero_(); self.discount.fill_(1.0); self.step_type.fill_(int(StepType.FIRST))
+        else:  # the reset envs show FIRST / 0 / 1 like a full reset; the others keep what their last step returned
+            m = mask.to(self.torch.bool)
+            self.reward.masked_fill_(m, 0.0); self.discount.masked_fill_(m, 1.0)
+            self.step_type.masked_fill_(m, int(StepType.FIRST))
         return self.obs, self.reward, self.discount, self.step_type
 
     def step(self, actions):

@@ -26,11 +26,17 @@ def pack_outputs(obs, reward, discount, step_type):
 
 
 def all_gather_outputs(local_block, world: int, n_total: int):
-    """All-gather the packed outputs of equally sized shards -> [n_total, obs_dim + 3]."""
+    """All-gather the packed outputs of equally sized shards -> [n_total, obs_dim + 3].
+
+    `all_gather_into_tensor` needs the same shard size on every rank: the global batch must divide evenly
+    (shard_range then gives every rank n_total / world envs)."""
     import torch
     import torch.distributed as dist
     if world == 1:
         return local_block
+    if n_total % world != 0 or local_block.shape[0] * world != n_total:
+        raise ValueError(f"all_gather_outputs needs equal shards: n_total={n_total}, world={world}, "
+                         f"local rows={local_block.shape[0]}")
     out = torch.empty((world * local_block.shape[0], local_block.shape[1]), dtype=local_block.dtype,
                       device=local_block.device)
     dist.all_gather_into_tensor(out, local_block.contiguous())

@@ -74,3 +74,33 @@ def test_ot_fingering_wrapper_on_the_host_matches_the_reference_logic():
             assert abs(got - want) < 1e-12, (song, t, got, want)
             partial += 0.0 < want < 1.0
         assert partial > 5
+
+
+def test_model_create_rejects_bad_task_arguments():
+    """rp_model_create validates what it dereferences: null goal / fingering tables, episode length, lookahead range,
+    task kind — NULL + rp_last_error instead of a crash."""
+    import ctypes as C
+    import helpers
+    from robopianist_b200 import cabi
+    from robopianist_b200.scene import cache
+    fm = cache.load_scene()
+    goal, fing = helpers.song_tables()
+    L = native.lib()
+    s, keep = cabi.pack_model(fm, None, None)
+
+    def create(**edit):
+        t, keep2 = cabi.pack_task(0, goal, fing)
+        for k, v in edit.items():
+            setattr(t, k, v)
+        p = L.rp_model_create(C.byref(s), C.byref(t))
+        if p:
+            L.rp_model_destroy(p)
+        return bool(p), L.rp_last_error().decode()
+
+    assert create()[0]
+    ok, msg = create(goal=C.POINTER(C.c_uint8)()); assert not ok and "null" in msg
+    ok, msg = create(fingering=C.POINTER(C.c_int8)()); assert not ok and "null" in msg
+    ok, msg = create(n_steps=0); assert not ok and "n_steps" in msg
+    ok, msg = create(n_steps_lookahead=-1); assert not ok and "lookahead" in msg
+    ok, msg = create(n_steps_lookahead=5000); assert not ok and "lookahead" in msg
+    ok, msg = create(kind=7); assert not ok and "kind" in msg

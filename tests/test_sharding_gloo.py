@@ -18,6 +18,8 @@ def test_shard_ranges_cover_batch():
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     with pytest.raises(ValueError):
         sharding.shard_range(4, 2, 2)
+    with pytest.raises(ValueError):      # unequal shards cannot go through all_gather_into_tensor
+        sharding.all_gather_outputs(torch.zeros((3, 4), dtype=torch.float64), 2, 7)
 
 
 def _worker(rank, world, port, n_total, q):

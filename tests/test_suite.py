@@ -46,7 +46,66 @@ def test_unsupported_kwargs_fail_loudly():
         suite.load(name, legacy_step=False, task_kwargs=KW)
 
 
+def test_song_without_fingering_switches_to_the_ot_reward():
+    """MidiFile.has_fingering (music/midi_file.py:252-261): `part` defaults to 0, so a song whose notes all carry
+    part 0 has NO fingering — the task then disables the fingering reward, drops the 10-dim `fingering` observable
+    and adds the optimal-transport fingering reward (piano_with_shadow_hands.py:109-111, 130-141, 443-449)."""
+    from robopianist_b200.suite import env as E
+    plain = NoteSeq()
+    plain.add(60, 0.0, 0.5); plain.add(64, 0.5, 1.0)
+    plain.total_time = 1.0
+    assert not plain.has_fingering()
+    cfg = E.derive_task_config(plain, True, dict(E._TASK_KWARGS))
+    assert cfg["disable_fingering_reward"] and cfg["ot_fingering_reward"]
+    assert (cfg["fingering"] >= 0).any()            # the table still lists finger 0 for every note: not the criterion
+    layout = E.obs_layout(True, cfg["n_steps_lookahead"], cfg["disable_fingering_reward"])
+    assert "fingering" not in layout and next(reversed(layout.values())).stop == 319
+    # one non-zero part among several distinct ones: fingering present
+    cfg = E.derive_task_config(_test_midi(), True, dict(E._TASK_KWARGS))
+    assert not cfg["disable_fingering_reward"] and not cfg["ot_fingering_reward"]
+    assert next(reversed(E.obs_layout(True, 1, False).values())).stop == 329
+    # all notes on the same non-zero part: a single distinct part is "no fingering" as well
+    mono = NoteSeq(); mono.add(60, 0.0, 0.5, 80, 3); mono.add(62, 0.5, 1.0, 80, 3); mono.total_time = 1.0
+    assert E.derive_task_config(mono, True, dict(E._TASK_KWARGS))["disable_fingering_reward"]
+    # the keys-only task never uses the OT term
+    assert not E.derive_task_config(plain, False, dict(E._TASK_KWARGS))["ot_fingering_reward"]
+
+
 # ------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_plain_midi_reaches_the_ot_reward_through_load(tmp_path):
+    """The same rule end to end: a song without fingering loaded through the suite runs the OT kernel (reward term
+    named ot_fingering_reward, obs 319 wide)."""
+    from robopianist_b200.suite.env import BatchedPianoEnv, PianoEnv
+    plain = NoteSeq()
+    plain.add(60, 0.0, 0.1); plain.add(64, 0.1, 0.2)
+    plain.total_time = 0.2
+    env = PianoEnv(BatchedPianoEnv(plain, num_envs=1, **KW))
+    ts = env.reset()
+    assert "fingering" not in ts.observation and sum(v.size for v in ts.observation.values()) == 319
+    ts = env.step(np.zeros(45))
+    terms = env.task.reward_fn.reward_terms
+    assert "ot_fingering_reward" in terms and "fingering_reward" not in terms
+    assert 0.0 <= terms["ot_fingering_reward"] <= 1.0
+    assert abs(sum(terms.values()) - ts.reward) < 1e-12
+    env.close()
+
+
+@pytest.mark.gpu
+def test_masked_reset_reports_first_for_the_reset_envs():
+    import torch
+    from robopianist_b200.suite.env import BatchedPianoEnv
+    env = BatchedPianoEnv(_test_midi(0.05), num_envs=4, control_timestep=0.05, **KW)
+    env.reset()
+    a = torch.zeros((4, 45), dtype=torch.float64, device="cuda")
+    env.step(a)
+    mask = torch.tensor([0, 1, 0, 1], dtype=torch.uint8, device="cuda")
+    _, rew, dis, st = env.reset(mask)
+    torch.cuda.synchronize()
+    assert st.tolist() == [1, 0, 1, 0] and dis.tolist()[1] == 1.0 and rew.tolist()[1] == 0.0 and rew.tolist()[3] == 0.0
+    env.close()
+
+
 @pytest.mark.gpu
 def test_all_debug_envs_load_and_step():
     """suite_test.py:27-56: every debug env loads, FIRST has no reward/discount, obs matches the spec."""

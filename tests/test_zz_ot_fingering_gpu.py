@@ -1,8 +1,7 @@
 """Optimal-transport fingering reward on the device (csrc/rp_task_kernels.cu, launched after the step kernel when
 the fingering reward is disabled: piano_with_shadow_hands.py:130-141, 333-369) against the restated reference
-logic (oracle/task_ref.py, scipy's linear_sum_assignment).  Written after the round's GPU budget was spent: its
-first run on a GPU is the driver's; the solver and the reward are pinned to scipy on the host
-(tests/test_hd_math.py), so what this adds is the kernel wrapper (indexing of sites, key poses, goals)."""
+logic (oracle/task_ref.py, scipy's linear_sum_assignment).  The solver and the reward are pinned to scipy on the host
+(tests/test_hd_math.py); this covers the kernel wrapper (indexing of sites, key poses, goals)."""
 import numpy as np
 import pytest
 import torch
@@ -16,7 +15,6 @@ def _dev(a):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first GPU run of rp_ot_fingering_kernel pending (host-side parts are pinned to scipy)")
 @pytest.mark.parametrize("song", ["TwinkleTwinkleRousseau", "CMajorScaleTwoHands"])
 def test_ot_fingering_reward_matches_reference_logic(song):
     fm, model, batch = helpers.make_native("piano_with_shadow_hands", song=song, nenv=3, disable_fingering_reward=True,
