@@ -141,7 +141,9 @@ int rp_get_state(rp_batch *, double *qpos, double *qvel, double *qacc_warmstart,
 int rp_set_state(rp_batch *, const double *qpos, const double *qvel, const double *qacc_warmstart,
                  const int32_t *t_idx);
 /* Diagnostics of the last substep (HOST buffers): ncon [N], niter [N] (PGS sweeps used),
- * flags [N] (bit0 contact overflow, bit1 non-finite state). */
+ * flags [N]: bit0 contact overflow (more than RP_MAXCON contacts), bit1 non-finite state, bit2 hand tree too deep,
+ * bit3 a hand collider the narrowphase does not cover (box / cylinder / mesh; rp_flat_model.geom_collide == 0) came
+ * within reach of the piano during the last step: its contact, if any, was not generated. */
 int rp_get_diag(rp_batch *, int32_t *ncon, int32_t *niter, int32_t *flags);
 /* Extra sensor-like outputs of the last step (HOST): actuator_force [N,nu], fingertip site
  * positions [N,nsite,3], key activation [N,88] uint8. */

@@ -296,6 +296,21 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
       ng++;
     }
     d.ngeom[h] = ng;
+    // colliders the narrowphase does not cover: oriented bounding boxes for the runtime proximity flag
+    int ni = 0;
+    for (int g = 0; g < m->ngeom; g++) {
+      if (m->geom_hand[g] != h || m->geom_collide[g] || !(m->geom_contype[g] | m->geom_conaffinity[g])) continue;
+      if (ni >= RP_NIGN) return bad("too many uncovered hand colliders");
+      int b = m->geom_bodyid[g];
+      d.ign_link[h][ni] = m->body_dofadr[b] + m->body_dofnum[b] - 1 - base;
+      for (int c = 0; c < 3; c++) d.ign_pos[h][ni][c] = m->geom_pos[3 * g + c];
+      const double* sz = m->geom_size + 3 * g;
+      quat_to_mat(m->geom_quat + 4 * g, d.ign_mat[h][ni]);
+      if (m->geom_type[g] == 5) { d.ign_half[h][ni][0] = d.ign_half[h][ni][1] = sz[0]; d.ign_half[h][ni][2] = sz[1]; }  // cylinder: radius, half height
+      else for (int c = 0; c < 3; c++) d.ign_half[h][ni][c] = sz[c];                                                    // box / mesh bounding box
+      ni++;
+    }
+    d.nign[h] = ni;
     if (m->nsite != 2 * RP_NSITE) return bad("expected 5 fingertip sites per hand");
     for (int s = 0; s < RP_NSITE; s++) {
       int si = h * RP_NSITE + s, b = m->site_bodyid[si];
@@ -307,6 +322,17 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
   }
   d.nhandgeom_total = order;
   if (order > 64) return bad("too many hand geoms for the contact sort key");
+  for (int c = 0; c < 3; c++) { d.piano_lo[c] = 1e30; d.piano_hi[c] = -1e30; }
+  for (int k = 0; k < RP_NK; k++)
+    for (int c = 0; c < 3; c++) {
+      d.piano_lo[c] = fmin(d.piano_lo[c], d.key_pos[k][c] - d.key_half[k][c]);
+      d.piano_hi[c] = fmax(d.piano_hi[c], d.key_pos[k][c] + d.key_half[k][c]);
+    }
+  if (d.has_base)
+    for (int c = 0; c < 3; c++) {
+      d.piano_lo[c] = fmin(d.piano_lo[c], d.base_pos[c] - d.base_half[c]);
+      d.piano_hi[c] = fmax(d.piano_hi[c], d.base_pos[c] + d.base_half[c]);
+    }
   // ---------------- task
   d.T = task->n_steps; d.lookahead = task->n_steps_lookahead;
   d.wrong_press_termination = task->wrong_press_termination;
@@ -335,8 +361,13 @@ extern "C" int rp_obs_dim(const rp_model* m) { return m->obs_dim; }
 extern "C" int rp_action_dim(const rp_model* m) { return m->act_dim; }
 extern "C" int rp_reward_terms(const rp_model* m) { return m->dm.task_kind == 0 ? 5 : 1; }
 
+// rp_debug_fail_alloc(k): the k-th device allocation from now on fails (tests of the failure path); -1 = off
+static int g_fail_alloc_after = -1;
+extern "C" int rp_debug_fail_alloc(int k) { g_fail_alloc_after = k; return 0; }
+
 template <typename T>
 static cudaError_t dalloc(T** p, size_t n) {
+  if (g_fail_alloc_after >= 0 && g_fail_alloc_after-- == 0) return cudaErrorMemoryAllocation;  // test hook (rp_debug_fail_alloc)
   cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (n ? n : 1));
   if (e == cudaSuccess) e = cudaMemset(*p, 0, sizeof(T) * (n ? n : 1));
   return e;
@@ -354,7 +385,9 @@ extern "C" rp_batch* rp_batch_create(const rp_model* model, int nenv, int device
   b->iterations = -1; b->tolerance = -1.0;
   size_t N = nenv, nv = model->nv, nu = model->nu;
   cudaError_t e = cudaSuccess;
-  auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+  // every allocation is skipped once one has failed (a batch too large for the device must not go on to ask for
+  // hundreds of gigabytes of pinned host memory)
+#define chk(x) do { if (e == cudaSuccess) e = (x); } while (0)
   chk(cudaMalloc((void**)&b->d_dm, sizeof(RpDevModel)));
   chk(cudaMemcpy(b->d_dm, &model->dm, sizeof(RpDevModel), cudaMemcpyHostToDevice));
   chk(cudaMalloc((void**)&b->d_goal, model->goal.size()));
@@ -369,10 +402,11 @@ extern "C" rp_batch* rp_batch_create(const rp_model* model, int nenv, int device
   chk(dalloc(&b->work, N)); chk(dalloc(&b->order, N));
   if (model->dm.ot_fingering) chk(dalloc(&b->ot_scratch, N * RP_OT_SCRATCH_DOUBLES));
   size_t out_doubles = N * (model->obs_dim + 2 + 5) + (N + 7) / 8 + 8;
-  chk(cudaMallocHost((void**)&b->h_action, sizeof(double) * N * model->act_dim));
-  chk(cudaMallocHost((void**)&b->h_out, sizeof(double) * out_doubles));
   chk(dalloc(&b->d_action, N * model->act_dim));
   chk(dalloc(&b->d_out, out_doubles));
+  chk(cudaMallocHost((void**)&b->h_action, sizeof(double) * N * model->act_dim));
+  chk(cudaMallocHost((void**)&b->h_out, sizeof(double) * out_doubles));
+#undef chk
   if (e != cudaSuccess) {  // release whatever was allocated before the failure
     fail(std::string("allocation failed: ") + cudaGetErrorString(e));
     rp_batch_destroy(b);

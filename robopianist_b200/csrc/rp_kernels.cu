@@ -113,6 +113,7 @@ struct Smem {
     RawContact raw[MAXCON];        // narrowphase output; moved to registers before con[] is written
   } u;
   int ncon, nraw, overflow, pad;
+  int near_uncovered, pad2;  // some collider outside the narrowphase's coverage came within reach of the piano (this launch)
 };
 
 constexpr size_t kSmemStride = (sizeof(Smem) + 15) / 16 * 16;  // per-environment shared memory (RP_EPB > 1: slot stride)
@@ -582,6 +583,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
 #endif
   // link world pose (kept for the task epilogue)
   double xp[3] = {0, 0, 0}, xq[4] = {1, 0, 0, 0};
+  if (tid == 0) sm.near_uncovered = 0;
   env_sync<NW, EPB>(bar_id);
 
   // =============================================================================================
@@ -998,6 +1000,35 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
             }
           }
         }
+      }
+    }
+    if (HANDS) {
+      // colliders outside the narrowphase's coverage (palm / knuckle / wrist boxes and cylinders, forearm): if the
+      // bounding box of one comes within reach of the piano the step is flagged (diag flag 8) — they are never
+      // dropped silently.  (They stay 5 cm clear of the piano on the recorded replay and cannot reach it while the joints
+      // respect their limits: see the tests.)
+      const bool isi = lane < dm->nign[h];
+      const int il = isi ? dm->ign_link[h][lane] : 0;
+      double lp[3], lq[4];
+#pragma unroll
+      for (int k = 0; k < 3; k++) lp[k] = shfl(xp[k], il);
+#pragma unroll
+      for (int k = 0; k < 4; k++) lq[k] = shfl(xq[k], il);
+      if (isi) {
+        double tmp[3], gp[3] = {dm->ign_pos[h][lane][0], dm->ign_pos[h][lane][1], dm->ign_pos[h][lane][2]};
+        double Rl[9];
+        rp::quat2mat(Rl, lq);
+        rp::mat_vec(tmp, Rl, gp);
+        bool near = true;
+        for (int k = 0; k < 3; k++) {
+          double e = 0;  // half extent of the box along world axis k: sum_j |(Rl Rg)_kj| half_j
+          for (int j = 0; j < 3; j++) {
+            const double rkj = Rl[3 * k] * dm->ign_mat[h][lane][j] + Rl[3 * k + 1] * dm->ign_mat[h][lane][3 + j] + Rl[3 * k + 2] * dm->ign_mat[h][lane][6 + j];
+            e += fabs(rkj) * dm->ign_half[h][lane][j];
+          }
+          near = near && (lp[k] + tmp[k] + e > dm->piano_lo[k]) && (lp[k] + tmp[k] - e < dm->piano_hi[k]);
+        }
+        if (near) atomicOr(&sm.near_uncovered, 1);
       }
     }
     TICK(5)
@@ -1473,7 +1504,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       anybad = sm.pad;
     }
     if (anybad) flags |= 2;
-    if (tid == 0 && a.diag) { a.diag[3 * env + 0] = ncon_last; a.diag[3 * env + 1] = niter_last; a.diag[3 * env + 2] = flags; }
+    if (tid == 0 && a.diag) { a.diag[3 * env + 0] = ncon_last; a.diag[3 * env + 1] = niter_last; a.diag[3 * env + 2] = flags | (sm.near_uncovered ? 8 : 0); }
     if (tid == 0 && a.work) a.work[env] = work;
     if (a.act_force) {
       if (HANDS && lane < dm->nact[h]) a.act_force[(size_t)env * nu + h * dm->nact[0] + lane] = actforce;
@@ -1635,6 +1666,13 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       terms[0] = reward;
       if (should_terminate) step_type = RP_STEP_LAST_;
     }
+  }
+  // A diverged environment (non-finite qpos / qvel: where MuJoCo raises mjWARN_BADQPOS / BADQACC and dm_control a
+  // PhysicsError) ends its episode instead: LAST with discount 0 and reward 0, diag flag 2 — and the next step
+  // auto-resets it like any other finished episode.  Its last observation may hold non-finite values.
+  if (!first && (flags & 2)) {
+    step_type = RP_STEP_LAST_; discount = 0.0; reward = 0.0;
+    for (int k = 0; k < 5; k++) terms[k] = 0.0;
   }
   // ---- observation (order: piano/state, piano/sustain_state, rh joints_pos, lh joints_pos, goal, fingering)
   if (a.obs) {

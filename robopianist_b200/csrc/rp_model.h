@@ -14,6 +14,7 @@
 #define RP_MAXD 10    // max chain length (depth+1)
 #define RP_NGH 20     // colliding primitive geoms per hand (capsules / spheres), max
 #define RP_NAH 24     // actuators per hand, max
+#define RP_NIGN 32    // hand colliders outside the narrowphase's coverage (per hand), max
 #define RP_NSITE 5    // fingertip sites per hand
 #ifndef RP_MAXCON
 #define RP_MAXCON 21  // contact capacity per environment (shared memory: 584 B each; 3 x 21 rows = one thread per row)
@@ -86,6 +87,12 @@ struct RpDevModel {
   double geom_size[RP_NHMAX][RP_NGH][2];
   RpGeomParams geom_gp[RP_NHMAX][RP_NGH];
   int nhandgeom_total, pad3;
+  // hand colliders of the reference model the narrowphase does not handle (boxes, cylinders, forearm mesh): oriented
+  // bounding boxes, checked every substep against the piano's bounding box -> diag flag 8 when one comes within reach
+  int nign[RP_NHMAX];
+  int ign_link[RP_NHMAX][RP_NIGN];
+  double ign_pos[RP_NHMAX][RP_NIGN][3], ign_mat[RP_NHMAX][RP_NIGN][9], ign_half[RP_NHMAX][RP_NIGN][3];  // oriented bounding box in the link frame
+  double piano_lo[3], piano_hi[3];  // world bounding box of base + keys at rest (pressed keys only move down)
   // fingertip sites
   int site_link[RP_NHMAX][RP_NSITE];
   double site_pos[RP_NHMAX][RP_NSITE][3];

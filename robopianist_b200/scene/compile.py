@@ -268,6 +268,14 @@ def _add_hand(b: _Builder, side: str, asset_dir: Path, piano_half_length: float,
                 quat = mu.quat_mul(quat, cquat)
                 size = np.array([radius, half, 0.0])
                 gtype = GEOM_CAPSULE
+            elif gtype == GEOM_MESH:
+                # not collided (see geom_collide / meta["ignored_colliders"]); kept with its bounding box in the
+                # geom frame (size = half extents, pos moved to the box centre) so that tests can bound its clearance
+                m = spec.meshes[g.mesh]
+                verts = meshfit.load_obj_vertices(spec.asset_dir / m["file"], m["scale"])
+                lo, hi = verts.min(axis=0), verts.max(axis=0)
+                pos = pos + mu.rotate(quat, 0.5 * (lo + hi))
+                size = 0.5 * (hi - lo)
             contype, conaff = g.contype, g.conaffinity
             if disable_hand_collisions:  # piano_with_shadow_hands.py:476-489
                 contype, conaff = 1, 0
@@ -496,6 +504,10 @@ def compile_scene(
     # narrowphase coverage: hand capsules / spheres against piano boxes
     supported = np.isin(A["geom_type"], [GEOM_SPHERE, GEOM_CAPSULE]) & (A["geom_hand"] >= 0)
     A["geom_collide"] = supported.astype(np.int32)
+    # hand colliders of the reference model that this narrowphase does NOT collide with the piano (boxes, cylinders,
+    # the forearm mesh: MuJoCo's box-box / general convex routines are not restated) — surfaced, never silent
+    ignored = [i for i in range(len(geoms)) if A["geom_hand"][i] >= 0 and not supported[i]
+               and (A["geom_contype"][i] | A["geom_conaffinity"][i])]
     ns = len(b.sites)
     A["site_bodyid"] = stack("body", b.sites, np.int32) if ns else np.zeros(0, np.int32)
     A["site_pos"] = stack("pos", b.sites) if ns else np.zeros((0, 3))
@@ -548,5 +560,6 @@ def compile_scene(
         body_names=[bd["name"] for bd in bodies], joint_names=[j["name"] for j in joints],
         geom_names=[g["name"] for g in geoms], actuator_names=[a["name"] for a in acts],
         site_names=[s["name"] for s in b.sites],
+        ignored_colliders=[geoms[i]["name"] for i in ignored], n_ignored_colliders=len(ignored),
     )
     return FlatModel(A, meta)

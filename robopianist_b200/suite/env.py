@@ -182,6 +182,14 @@ class BatchedPianoEnv:
                                      physics_timestep=float(kw["physics_timestep"]),
                                      control_timestep=self.control_timestep,
                                      forearm_dofs=tuple(kw["forearm_dofs"]))
+        n_ign = int(self.flat.meta.get("n_ignored_colliders", 0))
+        if hands and n_ign:
+            import warnings
+            warnings.warn(
+                f"{n_ign} hand colliders of the reference model (palm / knuckle / wrist boxes and cylinders, forearm "
+                "mesh) are outside the narrowphase's coverage and do not collide with the piano; environments in "
+                "which one of them comes within reach of the piano are flagged (rp_get_diag flags bit 3, "
+                "BatchedPianoEnv.uncovered_collider_flags())", RuntimeWarning, stacklevel=3)
         self.model = native.Model(
             self.flat, goal, fing, kind=0 if hands else 1, iterations=iterations, tolerance=tolerance,
             n_steps_lookahead=L, wrong_press_termination=bool(kw["wrong_press_termination"]),
@@ -264,6 +272,11 @@ class BatchedPianoEnv:
         """Per env, the messages of the running episode as (time, kind, midi_note) in the reference's order
         (MidiModule.get_all_midi_messages); read them before stepping past the end of the episode."""
         return self.batch.get_midi(self.flat.meta["timestep"])
+
+    def uncovered_collider_flags(self):
+        """bool [N]: during the last step a hand collider the narrowphase does not cover (meta['ignored_colliders'])
+        came within reach of the piano — its contact, if any, was not generated."""
+        return (self.batch.get_diag()["flags"] & 8) != 0
 
     def get_state(self):
         return self.batch.get_state()

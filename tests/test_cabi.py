@@ -104,3 +104,49 @@ def test_model_create_rejects_bad_task_arguments():
     ok, msg = create(n_steps_lookahead=-1); assert not ok and "lookahead" in msg
     ok, msg = create(n_steps_lookahead=5000); assert not ok and "lookahead" in msg
     ok, msg = create(kind=7); assert not ok and "kind" in msg
+
+
+def test_batch_create_fails_cleanly_without_a_device():
+    """On a box without a usable CUDA device rp_batch_create(device >= 0) returns NULL with an error string (no crash)."""
+    import ctypes
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without CUDA")
+    import helpers
+    from robopianist_b200.scene import cache
+    fm = cache.load_scene()
+    goal, fing = helpers.song_tables()
+    model = native.Model(fm, goal, fing, kind=0)
+    assert not native.lib().rp_batch_create(model.ptr, 4, 0, ctypes.c_void_p(0))
+    assert native.lib().rp_last_error()
+    with pytest.raises(native.NativeError):
+        native.Batch(model, 4)
+
+
+@pytest.mark.gpu
+def test_batch_create_releases_partial_allocations_on_failure():
+    """An allocation failing half-way through rp_batch_create (injected with the library's test hook — never by
+    asking for more memory than the box has) gives NULL + an error string, skips the remaining allocations and
+    gives back what it had allocated; the library stays usable."""
+    import ctypes
+    import torch
+    import helpers
+    from robopianist_b200.scene import cache
+    fm = cache.load_scene()
+    goal, fing = helpers.song_tables()
+    model = native.Model(fm, goal, fing, kind=0)
+    L = native.lib()
+    L.rp_debug_fail_alloc.argtypes = [ctypes.c_int]
+    b = native.Batch(model, 4096); b.close()     # warm the context / allocator
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for k in (0, 3, 9):
+        L.rp_debug_fail_alloc(k)
+        with pytest.raises(native.NativeError, match="allocation failed"):
+            native.Batch(model, 4096)
+        L.rp_debug_fail_alloc(-1)
+        torch.cuda.synchronize()
+        free1, _ = torch.cuda.mem_get_info()
+        assert abs(free0 - free1) < 64 << 20, (k, free0, free1)
+    b = native.Batch(model, 8)
+    b.close()

@@ -371,3 +371,109 @@ def test_launch_shapes_are_bitwise_identical():
     assert any(x.dtype == np.uint8 and (x == 2).any() for x in outs[0])  # some environments ended their episode early
     for x, y in zip(*outs):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.gpu
+def test_uncovered_collider_proximity_flag():
+    """diag flag 8: a hand collider outside the narrowphase's coverage (palm boxes, ...) within reach of the piano.
+    Never on the recorded replay; set when the state is forced far outside the joint limits (forearm 15 cm in, wrist
+    bent 90 degrees: tests/test_oracle.py restates the geometry)."""
+    fm, model, batch = helpers.make_native("piano_with_shadow_hands", nenv=2)
+    N = 2
+    obs = torch.empty((N, model.obs_dim), dtype=torch.float64, device="cuda")
+    rew = torch.empty(N, dtype=torch.float64, device="cuda"); dis = torch.empty_like(rew)
+    st = torch.empty(N, dtype=torch.uint8, device="cuda")
+    acts = helpers.twinkle_actions()
+    batch.reset(None, obs.data_ptr())
+    for t in range(60):
+        a = torch.tensor(np.tile(acts[t], (N, 1)), dtype=torch.float64, device="cuda")
+        batch.step(a.data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
+        assert not (batch.get_diag()["flags"] & 8).any()
+    q, v, w, tidx = batch.get_state()
+    q[1, 89] = 0.15; q[1, 91] = 1.57
+    batch.set_state(q, v, w, tidx)
+    a = torch.tensor(np.tile(acts[60], (N, 1)), dtype=torch.float64, device="cuda")
+    batch.step(a.data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
+    f = batch.get_diag()["flags"]
+    assert not (f[0] & 8) and (f[1] & 8)
+    batch.close()
+
+
+@pytest.mark.parametrize("reward_type", [0, 1])
+def test_self_actuated_reward_identity_on_the_cuda_path(reward_type):
+    """self_actuated_piano_test.py:139-166 on the CUDA path: random controls in the action spec; at every step the
+    returned reward equals RewardType.get()(concat(activation, sustain_activation), goal_current) — negative L2
+    distance (self_actuated_piano.py:49-57) or negative binary cross entropy (:38-47) — recomputed here in numpy from
+    the activation the kernel reports and the goal row of the previous observation; observation, step type and
+    discount against the restated task (oracle/task_ref.py) through the end of the episode and the auto-reset."""
+    song = "CMajorScaleTwoHands"
+    fm, model, batch = helpers.make_native("self_actuated_piano", song=song, nenv=3, lookahead=1, gravity_compensation=False,
+                                           reward_type=reward_type)
+    goal, fing = helpers.song_tables(song)
+    ref = task_ref.RefEnv(fm, goal, fing, kind=1, n_steps_lookahead=1, reward_type=reward_type)
+    N = 3
+    obs = torch.empty((N, model.obs_dim), dtype=torch.float64, device="cuda")
+    rew = torch.empty(N, dtype=torch.float64, device="cuda"); dis = torch.empty_like(rew)
+    st = torch.empty(N, dtype=torch.uint8, device="cuda")
+    batch.reset(None, obs.data_ptr()); ref.reset()
+    torch.cuda.synchronize()
+    lo = np.append(fm.actuator_ctrlrange[:, 0], 0.0); hi = np.append(fm.actuator_ctrlrange[:, 1], 1.0)
+    rng = np.random.default_rng(12345)
+    prev_goal = obs[0].cpu().numpy()[89:89 + 89].copy()      # obs = activation(88), sustain(1), goal((L+1)*89)
+    nonzero = 0
+    for t in range(goal.shape[0] + 2):
+        a = rng.uniform(lo, hi)
+        batch.step(_dev(np.tile(a, (N, 1))).data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
+        rst, rrew, rdis, robs = ref.step(a)
+        torch.cuda.synchronize()
+        o = obs[0].cpu().numpy()
+        assert int(st[0]) == rst and np.abs(o - robs).max() < 1e-12
+        assert torch.equal(obs[0], obs[2]) and torch.equal(rew[0:1], rew[2:3])
+        if rst != task_ref.FIRST:
+            pred = np.append(batch.get_aux()["activation"][0].astype(np.float64), float(a[-1] >= 0.5))
+            assert np.array_equal(pred, o[:89])              # the observables are the activations themselves
+            if reward_type == 0:
+                want = -np.sqrt(np.sum((pred - prev_goal) ** 2))
+            else:
+                want = np.sum(prev_goal * np.log(pred + 1e-6) + (1 - prev_goal) * np.log(1 - pred + 1e-6))
+            assert abs(float(rew[0]) - want) < 1e-12 and abs(float(rew[0]) - rrew) < 1e-12 and float(dis[0]) == rdis
+            nonzero += want != 0
+        prev_goal = o[89:89 + 89].copy()
+    assert nonzero > 50
+    batch.close()
+
+
+def test_diverged_environment_ends_its_episode_and_auto_resets():
+    """Non-finite state (mjWARN_BADQPOS territory; dm_control raises PhysicsError): the environment is flagged (diag
+    bit 1), returns LAST with discount 0 and reward 0, and the next step starts a fresh episode; its neighbours are
+    bit-for-bit what they are without the incident."""
+    acts = helpers.twinkle_actions()
+    outs = []
+    for poison in (False, True):
+        fm, model, batch = helpers.make_native("piano_with_shadow_hands", nenv=3)
+        N = 3
+        obs = torch.empty((N, model.obs_dim), dtype=torch.float64, device="cuda")
+        rew = torch.empty(N, dtype=torch.float64, device="cuda"); dis = torch.empty_like(rew)
+        st = torch.empty(N, dtype=torch.uint8, device="cuda")
+        batch.reset(None, obs.data_ptr())
+        rec = []
+        for t in range(8):
+            if poison and t == 4:
+                q, v, w, tidx = batch.get_state()
+                v[1, 95] = np.inf
+                batch.set_state(q, v, w, tidx)
+            batch.step(_dev(np.tile(acts[t], (N, 1))).data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
+            torch.cuda.synchronize()
+            rec.append((obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), dis.cpu().numpy().copy(), st.cpu().numpy().copy(),
+                        batch.get_diag()["flags"].copy()))
+        outs.append(rec)
+        batch.close()
+    clean, bad = outs
+    o, r, d, s_, f = bad[4]
+    assert (f[1] & 2) and s_[1] == 2 and d[1] == 0.0 and r[1] == 0.0 and not (f[0] & 2) and not (f[2] & 2)
+    o, r, d, s_, f = bad[5]
+    assert s_[1] == 0 and r[1] == 0.0 and d[1] == 1.0 and np.isfinite(o[1]).all() and not (f[1] & 2)
+    assert bad[6][3][1] == 1 and np.isfinite(bad[6][0][1]).all()
+    for t in range(8):
+        for k in range(4):
+            assert np.array_equal(clean[t][k][[0, 2]], bad[t][k][[0, 2]])

@@ -469,3 +469,94 @@ def test_warm_start_uses_the_regularised_cone_and_the_fixed_point_does_not_care(
             assert np.abs(f_a - f_b).max() < 1e-6 * max(1.0, np.abs(f_a).max())
             checked += 1
     assert checked == 4 and differs > 0 and middle > 0
+
+
+def _surface_points(gtype, size):
+    if gtype in (6, 7):      # box, or the bounding box kept for a mesh
+        u = np.linspace(-1, 1, 7)
+        pts = []
+        for ax in range(3):
+            a, b = [k for k in range(3) if k != ax]
+            U, V = np.meshgrid(u, u, indexing="ij")
+            for sgn in (-1, 1):
+                p = np.zeros((U.size, 3)); p[:, a] = U.ravel() * size[a]; p[:, b] = V.ravel() * size[b]; p[:, ax] = sgn * size[ax]
+                pts.append(p)
+        return np.concatenate(pts)
+    r, hh = size[0], size[1]   # cylinder, axis z
+    th = np.linspace(0, 2 * np.pi, 16, endpoint=False)
+    side = np.array([[r * np.cos(t), r * np.sin(t), z] for z in np.linspace(-hh, hh, 5) for t in th])
+    caps = np.array([[rr * np.cos(t), rr * np.sin(t), s * hh] for s in (-1, 1) for rr in (0, r / 2, r) for t in th])
+    return np.concatenate([side, caps])
+
+
+def test_uncovered_hand_colliders_stay_clear_of_the_piano_on_the_replay(hands):
+    """40 hand colliders of the reference model (12 boxes, 7 cylinders and the forearm mesh per hand:
+    right_hand.xml:101-288) are outside the narrowphase's coverage (meta['ignored_colliders']; MuJoCo's box-box and
+    general convex routines are not restated).  On the recorded action replay they never come near the piano: brute
+    force, surface samples of every such geom against every key / base box, every fourth control step, clearance
+    > 3 cm.  (At runtime the kernel flags any environment in which one of them comes within reach: diag bit 3.)"""
+    fm, _ = hands
+    names = fm.meta["geom_names"]
+    ign = [names.index(n) for n in fm.meta["ignored_colliders"]]
+    assert len(ign) == fm.meta["n_ignored_colliders"] == 40
+    assert sorted(int(fm.geom_type[g]) for g in ign) == [5] * 14 + [6] * 24 + [7] * 2
+    assert not fm.geom_collide[ign].any()
+    piano = [i for i in range(len(names)) if fm.geom_key[i] != -1]
+    P = {g: _surface_points(int(fm.geom_type[g]), fm.geom_size[g]) for g in ign}
+    om = O.OracleModel(fm); om.set_option(maxcon=24)
+    d = O.OracleData(om); d.reset()
+    acts = helpers.twinkle_actions()
+    half = fm.geom_size[piano]
+    best = 1e9
+    for t in range(acts.shape[0]):
+        d.control_step(acts[t, :44])
+        if t % 4:
+            continue
+        c = d.geom_xpos[piano]; R = d.geom_xmat[piano].reshape(-1, 3, 3)
+        for g in ign:
+            pw = d.geom_xpos[g] + P[g] @ d.geom_xmat[g].reshape(3, 3).T
+            loc = np.einsum("pkc,kcd->pkd", pw[:, None, :] - c[None], R)
+            q = np.abs(loc) - half[None]
+            sd = np.linalg.norm(np.maximum(q, 0), axis=2) + np.minimum(q.max(axis=2), 0)
+            best = min(best, sd.min())
+    assert best > 0.03, best
+
+
+def _uncovered_boxes_near_piano(fm, d, q):
+    """The kernel's runtime test (rp_kernels.cu, diag flag 8) restated: world AABB of each uncovered collider's oriented
+    bounding box against the piano's bounding box."""
+    names = fm.meta["geom_names"]
+    ign = [names.index(n) for n in fm.meta["ignored_colliders"]]
+    piano = [i for i in range(len(names)) if fm.geom_key[i] != -1]
+    d.qpos[:] = 0; d.call("orc_kinematics")
+    lo = np.min(d.geom_xpos[piano] - fm.geom_size[piano], axis=0); hi = np.max(d.geom_xpos[piano] + fm.geom_size[piano], axis=0)
+    d.qpos[:] = q; d.call("orc_kinematics")
+    out = []
+    for g in ign:
+        h = fm.geom_size[g].copy()
+        if fm.geom_type[g] == 5:
+            h = np.array([h[0], h[0], h[1]])
+        e = np.abs(d.geom_xmat[g].reshape(3, 3)) @ h
+        c = d.geom_xpos[g]
+        if np.all(c + e > lo) and np.all(c - e < hi):
+            out.append(names[g])
+    return out
+
+
+def test_uncovered_colliders_cannot_reach_the_piano_within_joint_limits(hands):
+    """Why leaving the palm / wrist / knuckle / forearm colliders out of the piano narrowphase changes nothing while the
+    joints respect their ranges: the hands hang at x = 0.4 m pointing at the keys (tasks/base.py:34-37, 173-183), the
+    forearm slides only sideways and 6 cm in depth (shadow_hand.py:42-52), and every one of those colliders stays
+    outside the piano's bounding box for any joint configuration inside the limits (4000 random poses); a pose far
+    outside them (forearm 15 cm in, wrist bent 90 degrees) does reach it — that is what the runtime flag reports."""
+    fm, _ = hands
+    om = O.OracleModel(fm); d = O.OracleData(om); d.reset()
+    rng = np.random.default_rng(0)
+    r = fm.jnt_range
+    for _ in range(4000):
+        q = np.zeros(140)
+        q[88:] = rng.uniform(r[88:, 0], r[88:, 1])
+        q[:88] = rng.uniform(r[:88, 0], r[:88, 1])
+        assert not _uncovered_boxes_near_piano(fm, d, q)
+    q = np.zeros(140); q[89] = 0.15; q[91] = 1.57
+    assert "rh_shadow_hand/rh_palm_geom1" in _uncovered_boxes_near_piano(fm, d, q)
