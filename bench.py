@@ -99,33 +99,66 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_run(steps, warmup, sample_envs=None):
-    """Times the CPU path (oracle port, all host threads) on a bounded sample of the same workload."""
-    import helpers
-    from oracle import oracle as O
-    from robopianist_b200.scene import cache
+def physical_cores():
+    """(physical cores, logical CPUs) usable by this process (Linux: unique (package, core) pairs of the affinity set)."""
+    try:
+        logical = sorted(os.sched_getaffinity(0))
+    except Exception:
+        logical = list(range(os.cpu_count() or 1))
+    pairs = set()
+    try:
+        for c in logical:
+            base = Path(f"/sys/devices/system/cpu/cpu{c}/topology")
+            pairs.add((base.joinpath("physical_package_id").read_text().strip(), base.joinpath("core_id").read_text().strip()))
+    except Exception:
+        pairs = set()
+    return (len(pairs) if pairs else len(logical)), len(logical)
 
-    cores = os.cpu_count() or 1
-    fm = cache.load_scene(gravity_compensation=True)
+
+def cpu_reference_run(steps, warmup, envs=1024, repeats=3, single_core=True):
+    """Times the CPU path (the oracle port of the reference's mj_step path; MuJoCo itself is not installable here) on a
+    bounded sample of the bench workload: the first `envs` environments of rank 0's batch, same actions, `warmup`
+    untimed control steps from reset, then `repeats` consecutive timed segments of `steps` control steps (the rollout
+    simply continues), median.  One persistent workspace per thread (oracle.OraclePool): nothing is allocated inside
+    a timed call.  Threads = physical cores.  Also the single-thread figure on a smaller sample."""
+    from oracle import oracle as O
+
+    phys, logical = physical_cores()
+    nthreads = max(1, min(phys, 256))
+    total = warmup + repeats * steps
+    ctrl, fm = make_actions(envs, total, 0)
+    ctrl = np.ascontiguousarray(ctrl[:, :, :44])
     om = O.OracleModel(fm)
-    om.set_option(maxcon=24)
-    acts = helpers.twinkle_actions()[:, :44]
-    E = sample_envs or 4 * cores
-    rng = np.random.default_rng(12345)
-    total = warmup + steps
-    ctrl = np.empty((total, E, 44))
-    lo, hi = fm.actuator_ctrlrange[:, 0], fm.actuator_ctrlrange[:, 1]
-    for t in range(total):
-        ctrl[t] = np.clip(acts[t % 158] + rng.normal(0, 0.05, (E, 44)) * (hi - lo) / 2, lo, hi)
-    ctrl[:, 0] = acts[np.arange(total) % 158]
-    # the rollout entry restarts from reset; time (warmup+steps) minus warmup-only to isolate `steps`
-    t0 = time.perf_counter()
-    om.rollout(ctrl[:warmup], E, cores) if warmup else None
-    t1 = time.perf_counter()
-    om.rollout(ctrl, E, cores)
-    t2 = time.perf_counter()
-    dt = max((t2 - t1) - (t1 - t0), 1e-9)
-    return dict(value=E * steps / dt, cores=cores, envs=E, seconds=dt, ms_per_step=dt / steps * 1e3)
+    om.set_option(maxcon=21)
+    pool = O.OraclePool(om, envs, nthreads)
+    pool.run(ctrl[:max(warmup, 1)])
+    times, macs = [], 0
+    for r in range(repeats):
+        seg = ctrl[max(warmup, 1) + r * steps: max(warmup, 1) + (r + 1) * steps]
+        if seg.shape[0] == 0:
+            break
+        t0 = time.perf_counter()
+        macs += pool.run(seg)
+        times.append((time.perf_counter() - t0) / seg.shape[0])
+    dt = float(np.median(times))
+    n_timed = sum(1 for _ in times) * steps * envs
+    out = dict(value=envs / dt, cores=nthreads, logical_cpus=logical, envs=envs, seconds=float(np.sum(times) * steps),
+               ms_per_step=dt * 1e3, repeats=len(times), spread=float(max(times) / min(times)) if times else None,
+               flops_per_env_step=2.0 * macs / max(n_timed, 1))
+    pool.close()
+    if single_core:
+        e1 = 32
+        p1 = O.OraclePool(om, e1, 1)
+        p1.run(ctrl[:max(warmup, 1), :e1])
+        k1 = min(steps, 3)
+        t0 = time.perf_counter()
+        p1.run(ctrl[max(warmup, 1):max(warmup, 1) + k1, :e1])
+        out["single_core_value"] = e1 * k1 / (time.perf_counter() - t0)
+        p1.close()
+    return out
+
+
+FP64_PEAK_TFLOPS = 148 * 1.8 * 32 * 2 * 1.965e9 / 1e12  # measured DFMA issue rate 1.8 warp-instr/clk/SM (profiles/r01_ubench3_pipe_throughput.txt)
 
 
 def main():
@@ -135,14 +168,24 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--total-envs", type=int, default=0, help="strong scaling: fixed global batch split over the ranks (BASELINE config 4: 16384)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-episode", action="store_true", help="skip the second measurement with episode phases staggered across the batch")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    strong = args.total_envs > 0
+    if strong:
+        if args.total_envs % max(world, 1):
+            raise SystemExit("--total-envs must be a multiple of the number of ranks")
+        args.envs_per_gpu = args.total_envs // max(world, 1)
+    N = args.envs_per_gpu
     config = {"workload": f"piano_with_shadow_hands/{SONG} trim_silence gravcomp primitive_fingertips "
-                          f"disable_hand_collisions, {args.envs_per_gpu} envs/GPU, PGS<=50 it tol 1e-8, elliptic, dt=0.005x10",
-              "global_envs": args.envs_per_gpu * max(world, 1), "parallelism": f"env-shard x{max(world, 1)}",
+                          f"disable_hand_collisions, {N} envs/GPU, PGS<=50 it tol 1e-8, elliptic, dt=0.005x10; "
+                          "40 box/cylinder/mesh hand colliders of the reference model are outside the narrowphase's "
+                          "coverage (none within reach of the piano: solver.flagged_envs)",
+              "global_envs": N * max(world, 1), "parallelism": f"env-shard x{max(world, 1)}",
               "l2": "flushed between timed steps (256 MiB device memset)",
               "launch_shape": "3 environments per thread block (2 blocks per SM), phase-locked per substep (chosen by batch size; rp_set_block_envs)"}
 
@@ -150,102 +193,128 @@ def main():
         if rank != 0:
             return
         r = cpu_reference_run(args.steps, max(args.warmup, 1))
+        sample = (f"first {r['envs']} envs of the batch x {args.steps} control steps x {r['repeats']} consecutive segments (median) after "
+                  f"{max(args.warmup, 1)} warm-up steps, {r['cores']} threads (physical cores; {r['logical_cpus']} logical CPUs)")
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "env-steps/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(config, sample=f"{r['envs']} envs x {args.steps} control steps"),
-                "cpu_baseline": {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port",
-                                 "sample": f"{r['envs']} envs x {args.steps} control steps, {r['cores']} threads"},
+                "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": dict(config, sample=sample),
+                "cpu_baseline": {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port", "sample": sample,
+                                 "single_core_value": r.get("single_core_value"), "segment_spread": r["spread"],
+                                 "note": "CPU restatement of the reference's MuJoCo path (MuJoCo itself is not installable here and would be several times faster per core)"},
                 "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
     import torch
     import torch.distributed as dist
-    from robopianist_b200 import native
-    import helpers
+    import warnings
+    from robopianist_b200.music import library
+    from robopianist_b200.suite.sharded import ShardedPianoEnv
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    N = args.envs_per_gpu
-    pool = max(8, min(64, args.steps + args.warmup))
-    actions_np, fm = make_actions(N, pool, rank)
-    goal, fing = helpers.song_tables(SONG)
-    model = native.Model(fm, goal, fing, kind=0, n_steps_lookahead=1)
-    batch = native.Batch(model, N, device=local_rank)
     dev = torch.device("cuda", local_rank)
+    T_CYCLE = 159                    # 158 control steps + the auto-reset step
+    pool = T_CYCLE if not args.no_full_episode else max(8, min(64, args.steps + args.warmup))
+    actions_np, fm = make_actions(N, pool, rank)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)   # the uncovered-collider notice: part of config.workload here
+        env = ShardedPianoEnv(library.load(SONG), N * world, device=local_rank, trim_silence=True, gravity_compensation=True,
+                              primitive_fingertip_collisions=True, disable_hand_collisions=True, n_steps_lookahead=1)
+    loc = env.local                  # BatchedPianoEnv of this rank
+    model, batch = loc.model, loc.batch
     actions = torch.from_numpy(actions_np).to(dev)
-    obs = torch.empty((N, model.obs_dim), dtype=torch.float64, device=dev)
-    rew = torch.empty(N, dtype=torch.float64, device=dev)
-    dis = torch.empty_like(rew)
-    st = torch.empty(N, dtype=torch.uint8, device=dev)
-    obs_all = torch.empty((N * world, model.obs_dim), dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def one_step(t):
-        batch.step(actions[t % pool].data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
-        if world > 1:
-            dist.all_gather_into_tensor(obs_all, obs)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    batch.reset(None, obs.data_ptr())
-    for t in range(args.warmup):
-        one_step(t)
-    barrier()
-    launches0 = batch.launches
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clocks:
-        wall0 = time.perf_counter()
-        for k in range(args.steps):
+    def timed_region(step_fn, steps):
+        """K steps, each bracketed by CUDA events on the launching stream (the L2 flush stays outside the brackets); the
+        gather of step k overlaps step k+1 — a wait for it lands inside a later bracket, the last one inside its own."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for k in range(steps):
             flush.zero_()
             evs[k][0].record()
-            one_step(args.warmup + k)
+            step_fn(k)
+            if k == steps - 1:
+                env.gathered()
             evs[k][1].record()
         barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- protocol A: reset, W warm-up steps, K timed steps (the window the driver uses)
+    env.reset()
+    for t in range(args.warmup):
+        env.step(actions[t % pool])
+    env.gathered()
+    barrier()
+    launches0 = batch.launches
+    with ClockSampler(local_rank) as clocks:
+        wall0 = time.perf_counter()
+        dev_ms = timed_region(lambda k: env.step(actions[(args.warmup + k) % pool]), args.steps)
         wall = time.perf_counter() - wall0
     launches = batch.launches - launches0
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    dev_ms = float(t_ms.item())
     value = N * world * args.steps / (dev_ms * 1e-3)
     diag = batch.get_diag()
 
-    # ---- e2e: the same step sequence again, through the host call (rp_step_staged: pageable numpy actions ->
-    # pinned staging -> device, launch, device -> pinned staging, read on the host), wall clock
-    batch.reset(None, obs.data_ptr())
+    # ---- e2e: the same step sequence again through the host call of the public API (BatchedPianoEnv.step_host: pageable
+    # numpy actions -> pinned staging -> device, launch, device -> pinned staging, read on the host), wall clock
+    loc.reset()
     for t in range(args.warmup):
-        one_step(t)
+        loc.step(actions[t % pool])
     barrier()
-    e2e_steps = args.steps
-    host_actions = actions_np
     w0 = time.perf_counter()
     e2e_reward = 0.0
-    for k in range(e2e_steps):
-        _, rew_h, _, _, _ = batch.step_host(host_actions[(args.warmup + k) % pool], copy=False)
+    for k in range(args.steps):
+        _, rew_h, _, _, _ = loc.step_host(actions_np[(args.warmup + k) % pool], copy=False)
         e2e_reward += float(rew_h.sum())  # each rank consumes its own shard on the host (no collective on this path)
     barrier()
     e2e_s = time.perf_counter() - w0
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = N * world * e2e_steps / float(t_e.item())
+    e2e_value = N * world * args.steps / float(t_e.item())
     h2d = N * model.act_dim * 8
     d2h = N * (model.obs_dim + 2 + 5) * 8 + N
 
+    # ---- protocol B: episode phases staggered uniformly over the batch (env i is reset at global step i mod 159 of a 159
+    # step lead-in), so that the timed window holds every part of the song in equal measure: the full-episode mean
+    full = None
+    if not args.no_full_episode:
+        s_i = torch.arange(N, device=dev) % T_CYCLE
+        ar = torch.arange(N, device=dev)
+        loc.reset()
+        for g in range(T_CYCLE):
+            m = (s_i == g).to(torch.uint8)
+            if g > 0:
+                loc.reset(m)
+            loc.step(actions[(g - s_i) % T_CYCLE, ar])
+        staged = [actions[(T_CYCLE + k - s_i) % T_CYCLE, ar].contiguous() for k in range(args.steps)]
+        barrier()
+        ms_b = timed_region(lambda k: env.step(staged[k]), args.steps)
+        dg = batch.get_diag()
+        full = {"ms_per_step": ms_b / args.steps, "value": N * world * args.steps / (ms_b * 1e-3), "steps": args.steps,
+                "mean_contacts": float(dg["ncon"].mean()), "mean_pgs_iters_last_substep": float(dg["niter"].mean()),
+                "flagged_envs": int((dg["flags"] != 0).sum()),
+                "how": "episode phases staggered uniformly (env i reset at lead-in step i mod 159): every timed step sees the whole song's contact mix"}
+
     if rank != 0:
+        env.close()
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- roofline of the step kernel (the only kernel in the step)
+    # ---- roofline of the step kernel (the only kernel of a step; N>1 adds the all-gather)
     abytes = algorithmic_bytes_per_env_step(model.nv, model.nu, model.obs_dim, model.act_dim)
     peaks = {}
     try:
@@ -253,27 +322,45 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    kernel_ms = dev_ms / args.steps  # one launch per step (plus NCCL for N>1)
+    kernel_ms = dev_ms / args.steps
     achieved = N * abytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH if N == ENVS_PER_GPU else None, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/)",
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH if N == ENVS_PER_GPU else None,
+                "traffic_unit": "bytes/launch: ncu dram__bytes_read.sum + dram__bytes_write.sum of one captured launch, cited from profiles/ (NOT measured in this run)",
                 "peak_source": "measured" if peaks else "fallback",
                 "algorithmic_bytes_per_env_step": abytes,
-                "note": "latency/ALU-bound fp64 Gauss-Seidel; see profiles/ for pipe utilisation"}
+                "note": "latency-bound fp64 Gauss-Seidel: the HBM fraction is reported as required, the fp64 figures below say how far the solver is from the arithmetic roof"}
     line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "clocks": clocks.summary(), "wall_s": wall,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
+                    "steps": args.steps, "api": "BatchedPianoEnv.step_host"},
             "gpu_launches": int(launches), "roofline": roofline,
             "solver": {"mean_pgs_iters_last_substep": float(diag["niter"].mean()),
                        "mean_contacts": float(diag["ncon"].mean()), "flagged_envs": int((diag["flags"] != 0).sum())}}
+    if full is not None:
+        line["full_episode"] = full
+    if world > 1:
+        line["collective"] = {"op": "all_gather_into_tensor (NCCL), async, overlapped with the next step's kernel", "dtype": "float32",
+                              "bytes_received_per_rank_per_step": env.gather_bytes_per_step}
     if not args.no_cpu_baseline and world == 1:
-        r = cpu_reference_run(steps=20, warmup=2)
+        r = cpu_reference_run(steps=5, warmup=2, envs=512)
         line["cpu_baseline"] = {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port",
-                                "sample": f"{r['envs']} envs x 20 control steps, {r['cores']} threads, {r['seconds']:.1f} s"}
+                                "sample": f"first {r['envs']} envs x 5 control steps x {r['repeats']} consecutive segments (median) after 2 warm-up steps, "
+                                          f"{r['cores']} threads (physical cores; {r['logical_cpus']} logical CPUs), {r['seconds']:.1f} s",
+                                "single_core_value": r.get("single_core_value"), "segment_spread": r["spread"]}
+        # solver arithmetic: multiply-adds the oracle counts for the same workload (dense A+R formulation: projection
+        # J M^-1 J^T and the Gauss-Seidel residuals), two flops each
+        fl = r["flops_per_env_step"]
+        roofline.update({"flops_per_env_step": fl, "flops_source": "CPU oracle MAC counter on the same workload (first control steps of the sample), x2",
+                         "achieved_tflops": fl * N / (kernel_ms * 1e-3) / 1e12, "fp64_peak_tflops": FP64_PEAK_TFLOPS,
+                         "fp64_peak_source": "DFMA issue rate measured on B200 (scratch/ubench3.cu: 1.8 warp-instr/clk/SM x 148 SMs x 1.965 GHz)",
+                         "fp64_frac": fl * N / (kernel_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                         "arithmetic_intensity_flop_per_byte": fl / abytes})
     print(json.dumps(line))
+    env.close()
     if world > 1:
         dist.destroy_process_group()
 

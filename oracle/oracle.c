@@ -1182,6 +1182,88 @@ int orc_rollout(const orc_model *o, int nenv, int nsteps, const double *ctrl, in
   return 0;
 }
 
+/* Persistent pool for the CPU-baseline timing: one orc_data workspace per host thread, allocated (and touched) once,
+ * so that a timed call does no allocation at all — the r01 timing created 128 workspaces of ~3 MB per call and measured
+ * page faults and mmap contention as much as the solver (3.4k vs 20.9k env-steps/s on two identical boxes).  The
+ * environments' states live in a caller-owned array [nenv][3 nv + nu] (qpos, qvel, qacc_warmstart, ctrl); a thread
+ * loads a state, recomputes the position / velocity stage (orc_step1, what a running environment already holds),
+ * runs `nsteps` control steps and stores the state back, so a rollout can be continued call after call. */
+typedef struct orc_pool {
+  const orc_model *o;
+  int nthreads;
+  orc_data **d;
+} orc_pool;
+typedef struct {
+  orc_pool *pool;
+  int nenv, nsteps, per_env, reset, tid;
+  const double *ctrl;
+  double *state;
+  int *next;
+  pthread_mutex_t *mu;
+  long macs;
+} pool_job;
+orc_pool *orc_pool_create(const orc_model *o, int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 1024) nthreads = 1024;
+  orc_pool *p = (orc_pool *)calloc(1, sizeof(orc_pool));
+  p->o = o; p->nthreads = nthreads;
+  p->d = (orc_data **)calloc(nthreads, sizeof(orc_data *));
+  for (int i = 0; i < nthreads; i++) { p->d[i] = orc_data_create(o); orc_reset(o, p->d[i]); }
+  return p;
+}
+void orc_pool_destroy(orc_pool *p) {
+  for (int i = 0; i < p->nthreads; i++) orc_data_destroy(p->d[i]);
+  free(p->d); free(p);
+}
+static void *pool_worker(void *arg) {
+  pool_job *job = (pool_job *)arg;
+  const orc_model *o = job->pool->o;
+  orc_data *d = job->pool->d[job->tid];
+  int nv = o->m.nv, nu = o->m.nu, nsub = o->m.nsubstep, stride = 3 * nv + nu;
+  long mac0 = d->mac_count;
+  for (;;) {
+    pthread_mutex_lock(job->mu);
+    int e = (*job->next)++;
+    pthread_mutex_unlock(job->mu);
+    if (e >= job->nenv) break;
+    double *st = job->state + (size_t)e * stride;
+    if (job->reset) orc_reset(o, d);
+    else {
+      memcpy(d->qpos, st, sizeof(double) * nv); memcpy(d->qvel, st + nv, sizeof(double) * nv);
+      memcpy(d->qacc_warmstart, st + 2 * nv, sizeof(double) * nv); memcpy(d->ctrl, st + 3 * nv, sizeof(double) * nu);
+      memset(d->qfrc_applied, 0, sizeof(double) * nv);
+      orc_step1(o, d);
+    }
+    for (int t = 0; t < job->nsteps; t++) {
+      const double *c = job->ctrl + ((size_t)t * (job->per_env ? job->nenv : 1) + (job->per_env ? e : 0)) * nu;
+      orc_control_step(o, d, c, nsub);
+    }
+    memcpy(st, d->qpos, sizeof(double) * nv); memcpy(st + nv, d->qvel, sizeof(double) * nv);
+    memcpy(st + 2 * nv, d->qacc_warmstart, sizeof(double) * nv); memcpy(st + 3 * nv, d->ctrl, sizeof(double) * nu);
+  }
+  job->macs = d->mac_count - mac0;
+  return NULL;
+}
+/* returns the multiply-adds the solver counted during the call (projection + Gauss-Seidel residuals) */
+long orc_pool_rollout(orc_pool *p, int nenv, int nsteps, const double *ctrl, int per_env, double *state, int reset, int nthreads) {
+  if (nthreads < 1 || nthreads > p->nthreads) nthreads = p->nthreads;
+  pthread_mutex_t mu;
+  pthread_mutex_init(&mu, NULL);
+  int next = 0;
+  pool_job *jobs = (pool_job *)calloc(nthreads, sizeof(pool_job));
+  pthread_t *th = (pthread_t *)calloc(nthreads, sizeof(pthread_t));
+  for (int i = 0; i < nthreads; i++) {
+    pool_job j = {p, nenv, nsteps, per_env, reset, i, ctrl, state, &next, &mu, 0};
+    jobs[i] = j;
+    pthread_create(&th[i], NULL, pool_worker, &jobs[i]);
+  }
+  long macs = 0;
+  for (int i = 0; i < nthreads; i++) { pthread_join(th[i], NULL); macs += jobs[i].macs; }
+  pthread_mutex_destroy(&mu);
+  free(jobs); free(th);
+  return macs;
+}
+
 /* accessors for ctypes */
 double *orc_ptr(orc_data *d, const char *name) {
 #define F(n) if (!strcmp(name, #n)) return d->n;

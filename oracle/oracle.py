@@ -54,6 +54,12 @@ def lib():
         L.orc_contact_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         L.orc_mac_count.restype = C.c_long
         L.orc_mac_count.argtypes = [C.c_void_p]
+        L.orc_pool_create.restype = C.c_void_p
+        L.orc_pool_create.argtypes = [C.c_void_p, C.c_int]
+        L.orc_pool_destroy.argtypes = [C.c_void_p]
+        L.orc_pool_rollout.restype = C.c_long
+        L.orc_pool_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double),
+                                       C.c_int, C.c_int]
     return _LIB
 
 
@@ -83,6 +89,42 @@ class OracleModel:
         lib().orc_rollout(self.ptr, nenv, ctrl.shape[0], ctrl.ctypes.data_as(C.POINTER(C.c_double)), per_env,
                           out.ctypes.data_as(C.POINTER(C.c_double)), nthreads)
         return out
+
+
+class OraclePool:
+    """Persistent per-thread workspaces for timed multi-threaded rollouts (orc_pool_*): `run` continues every
+    environment from `self.state` ([nenv, 3 nv + nu]: qpos, qvel, qacc_warmstart, ctrl)."""
+
+    def __init__(self, model: OracleModel, nenv: int, nthreads: int):
+        self.model, self.nenv, self.nthreads = model, int(nenv), int(nthreads)
+        self.ptr = lib().orc_pool_create(model.ptr, self.nthreads)
+        self.state = np.zeros((self.nenv, 3 * model.nv + model.nu))
+        self._fresh = True
+
+    def run(self, ctrl: np.ndarray, nthreads: int = 0) -> int:
+        """ctrl [T, nu] (broadcast) or [T, nenv, nu]; returns the solver multiply-adds counted during the call."""
+        ctrl = np.ascontiguousarray(ctrl, np.float64)
+        per_env = 1 if ctrl.ndim == 3 else 0
+        dp = C.POINTER(C.c_double)
+        macs = lib().orc_pool_rollout(self.ptr, self.nenv, ctrl.shape[0], ctrl.ctypes.data_as(dp), per_env,
+                                      self.state.ctypes.data_as(dp), int(self._fresh), int(nthreads))
+        self._fresh = False
+        return int(macs)
+
+    @property
+    def qpos(self):
+        return self.state[:, :self.model.nv]
+
+    def close(self):
+        if self.ptr:
+            lib().orc_pool_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _SHAPES = {

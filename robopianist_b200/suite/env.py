@@ -248,9 +248,11 @@ class BatchedPianoEnv:
                         self.step_type.data_ptr(), self.reward_terms.data_ptr())
         return self.obs, self.reward, self.discount, self.step_type
 
-    def step_host(self, actions: np.ndarray):
-        """Host buffers in and out (pinned staging + copies inside the library): the e2e call."""
-        return self.batch.step_host(actions)
+    def step_host(self, actions: np.ndarray, copy: bool = True):
+        """Host buffers in and out (pinned staging + copies inside the library): the e2e call.  Returns (obs, reward,
+        discount, step_type, reward_terms) as numpy arrays; copy=False hands out views of the pinned output buffer
+        (overwritten by the next call)."""
+        return self.batch.step_host(actions, copy=copy)
 
     def get_musical_metrics(self):
         """Mean precision / recall / F1 (keys and sustain) over the envs that completed an episode:

@@ -49,3 +49,71 @@ def test_all_gather_outputs_world2():
         assert full.shape == (8, 10)
         assert (full[:, 0] == np.arange(8)).all() and (full[:, 7] == 2 * np.arange(8)).all()
         assert (full[:, 9] == np.arange(8) % 3).all()
+
+
+class _FakeLocalEnv:
+    """Stands in for BatchedPianoEnv on CPU: env i of the global batch reports obs = 1000 i + step, reward = i, ..."""
+
+    class _M:
+        obs_dim, act_dim = 5, 2
+
+    def __init__(self, n, first):
+        self.num_envs, self.model, self.device = n, self._M(), torch.device("cpu")
+        self.ids = torch.arange(first, first + n, dtype=torch.float64)
+        self.obs = torch.zeros((n, 5), dtype=torch.float64)
+        self.reward = torch.zeros(n, dtype=torch.float64); self.discount = torch.ones(n, dtype=torch.float64)
+        self.step_type = torch.zeros(n, dtype=torch.uint8)
+        self.t = 0
+
+    def _fill(self):
+        self.obs[:] = (1000 * self.ids + self.t)[:, None]
+        self.reward[:] = self.ids * 0.5
+        self.step_type[:] = 1 if self.t else 0
+        return self.obs, self.reward, self.discount, self.step_type
+
+    def reset(self):
+        self.t = 0
+        return self._fill()
+
+    def step(self, actions):
+        assert actions.shape == (self.num_envs, 2) and torch.equal(actions[:, 0], self.ids)   # got its own slice
+        self.t += 1
+        return self._fill()
+
+    def close(self):
+        pass
+
+
+def _sharded_worker(rank, world, port, q):
+    from robopianist_b200.suite.sharded import ShardedPianoEnv
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    env = ShardedPianoEnv(None, 8, local_factory=_FakeLocalEnv)
+    env.reset()
+    recs = [tuple(x.clone().numpy() for x in env.gathered())]
+    glob_actions = torch.stack([torch.arange(8, dtype=torch.float64), torch.zeros(8, dtype=torch.float64)], dim=1)
+    for t in range(5):     # more steps than buffers: exercises the wait-before-reuse path
+        env.step(glob_actions)
+        recs.append(tuple(x.clone().numpy() for x in env.gathered()))
+    env.close()
+    q.put((rank, recs))
+    dist.destroy_process_group()
+
+
+def test_sharded_env_gathers_the_global_batch_world2():
+    """ShardedPianoEnv over a fake CPU env, world size 2 (gloo): global actions are sliced per rank, every rank sees the
+    whole batch's packed float32 outputs after every step, in env order, across the double-buffer wrap-around."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=180) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    for r in range(2):
+        for t, (obs, rew, dis, st) in enumerate(res[r]):
+            assert obs.dtype == np.float32 and obs.shape == (8, 5)
+            assert (obs[:, 0] == 1000 * np.arange(8) + t).all() and (rew == 0.5 * np.arange(8)).all()
+            assert (dis == 1).all() and (st == (1 if t else 0)).all()
