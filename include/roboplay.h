@@ -170,6 +170,12 @@ int rp_get_metrics(rp_batch *, double *out);
 int rp_midi_enable(rp_batch *, int capacity);
 int rp_get_midi(rp_batch *, uint32_t *events, int32_t *counts);
 
+/* Replaces the song of a batch (goal table uint8 [n_steps, 89], fingering table int8 [n_steps, 88], HOST buffers;
+ * synchronous): what PianoWithShadowHands._maybe_change_midi + _reset_trajectory do at an episode start when the task has
+ * augmentations (piano_with_shadow_hands.py:151-165).  Lookahead, reward switches and observation width stay those of
+ * the model.  Call rp_reset afterwards: running episodes are not re-indexed. */
+int rp_set_song(rp_batch *, const uint8_t *goal, const int8_t *fingering, int n_steps);
+
 /* Launch shape of the step kernel (results do not depend on it): environments per thread block, 1 or
  * RP_BLOCK_ENVS (blocks whose environments run each substep in step with each other, which shares their
  * instruction fetches); 0 = chosen from the batch size (default). */

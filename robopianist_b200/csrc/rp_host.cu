@@ -2,6 +2,7 @@
 // launches.  No CPU fallback: every entry point that computes needs a CUDA device.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -428,6 +429,25 @@ extern "C" int rp_batch_destroy(rp_batch* b) {
   cudaFree(b->midi_events); cudaFree(b->midi_count); cudaFree(b->ot_scratch);
   cudaFreeHost(b->h_action); cudaFreeHost(b->h_out);
   delete b;
+  return 0;
+}
+
+extern "C" int rp_set_song(rp_batch* b, const uint8_t* goal, const int8_t* fingering, int n_steps) {
+  if (!b || !goal || !fingering || n_steps < 1) return fail("rp_set_song: bad arguments");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  uint8_t* ng = nullptr; int8_t* nf = nullptr;
+  const size_t gb = (size_t)n_steps * RP_GOAL_DIM, fb = (size_t)n_steps * RP_NK;
+  if (cudaMalloc((void**)&ng, gb) != cudaSuccess || cudaMalloc((void**)&nf, fb) != cudaSuccess) {
+    cudaFree(ng); cudaFree(nf);
+    return fail("rp_set_song: allocation failed");
+  }
+  CUDA_OK(cudaMemcpy(ng, goal, gb, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(nf, fingering, fb, cudaMemcpyHostToDevice));
+  // episode length lives in the batch's device copy of the model constants
+  CUDA_OK(cudaMemcpy((char*)b->d_dm + offsetof(RpDevModel, T), &n_steps, sizeof(int), cudaMemcpyHostToDevice));
+  cudaFree(b->d_goal); cudaFree(b->d_fingering);
+  b->d_goal = ng; b->d_fingering = nf;
   return 0;
 }
 

@@ -21,7 +21,7 @@ EXPORTS = [
     "rp_last_error", "rp_version", "rp_model_create", "rp_model_destroy", "rp_obs_dim", "rp_action_dim",
     "rp_reward_terms", "rp_batch_create", "rp_batch_destroy", "rp_set_option", "rp_reset", "rp_step",
     "rp_step_host", "rp_physics_step", "rp_get_state", "rp_set_state", "rp_get_diag", "rp_get_aux",
-    "rp_launch_count", "rp_step_staged", "rp_host_buffers", "rp_get_metrics", "rp_midi_enable", "rp_get_midi", "rp_set_block_envs",
+    "rp_launch_count", "rp_step_staged", "rp_host_buffers", "rp_get_metrics", "rp_midi_enable", "rp_get_midi", "rp_set_block_envs", "rp_set_song",
 ]
 
 
@@ -63,6 +63,7 @@ def lib():
         L.rp_host_buffers.argtypes = [vp, C.POINTER(dp), C.POINTER(dp)]
         L.rp_get_metrics.argtypes = [vp, dp]
         L.rp_midi_enable.argtypes = [vp, C.c_int]
+        L.rp_set_song.argtypes = [vp, C.POINTER(C.c_uint8), C.POINTER(C.c_int8), C.c_int]
         L.rp_set_block_envs.argtypes = [vp, C.c_int]
         L.rp_get_midi.argtypes = [vp, C.POINTER(C.c_uint32), ip]
         L.rp_launch_count.restype = C.c_int64
@@ -163,6 +164,12 @@ class Batch:
         if copy:
             return obs.copy(), rew.copy(), dis.copy(), st.copy(), terms.copy()
         return obs, rew, dis, st, terms
+
+    def set_song(self, goal: np.ndarray, fingering: np.ndarray):
+        """New goal / fingering tables (uint8 [T, 89], int8 [T, 88]) for every environment; reset afterwards."""
+        g = np.ascontiguousarray(goal, np.uint8); f = np.ascontiguousarray(fingering, np.int8)
+        assert g.ndim == 2 and g.shape[1] == 89 and f.shape == (g.shape[0], 88)
+        _check(lib().rp_set_song(self.ptr, g.ctypes.data_as(C.POINTER(C.c_uint8)), f.ctypes.data_as(C.POINTER(C.c_int8)), int(g.shape[0])))
 
     def physics_step(self, ctrl_ptr=None, nsub=1):
         _check(lib().rp_physics_step(self.ptr, ctrl_ptr, nsub))

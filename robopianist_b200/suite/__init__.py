@@ -6,8 +6,8 @@
 
 The PIG-dataset names (``REPERTOIRE_150`` / ``ETUDE_12``) need the PIG ``.proto`` files the reference
 downloads separately (cli.py:231-288); they are not distributable, so those lists are empty here and
-only the programmatic debug songs (music/library.py) are registered.  Any ``.mid`` file can be passed
-through ``midi_file``.
+only the programmatic debug songs (music/library.py) are registered.  Any ``.mid`` file, and any serialised
+``NoteSequence`` ``.proto`` file (the PIG format; music/proto.py), can be passed through ``midi_file``.
 """
 from __future__ import annotations
 
@@ -43,14 +43,14 @@ def load(
 ):
     """Loads a RoboPianist environment backed by the CUDA rollout.
 
-    ``seed`` is accepted for signature compatibility: the environment itself draws no random numbers
-    (qpos0 start, no augmentations).  ``recompile_physics`` is meaningless here (the scene is
+    ``seed`` seeds the environment's ``numpy.random.RandomState`` (the reference's ``random_state``); the only draws are
+    those of the song augmentations (``task_kwargs['augmentations']``, suite/variations.py).  ``recompile_physics`` is meaningless here (the scene is
     flattened once).  ``legacy_step=False`` is rejected: the kernel implements the reference's
     default legacy ordering (mj_step2 + mj_step1; SURVEY.md §2 table, `Physics.step`).
     """
     if not legacy_step:
         raise NotImplementedError("only legacy_step=True (the reference default) is implemented")
-    del seed, recompile_physics
+    del recompile_physics
     if midi_file is not None:
         midi = library.load(midi_file, stretch=stretch, shift=shift)
     else:
@@ -58,7 +58,7 @@ def load(
             raise ValueError(f"Unknown environment {environment_name}. Available environments: {ALL}")
         midi = library.load(_ALL_DICT[environment_name], stretch=stretch, shift=shift)
     batched = BatchedPianoEnv(midi, num_envs=num_envs, device=device, iterations=iterations,
-                              tolerance=tolerance, **dict(task_kwargs or {}))
+                              tolerance=tolerance, seed=seed, **dict(task_kwargs or {}))
     return PianoEnv(batched) if num_envs == 1 else batched
 
 

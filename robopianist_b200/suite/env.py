@@ -80,8 +80,6 @@ class BoundedArray(Array):
 
 def _unsupported(kw: Mapping[str, Any]):
     """Reference kwargs this path does not implement must fail loudly, not be ignored."""
-    if kw["augmentations"]:
-        raise NotImplementedError("augmentations (variations.py) are host-side per-reset MIDI edits: out of scope")
     if kw["randomize_hand_positions"]:
         raise NotImplementedError("randomize_hand_positions is not implemented")
     if kw["reduced_action_space"]:
@@ -154,7 +152,7 @@ class BatchedPianoEnv:
 
     def __init__(self, midi, num_envs: int = 1, device: int = 0, task: str = "piano_with_shadow_hands",
                  iterations: Optional[int] = None, tolerance: Optional[float] = None,
-                 reward_type: int = 0, **task_kwargs):
+                 reward_type: int = 0, seed: Optional[int] = None, **task_kwargs):
         import torch
 
         unknown = set(task_kwargs) - set(_TASK_KWARGS)
@@ -169,6 +167,13 @@ class BatchedPianoEnv:
         self.torch = torch
         self.task_name = task
         cfg = derive_task_config(midi, hands, kw)
+        # augmentations (suite/variations.py): applied to the initial song at every full reset(); the whole batch gets the
+        # same draw (one song table per batch on the device), episodes that auto-reset inside the kernel keep the
+        # current song until the next reset() call.  The reference draws per episode of its single environment.
+        self._augmentations = list(kw["augmentations"]) if kw["augmentations"] else None
+        self._initial_midi = cfg["midi"]
+        self._initial_buffer_time = float(kw["initial_buffer_time"])
+        self.random_state = np.random.RandomState(seed)
         self.control_timestep = cfg["control_timestep"]
         midi = self.midi = cfg["midi"]
         traj = self.trajectory = cfg["trajectory"]
@@ -229,6 +234,8 @@ class BatchedPianoEnv:
     # ------------------------------------------------------------------ stepping
     def reset(self, mask=None):
         """FIRST observation for all envs (mask: uint8 CUDA tensor selecting the envs to reset)."""
+        if mask is None and self._augmentations:
+            self._change_midi()
         self.batch.reset(None if mask is None else mask.data_ptr(), self.obs.data_ptr())
         if mask is None:
             self.reward.zero_(); self.discount.fill_(1.0); self.step_type.fill_(int(StepType.FIRST))
@@ -237,6 +244,18 @@ class BatchedPianoEnv:
             self.reward.masked_fill_(m, 0.0); self.discount.masked_fill_(m, 1.0)
             self.step_type.masked_fill_(m, int(StepType.FIRST))
         return self.obs, self.reward, self.discount, self.step_type
+
+    def _change_midi(self):
+        """PianoWithShadowHands._maybe_change_midi + _reset_trajectory (piano_with_shadow_hands.py:151-165)."""
+        from . import variations
+        midi = variations.apply(self._augmentations, self._initial_midi, self.random_state)
+        traj = trajectory.NoteTrajectory.from_seq(midi, self.control_timestep)
+        if self._initial_buffer_time:
+            traj = traj.add_initial_buffer_time(self._initial_buffer_time)
+        self.midi, self.trajectory = midi, traj
+        self._notes, self._sustains = traj.notes, traj.sustains
+        self.goal_table, self.fingering_table = traj.goal_table(), traj.fingering_table()
+        self.batch.set_song(self.goal_table, self.fingering_table)
 
     def step(self, actions):
         """actions: float64 CUDA tensor [N, act_dim] (contiguous). One launch; asynchronous."""
@@ -322,12 +341,23 @@ class _Task:
     """`env.task` facade: `_notes`, `_sustains`, `piano`, `reward_fn.reward_terms`, `control_timestep`."""
 
     def __init__(self, env):
-        b = env._batched
-        self._notes, self._sustains = b._notes, b._sustains
+        self._b = env._batched
         self.piano = _Piano(env)
         self.reward_fn = _RewardFn()
-        self.control_timestep = b.control_timestep
-        self.midi = b.midi
+        self.control_timestep = self._b.control_timestep
+
+    # the song may change at every reset (augmentations): always the running episode's
+    @property
+    def _notes(self):
+        return self._b._notes
+
+    @property
+    def _sustains(self):
+        return self._b._sustains
+
+    @property
+    def midi(self):
+        return self._b.midi
 
 
 _TERM_NAMES = ("key_press_reward", "sustain_reward", "energy_reward", "fingering_reward", "forearm_reward")

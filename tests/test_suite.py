@@ -92,6 +92,33 @@ def test_plain_midi_reaches_the_ot_reward_through_load(tmp_path):
 
 
 @pytest.mark.gpu
+def test_augmentations_change_the_song_at_every_reset():
+    """task_kwargs['augmentations'] (suite/variations.py): a new song per reset, drawn from the env's seeded
+    RandomState exactly as the reference's _maybe_change_midi does (piano_with_shadow_hands.py:151-165); the goal
+    observation and the episode length follow the augmented song."""
+    from robopianist_b200.suite import variations as V
+    from robopianist_b200.suite.env import BatchedPianoEnv, PianoEnv
+    midi = _test_midi(0.05)
+    aug = [V.MidiPitchShift(prob=1.0, shift_range=12), V.MidiTemporalStretch(prob=1.0, stretch_range=0.5)]
+    env = PianoEnv(BatchedPianoEnv(midi, num_envs=1, seed=7, control_timestep=0.05, n_steps_lookahead=0, augmentations=aug, **KW))
+    rs = np.random.RandomState(7)
+    seen = set()
+    for ep in range(4):
+        ts = env.reset()
+        want = V.apply(aug, midi, rs)
+        traj = trajectory.NoteTrajectory.from_seq(want, 0.05)
+        assert len(env.task._notes) == len(traj.notes)
+        assert np.array_equal(ts.observation["goal"], traj.goal_table()[0].astype(np.float64))
+        seen.add((want.notes[0].pitch, len(traj.notes)))
+        n = 0
+        while not ts.last():
+            ts = env.step(np.zeros(45)); n += 1
+        assert n == len(traj.notes)
+    assert len(seen) > 1
+    env.close()
+
+
+@pytest.mark.gpu
 def test_masked_reset_reports_first_for_the_reset_envs():
     import torch
     from robopianist_b200.suite.env import BatchedPianoEnv
