@@ -266,7 +266,8 @@ __device__ __noinline__ int pgs_solve(Smem* smp, const int h, const int bar_id, 
     // that row commits and broadcasts, the search resumes behind it — the rows skipped in between would have
     // committed a change of exactly zero at their turn, so the iterates are those of the row-by-row sweep.  (A plain
     // row-by-row loop for sweeps in which most rows change — a hand at rest, nothing saturated — was measured and is
-    // slower at every switch-over threshold: 18.2 ms per step always on, 14.83 never, r02g.)
+    // slower at every switch-over threshold: 18.2 ms per step always on, 14.83 never, r02g; fetching the column of the
+    // most likely next row one commit ahead changed nothing, r02p.)
     {
       const double fbase = fr_b + fr_R * fr_f;  // f only changes at the lane's own commit
       double res = fbase + va;
@@ -274,21 +275,20 @@ __device__ __noinline__ int pgs_solve(Smem* smp, const int h, const int bar_id, 
       double fx = x < fr_lo ? fr_lo : x;
       fx = x > fr_hi ? fr_hi : fx;
       unsigned m = __ballot_sync(FULL, hl && fx != fr_f);
-      {
-        while (m != 0u) {
-          const int i = __ffs(m) - 1;
-          const double dl = fx - fr_f;
-          const double imp = dl * (0.5 * dl * fr_AR + res);
-          const double dbc = shfl(dl, i), ibc = shfl(imp, i);
-          va -= pcol[i * RS] * dbc;
-          improvement -= ibc;
-          if (lane == i) fr_f = fx;
-          res = fbase + va;
-          x = fr_f - res * fr_ARi;
-          fx = x < fr_lo ? fr_lo : x;
-          fx = x > fr_hi ? fr_hi : fx;
-          m = __ballot_sync(FULL, hl && lane > i && fx != fr_f);
-        }
+      while (m != 0u) {
+        const int i = __ffs(m) - 1;
+        const double col = pcol[i * RS];
+        const double dl = fx - fr_f;
+        const double imp = dl * (0.5 * dl * fr_AR + res);
+        const double dbc = shfl(dl, i), ibc = shfl(imp, i);
+        va -= col * dbc;
+        improvement -= ibc;
+        if (lane == i) fr_f = fx;
+        res = fbase + va;
+        x = fr_f - res * fr_ARi;
+        fx = x < fr_lo ? fr_lo : x;
+        fx = x > fr_hi ? fr_hi : fx;
+        m = __ballot_sync(FULL, hl && lane > i && fx != fr_f);
       }
     }
     PTICK(8)
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
 #pragma unroll
   for (int s = 0; s < KS; s++) key_actforce[s] = 0;
   int niter_last = 0, ncon_last = 0, flags = flags_init_overflow ? 4 : 0;
-  int work = 0;  // sum over substeps of sweeps x (1 + contacts): predictor of the next step's duration
+  long long busy = 0;  // cycles this environment spent in its own substeps (phase-barrier waits excluded): predictor of the next step's duration
   const int maxiter = a.iterations > 0 ? a.iterations : dm->iterations;
   const double tol = a.tolerance >= 0 ? a.tolerance : dm->tol;
 
@@ -595,6 +595,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         continue;
       }
     }
+    const long long t_sub = clock64();
     const bool last_pass = (sub == nsub);  // kinematics-only pass for the task epilogue / reset
     if (last_pass && a.mode == RP_MODE_PHYSICS) break;
     // ---------------------------------------------------------------- hand kinematics (by level)
@@ -1356,7 +1357,6 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       }
     }
     niter_last = iter;
-    work += iter * (1 + ncon);
 
     TICK(12)
     if (EPB > 1 && ((RP_PHASE_MASK) & 4)) __syncthreads();
@@ -1481,6 +1481,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       }
     }
     env_sync<NW, EPB>(bar_id);
+    busy += clock64() - t_sub;
     TICK(15)
   }  // substeps
 
@@ -1505,7 +1506,8 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     }
     if (anybad) flags |= 2;
     if (tid == 0 && a.diag) { a.diag[3 * env + 0] = ncon_last; a.diag[3 * env + 1] = niter_last; a.diag[3 * env + 2] = flags | (sm.near_uncovered ? 8 : 0); }
-    if (tid == 0 && a.work) a.work[env] = work;
+    if (tid == 0 && a.work) a.work[env] = (int)(busy >> 12);
+    //  // rp_order_kernel buckets by work >> 4: 64 K cycles per bucket
     if (a.act_force) {
       if (HANDS && lane < dm->nact[h]) a.act_force[(size_t)env * nu + h * dm->nact[0] + lane] = actforce;
       if (dm->nkey_act) {
@@ -1737,7 +1739,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
   }
 }
 
-// Launch order for the next step: environments sorted by decreasing work of the last step (bucket sort,
+// Launch order for the next step: environments sorted by decreasing duration of their last step (bucket sort,
 // one block).  Durations vary 4x between environments (PGS sweeps x contacts); starting the long ones
 // first shortens the tail of the last wave.  Order inside a bucket is arbitrary (results do not depend
 // on which block runs which environment).

@@ -206,6 +206,9 @@ class BatchedPianoEnv:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             self.batch = native.Batch(self.model, self.num_envs, device=device, stream=stream)
+        import os
+        if os.environ.get("ROBOPLAY_BLOCK_ENVS"):   # launch shape under test (results do not depend on it)
+            self.batch.set_block_envs(int(os.environ["ROBOPLAY_BLOCK_ENVS"]))
         N, dev = self.num_envs, self.device
         self.obs = torch.empty((N, self.model.obs_dim), dtype=torch.float64, device=dev)
         self.reward = torch.empty(N, dtype=torch.float64, device=dev)
