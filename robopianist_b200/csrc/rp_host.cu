@@ -151,6 +151,36 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
       if (slot < 0 || slot >= 52 || d.black_after[slot] >= 0) return bad("black key lattice");
       d.black_after[slot] = k;
     }
+    // Broadphase slack along y.  With every hinge parallel to y a key's y extent does not change with its angle; white
+    // boxes inflated by half the pitch tile the y axis, and a black key's extent lies between the centres of its two
+    // white neighbours, so "white slots whose inflated extent overlaps the geom + the blacks next to them" is complete.
+    // (Any other hinge direction: the conservative 2 cm of the first version.)
+    bool ypar = true;
+    double maxmargin = d.has_base ? d.base_gp.margin : 0.0;
+    for (int k = 0; k < RP_NK; k++) {
+      ypar = ypar && fabs(d.key_axis[k][0]) < 1e-12 && fabs(d.key_axis[k][2]) < 1e-12;
+      maxmargin = fmax(maxmargin, d.key_gp[k].margin);
+    }
+    for (int s2 = 0; s2 < 52 && ypar; s2++) {
+      int b = d.black_after[s2];
+      if (b < 0) continue;
+      double lo = ys[d.white_of_slot[s2]], hi = s2 + 1 < 52 ? ys[d.white_of_slot[s2 + 1]] : lo + d.lattice_pitch;
+      if (ys[b] - d.key_half[b][1] < lo || ys[b] + d.key_half[b][1] > hi) ypar = false;
+    }
+    double hand_margin = 0;
+    for (int g = 0; g < m->ngeom; g++) if (m->geom_hand[g] >= 0) hand_margin = fmax(hand_margin, m->geom_margin[g]);
+    // geometric classes for the broadphase tables
+    d.keygeo_ok = 1;
+    bool have[2] = {false, false};
+    for (int k = 0; k < RP_NK; k++) {
+      const int c = d.key_half[k][1] > 0.008 ? 0 : 1;
+      d.key_class[k] = (uint8_t)c;
+      double v[10] = {d.key_jpos[k][0], d.key_jpos[k][1], d.key_jpos[k][2], d.key_half[k][0], d.key_half[k][1], d.key_half[k][2],
+                      d.key_axis[k][0], d.key_axis[k][1], d.key_axis[k][2], d.key_gp[k].margin};
+      if (!have[c]) { memcpy(d.keycls[c], v, sizeof(v)); have[c] = true; }
+      else if (memcmp(d.keycls[c], v, sizeof(v)) != 0) d.keygeo_ok = 0;
+    }
+    d.lattice_slack = ypar ? 0.5 * d.lattice_pitch + fmax(maxmargin, hand_margin) + 1e-9 : 0.02 + fmax(maxmargin, hand_margin);
   }
   // ---------------- actuators on keys (self-actuated piano)
   int nkey_act = 0;

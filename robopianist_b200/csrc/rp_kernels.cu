@@ -120,7 +120,16 @@ constexpr size_t kSmemStride = (sizeof(Smem) + 15) / 16 * 16;  // per-environmen
 // block-shared copy of the sweep schedule (the two hands have the same tree: one copy, checked on the host),
 // placed behind the environment slots of the hands kernels
 struct SweepSched { int off[32]; uint16_t pairs[RP_SW_NPAIRS_SMEM]; };
-constexpr size_t kSchedBytes = (sizeof(SweepSched) + 15) / 16 * 16;
+// block-shared broadphase tables (behind the schedule): per-key position, per-class geometry, the white-key lattice.
+// In global memory every candidate cost two dependent round trips to L2 (slot -> key -> pose).
+struct KeyGeo {
+  double pos[NK][3];
+  double cls[2][10];  // jpos[3], half[3], axis[3], margin
+  unsigned char cls_of[NK];
+  signed char white_of_slot[52], black_after[52];
+};
+constexpr size_t kSchedBytes = (sizeof(SweepSched) + 15) / 16 * 16 + (sizeof(KeyGeo) + 15) / 16 * 16;
+constexpr size_t kGeoOffset = (sizeof(SweepSched) + 15) / 16 * 16;
 
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
 __device__ __forceinline__ double warp_sum(double v) {
@@ -438,11 +447,17 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
   const int bar_id = slot + 1;
   const RpDevModel* __restrict__ dm = a.dm;
   const SweepSched* const sched = reinterpret_cast<const SweepSched*>(smem_raw + (size_t)EPB * kSmemStride);
+  const KeyGeo* const geo = reinterpret_cast<const KeyGeo*>(smem_raw + (size_t)EPB * kSmemStride + kGeoOffset);
   if (HANDS) {  // every thread of the block, before any early exit
     SweepSched* w = reinterpret_cast<SweepSched*>(smem_raw + (size_t)EPB * kSmemStride);
     const int np = dm->sw_off[0][NL];
     for (int i = (int)threadIdx.x; i <= NL; i += KT * EPB) w->off[i] = dm->sw_off[0][i];
     for (int i = (int)threadIdx.x; i < np; i += KT * EPB) w->pairs[i] = dm->sw_pairs[0][i];
+    KeyGeo* g = reinterpret_cast<KeyGeo*>(smem_raw + (size_t)EPB * kSmemStride + kGeoOffset);
+    for (int i = (int)threadIdx.x; i < NK * 3; i += KT * EPB) g->pos[i / 3][i % 3] = dm->key_pos[i / 3][i % 3];
+    for (int i = (int)threadIdx.x; i < 20; i += KT * EPB) g->cls[i / 10][i % 10] = dm->keycls[i / 10][i % 10];
+    for (int i = (int)threadIdx.x; i < NK; i += KT * EPB) g->cls_of[i] = dm->key_class[i];
+    for (int i = (int)threadIdx.x; i < 52; i += KT * EPB) { g->white_of_slot[i] = (signed char)dm->white_of_slot[i]; g->black_after[i] = (signed char)dm->black_after[i]; }
     __syncthreads();
   }
   const int tid = (int)threadIdx.x - slot * KT;
@@ -607,6 +622,16 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       // for every level: anything lane-local that is hoisted out of it is executed once instead of 9 times)
       double hsn = 0, hcs = 1;
       if (hl && ljt != 2) sincos(0.5 * qh, &hsn, &hcs);
+      // the lane's link constants, fetched once in front of the level loop: inside it they were a fresh round trip to
+      // L2 at every level (the model constants live in global memory and the L1 left over by 225 KB of shared memory
+      // does not keep them)
+      double lp[3] = {0, 0, 0}, lq[4] = {1, 0, 0, 0}, jp[3] = {0, 0, 0}, ja[3] = {0, 0, 1};
+      if (hl) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { lp[k] = dm->link_pos[h][lane][k]; jp[k] = dm->link_jpos[h][lane][k]; ja[k] = dm->link_jaxis[h][lane][k]; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) lq[k] = dm->link_quat[h][lane][k];
+      }
       for (int d = 0; d <= maxd; d++) {
         const int src = lpar >= 0 ? lpar : lane;
         double pp[3], pq[4];
@@ -616,10 +641,6 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         for (int k = 0; k < 4; k++) pq[k] = shfl(xq[k], src);
         if (hl && ldep == d) {
           if (lpar < 0) { pp[0] = pp[1] = pp[2] = 0; pq[0] = 1; pq[1] = pq[2] = pq[3] = 0; }
-          double lp[3] = {dm->link_pos[h][lane][0], dm->link_pos[h][lane][1], dm->link_pos[h][lane][2]};
-          double lq[4] = {dm->link_quat[h][lane][0], dm->link_quat[h][lane][1], dm->link_quat[h][lane][2], dm->link_quat[h][lane][3]};
-          double jp[3] = {dm->link_jpos[h][lane][0], dm->link_jpos[h][lane][1], dm->link_jpos[h][lane][2]};
-          double ja[3] = {dm->link_jaxis[h][lane][0], dm->link_jaxis[h][lane][1], dm->link_jaxis[h][lane][2]};
           double pos[3], quat[4], tmp[3];
           rotq(tmp, pq, lp);
           for (int k = 0; k < 3; k++) pos[k] = pp[k] + tmp[k];
@@ -916,92 +937,132 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         gmargin = dm->geom_gp[h][lane].margin;
         rb = rad + half;
         // candidate piano boxes: base + keys whose y-extent overlaps
-        i0 = (int)floor((gc[1] - rb - 0.02 - dm->lattice_y0) / dm->lattice_pitch);
-        i1 = (int)ceil((gc[1] + rb + 0.02 - dm->lattice_y0) / dm->lattice_pitch);
+        // white keys whose y extent (unchanged by the rotation about their y-parallel hinge: lattice_slack is their half
+        // width plus the largest margin; 0.02 m when some hinge is not y-parallel) overlaps the geom's bounding sphere
+        i0 = (int)floor((gc[1] - rb - dm->lattice_slack - dm->lattice_y0) / dm->lattice_pitch);
+        i1 = (int)ceil((gc[1] + rb + dm->lattice_slack - dm->lattice_y0) / dm->lattice_pitch);
         i0 = max(i0, 0); i1 = min(i1, 51);
         ncand = (i1 >= i0) ? 2 * (i1 - i0 + 1) + 1 : 0;
       }
-      // structured, warp-uniform trip count (no continue/break: keeps the warp reconvergent)
+      // Two passes.  Broadphase: every lane walks the candidate boxes of its geom (warp-uniform trip count) and only tests
+      // the bounding sphere against the box in the box's frame; the pairs that pass go to a per-hand list (wbuf is
+      // free between the smooth-acceleration product and the publication of qacc_smooth).  Narrowphase: one lane per
+      // listed pair — the expensive part (segment / box closest point, up to three sphere / box tests) runs once per
+      // 32 pairs instead of once per candidate round in which some lane passed.
+      // Box frame.  Base: axis aligned at base_pos.  Key: the geom sits at the body origin with the body's orientation,
+      // the body is turned by q about the hinge axis a through anchor = key_pos + jpos, so a world point p maps to
+      // Rot(a, -q)(p - anchor) + jpos — one Rodrigues rotation per vector; contacts map back with Rot(a, +q).
+      unsigned short* plist = reinterpret_cast<unsigned short*>(sm.wbuf[h]);  // 128 entries: geom lane | (key + 1) << 8
+      int npair = 0;
       const int ncand_max = __reduce_max_sync(FULL, isg ? ncand : 0);
+      const unsigned ltmask = (1u << lane) - 1u;
+      auto box_frame = [&](int key, const double* gcw, double* c, double* bhalf, double* kax, double* jp, double* anchor,
+                           double& sn, double& cs) -> double {  // returns the box's margin
+        if (key < 0) {
+          for (int k = 0; k < 3; k++) { anchor[k] = dm->base_pos[k]; bhalf[k] = dm->base_half[k]; c[k] = gcw[k] - anchor[k]; kax[k] = k == 2; jp[k] = 0; }
+          sn = 0; cs = 1;
+          return dm->base_gp.margin;
+        }
+        sn = sm.v.pre.ksn[key]; cs = sm.v.pre.kcs[key];
+        double rel[3];
+        // class geometry from the block-shared table (or per key from the model when the classes are not uniform)
+        const double* kc = dm->keygeo_ok ? geo->cls[geo->cls_of[key]] : nullptr;
+        for (int k = 0; k < 3; k++) {
+          kax[k] = kc ? kc[6 + k] : dm->key_axis[key][k]; jp[k] = kc ? kc[k] : dm->key_jpos[key][k];
+          bhalf[k] = kc ? kc[3 + k] : dm->key_half[key][k];
+          anchor[k] = geo->pos[key][k] + jp[k];
+          rel[k] = gcw[k] - anchor[k];
+        }
+        rot_axis(c, kax, -sn, cs, rel);
+        for (int k = 0; k < 3; k++) c[k] += jp[k];
+        return kc ? kc[9] : dm->key_gp[key].margin;
+      };
       for (int ci = -1; ci < ncand_max; ci++) {
         // candidate -> piano box: ci = -1 base; 2k / 2k+1 = white / following black of slot i0+k;
         // last = the black key before the first slot
         int key = -2;
         if (isg && ci < ncand) {
           if (ci < 0) key = dm->has_base ? -1 : -2;
-          else if (ci == ncand - 1) key = i0 > 0 ? dm->black_after[i0 - 1] : -1, key = key < 0 ? -2 : key;
+          else if (ci == ncand - 1) key = i0 > 0 ? geo->black_after[i0 - 1] : -1, key = key < 0 ? -2 : key;
           else {
             const int slot = i0 + (ci >> 1);
-            key = (ci & 1) ? dm->black_after[slot] : dm->white_of_slot[slot];
+            key = (ci & 1) ? geo->black_after[slot] : geo->white_of_slot[slot];
             key = key < 0 ? -2 : key;
           }
         }
+        bool pass = false;
         if (key > -2) {
-          // box pose
-          double bpos[3], bhalf[3], R[9];
-          double margin;
-          if (key < 0) {
-            for (int k = 0; k < 3; k++) { bpos[k] = dm->base_pos[k]; bhalf[k] = dm->base_half[k]; }
-            R[0] = R[4] = R[8] = 1; R[1] = R[2] = R[3] = R[5] = R[6] = R[7] = 0;
-            margin = fmax(gmargin, dm->base_gp.margin);
-          } else {
-            double ax[3] = {dm->key_axis[key][0], dm->key_axis[key][1], dm->key_axis[key][2]};
-            const double sn = sm.v.pre.ksn[key], cs = sm.v.pre.kcs[key];
-            // rotation matrix about axis: columns = rotated basis vectors
-            double ex[3] = {1, 0, 0}, ey[3] = {0, 1, 0}, ez[3] = {0, 0, 1}, cx[3], cy[3], cz[3];
-            rot_axis(cx, ax, sn, cs, ex); rot_axis(cy, ax, sn, cs, ey); rot_axis(cz, ax, sn, cs, ez);
-            R[0] = cx[0]; R[3] = cx[1]; R[6] = cx[2];
-            R[1] = cy[0]; R[4] = cy[1]; R[7] = cy[2];
-            R[2] = cz[0]; R[5] = cz[1]; R[8] = cz[2];
-            double jp[3] = {dm->key_jpos[key][0], dm->key_jpos[key][1], dm->key_jpos[key][2]}, rj[3];
-            rp::mat_vec(rj, R, jp);
-            for (int k = 0; k < 3; k++) { bpos[k] = dm->key_pos[key][k] + jp[k] - rj[k]; bhalf[k] = dm->key_half[key][k]; }
-            margin = fmax(gmargin, dm->key_gp[key].margin);
-          }
-          double rel[3] = {gc[0] - bpos[0], gc[1] - bpos[1], gc[2] - bpos[2]}, c[3];
-          rp::matT_vec(c, R, rel);
+          double c[3], bhalf[3], kax[3], jp[3], anchor[3], sn, cs;
+          const double margin = fmax(gmargin, box_frame(key, gc, c, bhalf, kax, jp, anchor, sn, cs));
           const double bound = rb + margin;
-          if (rp::point_box_d2(c, bhalf) <= bound * bound) {
-            // narrowphase: sphere, or capsule end points + interior closest point
-            int ntest = 1;
-            double pts[3][3];
-            if (gtype == 2) {
-              for (int k = 0; k < 3; k++) { pts[0][k] = c[k]; pts[1][k] = c[k]; pts[2][k] = c[k]; }
-            } else {
-              double ax[3];
-              rp::matT_vec(ax, R, gax);
-              for (int k = 0; k < 3; k++) { pts[0][k] = c[k] - half * ax[k]; pts[1][k] = c[k] + half * ax[k]; pts[2][k] = c[k]; }
-              ntest = 2;
-              const double t = rp::segment_box_closest_t(pts[0], pts[1], bhalf);
-              if (t > 1e-9 && t < 1 - 1e-9) {
-                for (int k = 0; k < 3; k++) pts[2][k] = pts[0][k] + t * (pts[1][k] - pts[0][k]);
-                ntest = 3;
-              }
-            }
+          pass = rp::point_box_d2(c, bhalf) <= bound * bound;
+        }
+        const unsigned pm = __ballot_sync(FULL, pass);
+        if (pass) {
+          const int slot = npair + __popc(pm & ltmask);
+          if (slot < 128) plist[slot] = (unsigned short)(lane | ((key + 1) << 8));
+        }
+        npair += __popc(pm);
+      }
+      if (npair > 128) { npair = 128; sm.overflow = 1; }  // more close pairs than the list holds: reported like a contact overflow
+      __syncwarp();
+      for (int p0 = 0; p0 < npair; p0 += 32) {
+        const bool act = p0 + lane < npair;
+        const unsigned e = act ? plist[p0 + lane] : 0u;
+        const int g = e & 0xff, key = (int)(e >> 8) - 1;
+        // the pair's geom lives in lane g
+        double pgc[3], pgax[3];
 #pragma unroll
-            for (int ti = 0; ti < 3; ti++) {
-              double n[3], p[3];
-              const double dist = rp::sphere_box(pts[ti], rad, bhalf, n, p);
-              if (ti < ntest && dist < margin) {
-                const int slot = atomicAdd(&sm.nraw, 1);
-                if (slot < MAXCON) {
-                  RawContact& rc = sm.u.raw[slot];
-                  double nw[3], pw[3];
-                  rp::mat_vec(nw, R, n);
-                  rp::mat_vec(pw, R, p);
-                  rc.dist = dist;
-                  for (int k = 0; k < 3; k++) { rc.n[k] = nw[k]; rc.pos[k] = bpos[k] + pw[k]; }
-                  rc.hand = h; rc.geom = lane; rc.key = key; rc.sub = ti;
-                  // MuJoCo order: piano geom (base, then keys) major, hand geom (model order) minor
-                  rc.sortkey = (unsigned)(((key + 1) * 64 + gorder) * 4 + ti);
-                } else {
-                  sm.overflow = 1;
+        for (int k = 0; k < 3; k++) { pgc[k] = shfl(gc[k], g); pgax[k] = shfl(gax[k], g); }
+        const double prad = shfl(rad, g), phalf = shfl(half, g), pgmargin = shfl(gmargin, g);
+        const int pgtype = __shfl_sync(FULL, gtype, g), pgorder = __shfl_sync(FULL, gorder, g);
+        if (act) {
+          double c[3], bhalf[3], kax[3], jp[3], anchor[3], sn, cs;
+          const double margin = fmax(pgmargin, box_frame(key, pgc, c, bhalf, kax, jp, anchor, sn, cs));
+          const bool iskey = key >= 0;
+          // narrowphase: sphere, or capsule end points + interior closest point
+          int ntest = 1;
+          double pts[3][3];
+          if (pgtype == 2) {
+            for (int k = 0; k < 3; k++) { pts[0][k] = c[k]; pts[1][k] = c[k]; pts[2][k] = c[k]; }
+          } else {
+            double ax[3] = {pgax[0], pgax[1], pgax[2]};
+            if (iskey) rot_axis(ax, kax, -sn, cs, pgax);
+            for (int k = 0; k < 3; k++) { pts[0][k] = c[k] - phalf * ax[k]; pts[1][k] = c[k] + phalf * ax[k]; pts[2][k] = c[k]; }
+            ntest = 2;
+            const double t = rp::segment_box_closest_t(pts[0], pts[1], bhalf);
+            if (t > 1e-9 && t < 1 - 1e-9) {
+              for (int k = 0; k < 3; k++) pts[2][k] = pts[0][k] + t * (pts[1][k] - pts[0][k]);
+              ntest = 3;
+            }
+          }
+#pragma unroll 1
+          for (int ti = 0; ti < ntest; ti++) {
+            double n[3], p[3];
+            const double dist = rp::sphere_box(pts[ti], prad, bhalf, n, p);
+            if (dist < margin) {
+              const int slot = atomicAdd(&sm.nraw, 1);
+              if (slot < MAXCON) {
+                RawContact& rc = sm.u.raw[slot];
+                double nw[3] = {n[0], n[1], n[2]}, pw[3] = {p[0], p[1], p[2]};
+                if (iskey) {
+                  double pr[3] = {p[0] - jp[0], p[1] - jp[1], p[2] - jp[2]};
+                  rot_axis(nw, kax, sn, cs, n);
+                  rot_axis(pw, kax, sn, cs, pr);
                 }
+                rc.dist = dist;
+                for (int k = 0; k < 3; k++) { rc.n[k] = nw[k]; rc.pos[k] = anchor[k] + pw[k]; }
+                rc.hand = h; rc.geom = g; rc.key = key; rc.sub = ti;
+                // MuJoCo order: piano geom (base, then keys) major, hand geom (model order) minor
+                rc.sortkey = (unsigned)(((key + 1) * 64 + pgorder) * 4 + ti);
+              } else {
+                sm.overflow = 1;
               }
             }
           }
         }
       }
+      __syncwarp();
     }
     if (HANDS) {
       // colliders outside the narrowphase's coverage (palm / knuckle / wrist boxes and cylinders, forearm): if the
@@ -1041,7 +1102,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     env_sync<NW, EPB>(bar_id);
     TICK(4)
     const int nraw = min(sm.nraw, MAXCON);
-    if (sm.nraw > MAXCON) flags |= 1;
+    if (sm.nraw > MAXCON || sm.overflow) flags |= 1;
     // NOTE: on overflow the kept subset depends on atomic order; the flag marks the env invalid.
     const int ncon = nraw;
     ncon_last = ncon;
@@ -1079,17 +1140,20 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         dep = sm.dep[ch][link];
         const double* dir = c_frame + 3 * r;
         const double* Ac = sm.A[ch];
+        // chain of the contact's link (dof at depth d), once, into registers: the loops below index shared memory
+        // through it and are fully unrolled (an index load in front of every element made this stage the longest
+        // serial chain of the contact rows: depth^2 dependent load pairs per row)
+        int cidx[MAXD];
+#pragma unroll
+        for (int d = 0; d < MAXD; d++) cidx[d] = sm.anc[ch][link][d <= dep ? d : dep];
         // Jacobian row: frame direction r, body2 (key) minus body1 (hand link)
         double jrow[MAXD];
-#pragma unroll 1
+#pragma unroll
         for (int d = 0; d < MAXD; d++) {
-          double v = 0;
-          if (d <= dep) {
-            const double* S = sm.v.pre.S[ch][sm.anc[ch][link][d]];
-            double wxp[3];
-            rp::cross3(wxp, S, c_pos);
-            v = -(dir[0] * (S[3] + wxp[0]) + dir[1] * (S[4] + wxp[1]) + dir[2] * (S[5] + wxp[2]));
-          }
+          const double* S = sm.v.pre.S[ch][cidx[d]];
+          double wxp[3];
+          rp::cross3(wxp, S, c_pos);
+          const double v = d <= dep ? -(dir[0] * (S[3] + wxp[0]) + dir[1] * (S[4] + wxp[1]) + dir[2] * (S[5] + wxp[2])) : 0.0;
           jrow[d] = v;
           cn.Jc[r][d] = v;
         }
@@ -1120,21 +1184,36 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         mu_row = mu;
         // row velocity -> reference acceleration
         double sv = 0;
-        for (int d = 0; d <= dep; d++) sv += jrow[d] * sm.v.pre.vh[ch][sm.anc[ch][link][d]];
+#pragma unroll
+        for (int d = 0; d < MAXD; d++) sv += jrow[d] * sm.v.pre.vh[ch][cidx[d]];  // jrow is zero beyond the chain
         if (c_key >= 0) sv += jk * sm.v.pre.vk[c_key];
         arefr = r == 0 ? -B * sv - K * imp * (c_dist - incl) : -B * sv;
         // u = Minv_chain Jc_r^T (kept in registers for the A block)
-#pragma unroll 1
-        for (int d = 0; d <= dep; d++) {
-          const int jd = sm.anc[ch][link][d];
+#pragma unroll
+        for (int d = 0; d < MAXD; d++) {
+          const double* rowd = Ac + cidx[d] * RS;
           double s2 = 0;
-          for (int e = 0; e <= dep; e++) s2 -= Ac[jd * RS + sm.anc[ch][link][e]] * jrow[e];
+#pragma unroll
+          for (int e = 0; e < MAXD; e++) s2 -= rowd[cidx[e]] * jrow[e];
           u[d] = s2;
+        }
+        // b = J qacc_smooth - aref; jar = J qacc_warmstart - aref (parked in f[] for the primal map)
+        {
+          double s2 = 0, s3 = 0;
+#pragma unroll
+          for (int d = 0; d < MAXD; d++) {
+            s2 += jrow[d] * sm.wbuf[ch][cidx[d]];
+            s3 += jrow[d] * sm.v.pre.wsb[ch][cidx[d]];
+          }
+          if (c_key >= 0) { s2 += jk * sm.vak[c_key]; s3 += jk * sm.kfc[c_key]; }
+          cn.b[r] = s2 - arefr;
+          cn.f[r] = s3 - arefr;
         }
         if (r == 0) {
           cn.hand = ch; cn.link = link; cn.key = c_key; cn.mu = mu;
           cn.invMk = c_key >= 0 ? 1.0 / dm->key_M[c_key] : 0.0;
-          for (int d = 0; d < 16; d++) cn.chain[d] = (signed char)(d <= dep ? sm.anc[ch][link][d] : 0);
+#pragma unroll
+          for (int d = 0; d < 16; d++) cn.chain[d] = (signed char)(d < MAXD && d <= dep ? cidx[d < MAXD ? d : 0] : 0);
         }
       }
       env_sync<NW, EPB>(bar_id);
@@ -1148,16 +1227,6 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
           if (r == s2) v += cn.R[r];
           cn.A[3 * s2 + r] = v;
         }
-        // b = J qacc_smooth - aref; jar = J qacc_warmstart - aref (parked in f[] for the primal map)
-        double s2 = 0, s3 = 0;
-        for (int d = 0; d <= dep; d++) {
-          const int j = sm.anc[ch][link][d];
-          s2 += cn.Jc[r][d] * sm.wbuf[ch][j];
-          s3 += cn.Jc[r][d] * sm.v.pre.wsb[ch][j];
-        }
-        if (c_key >= 0) { s2 += cn.Jk[r] * sm.vak[c_key]; s3 += cn.Jk[r] * sm.kfc[c_key]; }
-        cn.b[r] = s2 - arefr;
-        cn.f[r] = s3 - arefr;
       }
       env_sync<NW, EPB>(bar_id);
       if (rowt && r == 0) {
@@ -1232,8 +1301,8 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
           const Contact& cn = sm.u.con[c];
           const int dep = cn.dep & 0xff;
           double u0 = 0, u1 = 0, u2 = 0;
-#pragma unroll 1
-          for (int d = 0; d <= dep; d++) {
+#pragma unroll
+          for (int d = 0; d < MAXD; d++) {  // Jc is zero beyond the chain, chain[] repeats dof 0 there
             const double m = Ah[cn.chain[d] * RS + lc];
             u0 -= m * cn.Jc[0][d]; u1 -= m * cn.Jc[1][d]; u2 -= m * cn.Jc[2][d];
           }

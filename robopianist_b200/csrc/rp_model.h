@@ -103,7 +103,12 @@ struct RpDevModel {
   int obs_dim, act_dim;
   double energy_coef;
   // white-key lattice for the broadphase
-  double lattice_y0, lattice_pitch;
+  double lattice_y0, lattice_pitch, lattice_slack;
+  // keys come in two geometric classes (white / black): joint anchor, half sizes, hinge axis and margin are shared inside a
+  // class (checked on the host: keygeo_ok), only the position differs — the broadphase keeps these in shared memory
+  int keygeo_ok, pad4;
+  uint8_t key_class[RP_NK];
+  double keycls[2][10];   // jpos[3], half[3], axis[3], margin
   int white_of_slot[52];   // key number of the i-th white key
   int black_after[52];     // key number of the black key on the boundary after white i, -1 none
 };
