@@ -276,7 +276,8 @@ __device__ __noinline__ int pgs_solve(Smem* smp, const int h, const int bar_id, 
     // committed a change of exactly zero at their turn, so the iterates are those of the row-by-row sweep.  (A plain
     // row-by-row loop for sweeps in which most rows change — a hand at rest, nothing saturated — was measured and is
     // slower at every switch-over threshold: 18.2 ms per step always on, 14.83 never, r02g; fetching the column of the
-    // most likely next row one commit ahead changed nothing, r02p.)
+    // most likely next row one commit ahead changed nothing, r02p; a fixed-order sweep that broadcasts the unclamped change
+    // first and redoes the rare clamped row — a shorter dependency chain on paper — is slower as well, r02x.)
     {
       const double fbase = fr_b + fr_R * fr_f;  // f only changes at the lane's own commit
       double res = fbase + va;
