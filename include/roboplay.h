@@ -176,6 +176,16 @@ int rp_get_midi(rp_batch *, uint32_t *events, int32_t *counts);
  * the model.  Call rp_reset afterwards: running episodes are not re-indexed. */
 int rp_set_song(rp_batch *, const uint8_t *goal, const int8_t *fingering, int n_steps);
 
+/* randomize_hand_positions (robopianist/suite/tasks/piano_with_shadow_hands.py:64,491-499; the shift itself is
+ * dm_control's Entity.shift_pose on the hands' attachment frames): from the next reset on, every episode start shifts
+ * both hands along y by one draw from U(-0.05, 0.05) m per environment; like the reference (model not recompiled
+ * between episodes, suite/__init__.py:56) the shifts accumulate.  One splitmix64 stream per environment seeded from
+ * (seed, environment index).  enable = 0 switches it off and clears the offsets; enable = 2 draws every episode's shift
+ * from the unshifted pose (suite.load(recompile_physics=True)).  rp_get_hand_offsets: current
+ * offsets [N] into a host buffer. */
+int rp_randomize_hand_positions(rp_batch *, int enable, uint64_t seed);
+int rp_get_hand_offsets(rp_batch *, double *offsets_host);
+
 /* Launch shape of the step kernel (results do not depend on it): environments per thread block, 1 or
  * RP_BLOCK_ENVS (blocks whose environments run each substep in step with each other, which shares their
  * instruction fetches); 0 = chosen from the batch size (default). */

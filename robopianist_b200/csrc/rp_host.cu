@@ -28,6 +28,8 @@ struct rp_model {
   std::vector<uint8_t> goal;
   std::vector<int8_t> fingering;
   int nv, nu, nhand, obs_dim, act_dim;
+  int nl;      // dofs per hand of the flat model (<= RP_NL; the device layout pads every hand to RP_NL dofs)
+  int nv_dev;  // row length of the device state arrays: RP_NK + nhand * RP_NL
 };
 
 struct rp_batch {
@@ -46,6 +48,9 @@ struct rp_batch {
   double* ot_scratch;     // [N][RP_OT_SCRATCH_DOUBLES], only for tasks with the optimal-transport fingering reward
   int32_t* midi_count;
   int midi_cap;
+  double* hand_offset;    // [N] accumulated attachment offset of the hands (rp_randomize_hand_positions)
+  uint64_t* rng_state;    // [N] generator state of the offset draws
+  int hand_offset_fresh;  // offsets do not accumulate over episodes (the reference with recompile_physics=True)
   // staging for rp_step_host
   double *h_action, *h_out;  // pinned
   double *d_action, *d_out;
@@ -69,11 +74,116 @@ static void copy_gp(RpGeomParams& gp, const rp_flat_model* m, int g) {
   gp.pad = 0;
 }
 
+// ---- host-side helpers of the hand packer -------------------------------------------------------------------------
+static void quat_mul_h(const double* a, const double* b, double* o) {
+  o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  o[2] = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  o[3] = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+}
+struct Pose { double p[3], q[4]; };
+// pose of body b in the frame of its ancestor body a (a = 0: world); every body strictly between must be jointless
+static bool pose_in_ancestor(const rp_flat_model* m, int b, int a, Pose* out) {
+  Pose t;
+  for (int c = 0; c < 3; c++) t.p[c] = m->body_pos[3 * b + c];
+  for (int c = 0; c < 4; c++) t.q[c] = m->body_quat[4 * b + c];
+  int p = m->body_parentid[b];
+  while (p != a) {
+    if (p <= 0 || m->body_dofnum[p] != 0) return false;
+    double R[9], r[3], q2[4];
+    rp::quat2mat(R, m->body_quat + 4 * p);
+    rp::mat_vec(r, R, t.p);
+    for (int c = 0; c < 3; c++) t.p[c] = m->body_pos[3 * p + c] + r[c];
+    quat_mul_h(m->body_quat + 4 * p, t.q, q2);
+    for (int c = 0; c < 4; c++) t.q[c] = q2[c];
+    p = m->body_parentid[p];
+  }
+  *out = t;
+  return true;
+}
+// nearest ancestor-or-self with joints (0: none below the world), and the pose of b in that body's frame
+static int jointed_ancestor(const rp_flat_model* m, int b, Pose* rel) {
+  int a = b;
+  while (a > 0 && m->body_dofnum[a] == 0) a = m->body_parentid[a];
+  if (a == b) { rel->p[0] = rel->p[1] = rel->p[2] = 0; rel->q[0] = 1; rel->q[1] = rel->q[2] = rel->q[3] = 0; return a; }
+  if (!pose_in_ancestor(m, b, a, rel)) return -1;
+  return a;
+}
+// eigen-decomposition of a symmetric 3x3 matrix (cyclic Jacobi): A = V diag(w) V^T, V a proper rotation
+static void sym_eig3(const double* Ain, double* w, double* V) {
+  double A[9];
+  for (int i = 0; i < 9; i++) { A[i] = Ain[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 64; sweep++) {
+    double off = fabs(A[1]) + fabs(A[2]) + fabs(A[5]);
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++) {
+        if (fabs(A[3 * p + q]) < 1e-300) continue;
+        double theta = (A[3 * q + q] - A[3 * p + p]) / (2 * A[3 * p + q]);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+        double c = 1 / sqrt(t * t + 1), sn = t * c;
+        for (int k = 0; k < 3; k++) {  // A <- A J
+          double akp = A[3 * k + p], akq = A[3 * k + q];
+          A[3 * k + p] = c * akp - sn * akq; A[3 * k + q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < 3; k++) {  // A <- J^T A
+          double apk = A[3 * p + k], aqk = A[3 * q + k];
+          A[3 * p + k] = c * apk - sn * aqk; A[3 * q + k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; k++) {
+          double vkp = V[3 * k + p], vkq = V[3 * k + q];
+          V[3 * k + p] = c * vkp - sn * vkq; V[3 * k + q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  for (int i = 0; i < 3; i++) w[i] = A[4 * i];
+  double det = V[0] * (V[4] * V[8] - V[5] * V[7]) - V[1] * (V[3] * V[8] - V[5] * V[6]) + V[2] * (V[3] * V[7] - V[4] * V[6]);
+  if (det < 0) for (int k = 0; k < 3; k++) V[3 * k + 2] = -V[3 * k + 2];
+}
+static void mat_to_quat(const double* R, double* q) {  // proper rotation, row major
+  double tr = R[0] + R[4] + R[8];
+  if (tr > 0) { double s = sqrt(tr + 1.0) * 2; q[0] = 0.25 * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s; }
+  else if (R[0] > R[4] && R[0] > R[8]) { double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2; q[0] = (R[7] - R[5]) / s; q[1] = 0.25 * s; q[2] = (R[1] + R[3]) / s; q[3] = (R[2] + R[6]) / s; }
+  else if (R[4] > R[8]) { double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2; q[0] = (R[2] - R[6]) / s; q[1] = (R[1] + R[3]) / s; q[2] = 0.25 * s; q[3] = (R[5] + R[7]) / s; }
+  else { double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2; q[0] = (R[3] - R[1]) / s; q[1] = (R[2] + R[6]) / s; q[2] = (R[5] + R[7]) / s; q[3] = 0.25 * s; }
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int k = 0; k < 4; k++) q[k] /= n;
+}
+// One link's inertial from several rigidly attached bodies, each given in the link frame (mass, com, frame quaternion,
+// principal moments): total mass, centre of mass, principal axes of the summed tensor about it.
+struct Inertial { double mass, pos[3], quat[4], diag[3]; };
+static Inertial merge_inertials(const std::vector<Inertial>& parts) {
+  Inertial o;
+  memset(&o, 0, sizeof(o));
+  o.quat[0] = 1;
+  for (const Inertial& p : parts) { o.mass += p.mass; for (int c = 0; c < 3; c++) o.pos[c] += p.mass * p.pos[c]; }
+  if (o.mass <= 0) { for (int c = 0; c < 3; c++) o.pos[c] = 0; return o; }
+  for (int c = 0; c < 3; c++) o.pos[c] /= o.mass;
+  double I[9] = {0};
+  for (const Inertial& p : parts) {
+    double R[9];
+    rp::quat2mat(R, p.quat);
+    double d[3] = {p.pos[0] - o.pos[0], p.pos[1] - o.pos[1], p.pos[2] - o.pos[2]}, d2 = rp::dot3(d, d);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double v = 0;
+        for (int k = 0; k < 3; k++) v += R[3 * i + k] * p.diag[k] * R[3 * j + k];
+        I[3 * i + j] += v + p.mass * ((i == j ? d2 : 0.0) - d[i] * d[j]);
+      }
+  }
+  double V[9];
+  sym_eig3(I, o.diag, V);
+  mat_to_quat(V, o.quat);
+  return o;
+}
+
 extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task) {
   if (!m || !task) { fail("null model/task"); return nullptr; }
   if (m->nkey != RP_NK) { fail("model must have 88 keys"); return nullptr; }
   if (m->nhand != 0 && m->nhand != 2) { fail("nhand must be 0 or 2"); return nullptr; }
-  if (m->nv != RP_NK + m->nhand * RP_NL) { fail("unexpected nv (need 88 + nhand*26)"); return nullptr; }
+  const int nl = m->nhand ? m->nobsdof : 0;  // every hand dof is listed once in hand_obs_dofid (joints_pos)
+  if (nl < 0 || nl > RP_NL) { fail("a hand may have at most 26 dofs"); return nullptr; }
+  if (m->nv != RP_NK + m->nhand * nl) { fail("unexpected nv (need 88 + nhand * dofs per hand)"); return nullptr; }
   if (!task->goal || !task->fingering) { fail("task goal / fingering tables must not be null"); return nullptr; }
   if (task->n_steps < 1) { fail("task n_steps must be >= 1"); return nullptr; }
   if (task->n_steps_lookahead < 0 || task->n_steps_lookahead > 1024) { fail("task n_steps_lookahead out of range [0, 1024]"); return nullptr; }
@@ -197,23 +307,30 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
   if (nkey_act != 0 && nkey_act != RP_NK) return bad("either all or no keys may be actuated");
   d.nkey_act = nkey_act;
   // ---------------- hands
+  // Every hand occupies RP_NL link slots on the device (lane == link == dof).  A hand of the flat model may have fewer
+  // dofs (reduced action space, fewer forearm dofs: shadow_hand.py:162-182,272-311): the unused slots become inert
+  // one-dof dummies (unit inertia, no forces, never observed).  Bodies without joints are fused into the link of
+  // their nearest jointed ancestor — geoms, sites and inertia re-expressed in that body's frame; MuJoCo keeps them as
+  // separate bodies, which is the same rigid body up to rounding.
   int nact_hand = m->nhand ? (m->nu - nkey_act) / m->nhand : 0;
   int order = 0;
+  d.nobs[0] = d.nobs[1] = nl;
   for (int h = 0; h < m->nhand; h++) {
-    int base = RP_NK + h * RP_NL;
+    int base = RP_NK + h * nl;
     int maxdepth = 0;
-    for (int l = 0; l < RP_NL; l++) {
+    std::vector<std::vector<Inertial>> parts(RP_NL);
+    std::vector<double> link_gc(RP_NL, -1.0);
+    for (int l = 0; l < nl; l++) {
       int j = base + l, b = m->jnt_bodyid[j];
-      bool first = m->body_dofadr[b] == j, last = (m->body_dofadr[b] + m->body_dofnum[b] - 1) == j;
+      bool first = m->body_dofadr[b] == j;
       int parent;
       if (first) {
         int pj = m->dof_parentid[j];
         parent = pj < 0 ? -1 : pj - base;
-        int pb = m->body_parentid[b];
-        if (pj < 0 && pb != 0) return bad("hand root body must hang off the world");
-        if (pj >= 0 && m->jnt_bodyid[pj] != pb) return bad("hand bodies without joints are not supported");
-        for (int c = 0; c < 3; c++) d.link_pos[h][l][c] = m->body_pos[3 * b + c];
-        for (int c = 0; c < 4; c++) d.link_quat[h][l][c] = m->body_quat[4 * b + c];
+        Pose rel;
+        if (!pose_in_ancestor(m, b, pj < 0 ? 0 : m->jnt_bodyid[pj], &rel)) return bad("hand body tree: a jointed body must descend from the body of its parent dof through jointless bodies only");
+        for (int c = 0; c < 3; c++) d.link_pos[h][l][c] = rel.p[c];
+        for (int c = 0; c < 4; c++) d.link_quat[h][l][c] = rel.q[c];
       } else {
         parent = l - 1;
         d.link_quat[h][l][0] = 1;
@@ -230,12 +347,6 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
       d.link_limited[h][l] = m->jnt_limited[j];
       for (int c = 0; c < 3; c++) { d.link_jpos[h][l][c] = m->jnt_pos[3 * j + c]; d.link_jaxis[h][l][c] = m->jnt_axis[3 * j + c]; }
       d.link_iquat[h][l][0] = 1;
-      if (last) {
-        for (int c = 0; c < 3; c++) { d.link_ipos[h][l][c] = m->body_ipos[3 * b + c]; d.link_inertia[h][l][c] = m->body_inertia[3 * b + c]; }
-        for (int c = 0; c < 4; c++) d.link_iquat[h][l][c] = m->body_iquat[4 * b + c];
-        d.link_mass[h][l] = m->body_mass[b];
-        d.link_gravcomp[h][l] = m->body_gravcomp[b];
-      }
       d.link_body_invw[h][l] = m->body_invweight0[2 * b];
       d.link_damping[h][l] = m->dof_damping[j]; d.link_armature[h][l] = m->dof_armature[j];
       d.link_frictionloss[h][l] = m->dof_frictionloss[j];
@@ -248,6 +359,54 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
       d.link_fr_R[h][l] = fmax(RP_MINVAL, (1 - imp) * m->dof_invweight0[j] / imp);
       rp::ref_KB(m->dof_solref + 2 * j, m->dof_solimp[5 * j + 1], m->timestep, &K, &d.link_fr_B[h][l]);
       d.dof_act[h][l] = -1;
+    }
+    for (int l = nl; l < RP_NL; l++) {  // inert padding links
+      d.link_parent[h][l] = -1; d.link_depth[h][l] = 0;
+      for (int dd = 0; dd < RP_MAXD; dd++) d.link_anc[h][l][dd] = -1;
+      d.link_anc[h][l][0] = l;
+      d.link_jtype[h][l] = 3; d.link_jaxis[h][l][2] = 1;
+      d.link_quat[h][l][0] = 1; d.link_iquat[h][l][0] = 1;
+      d.link_armature[h][l] = 1.0; d.link_dof_invw[h][l] = 1.0; d.link_body_invw[h][l] = 1.0; d.link_fr_R[h][l] = 1.0;
+      d.dof_act[h][l] = -1;
+    }
+    // link of every hand body (-1: rigidly attached to the world) and its pose in that link's body frame
+    auto body_link = [&](int b, Pose* rel) -> int {
+      int a = jointed_ancestor(m, b, rel);
+      if (a <= 0) return -1;
+      return m->body_dofadr[a] + m->body_dofnum[a] - 1 - base;
+    };
+    // inertials: the link's own body plus the jointless bodies hanging off it
+    for (int b = 1; b < m->nbody; b++) {
+      int jb = b;
+      while (jb > 0 && m->body_dofnum[jb] == 0) jb = m->body_parentid[jb];
+      if (jb <= 0 || m->body_dofadr[jb] < base || m->body_dofadr[jb] >= base + nl) continue;  // not a (moving) body of this hand
+      Pose rel;
+      int l = body_link(b, &rel);
+      if (l < 0 || l >= nl) return bad("hand body outside its hand's dof range");
+      Inertial in;
+      in.mass = m->body_mass[b];
+      double R[9], r[3];
+      rp::quat2mat(R, rel.q);
+      rp::mat_vec(r, R, m->body_ipos + 3 * b);
+      for (int c = 0; c < 3; c++) { in.pos[c] = rel.p[c] + r[c]; in.diag[c] = m->body_inertia[3 * b + c]; }
+      quat_mul_h(rel.q, m->body_iquat + 4 * b, in.quat);
+      if (b == jb) {  // the jointed body itself: kept verbatim when nothing is fused into it
+        for (int c = 0; c < 3; c++) in.pos[c] = m->body_ipos[3 * b + c];
+        for (int c = 0; c < 4; c++) in.quat[c] = m->body_iquat[4 * b + c];
+        parts[l].insert(parts[l].begin(), in);
+      } else if (in.mass > 0) {
+        parts[l].push_back(in);
+      }
+      if (link_gc[l] >= 0 && link_gc[l] != m->body_gravcomp[b] && in.mass > 0) return bad("bodies fused into one link must share their gravcomp");
+      if (in.mass > 0 || b == jb) link_gc[l] = m->body_gravcomp[b];
+    }
+    for (int l = 0; l < nl; l++) {
+      if (parts[l].empty()) continue;  // all but the last dof of a multi-dof body: massless
+      Inertial in = parts[l].size() == 1 ? parts[l][0] : merge_inertials(parts[l]);
+      for (int c = 0; c < 3; c++) { d.link_ipos[h][l][c] = in.pos[c]; d.link_inertia[h][l][c] = in.diag[c]; }
+      for (int c = 0; c < 4; c++) d.link_iquat[h][l][c] = in.quat[c];
+      d.link_mass[h][l] = in.mass;
+      d.link_gravcomp[h][l] = link_gc[l] < 0 ? 0.0 : link_gc[l];
     }
     d.maxdepth[h] = maxdepth;
     // subtree sizes, sibling ranks
@@ -298,9 +457,9 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
         if (m->tendon_num[t] != 2) return bad("only two-joint fixed tendons are supported");
         d0 = m->wrap_dofid[m->tendon_adr[t]] - base; d1 = m->wrap_dofid[m->tendon_adr[t] + 1] - base;
         c0 = gear * m->wrap_coef[m->tendon_adr[t]]; c1 = gear * m->wrap_coef[m->tendon_adr[t] + 1];
-        if (d1 < 0 || d1 >= RP_NL) return bad("actuator does not belong to its hand");
+        if (d1 < 0 || d1 >= nl) return bad("actuator does not belong to its hand");
       }
-      if (d0 < 0 || d0 >= RP_NL) return bad("actuator does not belong to its hand (hand actuators must be contiguous)");
+      if (d0 < 0 || d0 >= nl) return bad("actuator does not belong to its hand (hand actuators must be contiguous)");
       d.act_dof0[h][ai] = d0; d.act_dof1[h][ai] = d1; d.act_coef0[h][ai] = c0; d.act_coef1[h][ai] = c1;
       d.act_gain[h][ai] = m->actuator_gainprm[a];
       for (int c = 0; c < 3; c++) d.act_bias[h][ai][c] = m->actuator_biasprm[3 * a + c];
@@ -316,13 +475,20 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
       if (m->geom_hand[g] != h || !m->geom_collide[g]) continue;
       if (ng >= RP_NGH) return bad("too many colliding hand geoms");
       int b = m->geom_bodyid[g];
-      int l = m->body_dofadr[b] + m->body_dofnum[b] - 1 - base;
+      Pose rel;
+      int l = body_link(b, &rel);
+      if (l < 0 || l >= nl) return bad("a colliding hand geom sits on a body that is welded to the world");
       if (m->geom_type[g] != 2 && m->geom_type[g] != 3) return bad("only sphere/capsule hand colliders are supported");
       d.geom_link[h][ng] = l; d.geom_type[h][ng] = m->geom_type[g]; d.geom_order[h][ng] = order++;
-      double R[9];
+      double R[9], Rb[9], r[3], ax[3];
       quat_to_mat(m->geom_quat + 4 * g, R);
-      for (int c = 0; c < 3; c++) { d.geom_pos[h][ng][c] = m->geom_pos[3 * g + c]; d.geom_axis[h][ng][c] = R[3 * c + 2]; }
+      rp::quat2mat(Rb, rel.q);
+      rp::mat_vec(r, Rb, m->geom_pos + 3 * g);
+      double axl[3] = {R[2], R[5], R[8]};
+      rp::mat_vec(ax, Rb, axl);
+      for (int c = 0; c < 3; c++) { d.geom_pos[h][ng][c] = rel.p[c] + r[c]; d.geom_axis[h][ng][c] = ax[c]; }
       d.geom_size[h][ng][0] = m->geom_size[3 * g]; d.geom_size[h][ng][1] = m->geom_size[3 * g + 1];
+      d.geom_body_invw[h][ng] = m->body_invweight0[2 * b];  // of the geom's own body (a fused body keeps its own value)
       copy_gp(d.geom_gp[h][ng], m, g);
       ng++;
     }
@@ -331,12 +497,20 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
     int ni = 0;
     for (int g = 0; g < m->ngeom; g++) {
       if (m->geom_hand[g] != h || m->geom_collide[g] || !(m->geom_contype[g] | m->geom_conaffinity[g])) continue;
-      if (ni >= RP_NIGN) return bad("too many uncovered hand colliders");
       int b = m->geom_bodyid[g];
-      d.ign_link[h][ni] = m->body_dofadr[b] + m->body_dofnum[b] - 1 - base;
-      for (int c = 0; c < 3; c++) d.ign_pos[h][ni][c] = m->geom_pos[3 * g + c];
+      Pose rel;
+      int l = body_link(b, &rel);
+      if (l < 0) continue;  // welded to the world (a forearm without dofs): its clearance never changes
+      if (ni >= RP_NIGN) return bad("too many uncovered hand colliders");
+      d.ign_link[h][ni] = l;
+      double Rb[9], Rg[9], r[3];
+      rp::quat2mat(Rb, rel.q);
+      rp::mat_vec(r, Rb, m->geom_pos + 3 * g);
+      for (int c = 0; c < 3; c++) d.ign_pos[h][ni][c] = rel.p[c] + r[c];
       const double* sz = m->geom_size + 3 * g;
-      quat_to_mat(m->geom_quat + 4 * g, d.ign_mat[h][ni]);
+      quat_to_mat(m->geom_quat + 4 * g, Rg);
+      for (int i = 0; i < 3; i++)
+        for (int k = 0; k < 3; k++) d.ign_mat[h][ni][3 * i + k] = Rb[3 * i] * Rg[k] + Rb[3 * i + 1] * Rg[3 + k] + Rb[3 * i + 2] * Rg[6 + k];
       if (m->geom_type[g] == 5) { d.ign_half[h][ni][0] = d.ign_half[h][ni][1] = sz[0]; d.ign_half[h][ni][2] = sz[1]; }  // cylinder: radius, half height
       else for (int c = 0; c < 3; c++) d.ign_half[h][ni][c] = sz[c];                                                    // box / mesh bounding box
       ni++;
@@ -345,11 +519,20 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
     if (m->nsite != 2 * RP_NSITE) return bad("expected 5 fingertip sites per hand");
     for (int s = 0; s < RP_NSITE; s++) {
       int si = h * RP_NSITE + s, b = m->site_bodyid[si];
-      d.site_link[h][s] = m->body_dofadr[b] + m->body_dofnum[b] - 1 - base;
-      for (int c = 0; c < 3; c++) d.site_pos[h][s][c] = m->site_pos[3 * si + c];
+      Pose rel;
+      int l = body_link(b, &rel);
+      if (l < 0 || l >= nl) return bad("fingertip site on a body welded to the world");
+      d.site_link[h][s] = l;
+      double Rb[9], r[3];
+      rp::quat2mat(Rb, rel.q);
+      rp::mat_vec(r, Rb, m->site_pos + 3 * si);
+      for (int c = 0; c < 3; c++) d.site_pos[h][s][c] = rel.p[c] + r[c];
     }
-    if (m->nobsdof != RP_NL) return bad("hand_obs_dofid must list 26 dofs per hand");
-    for (int l = 0; l < RP_NL; l++) d.obs_dof[h][l] = m->hand_obs_dofid[h * RP_NL + l] - base;
+    for (int l = 0; l < nl; l++) {
+      int od = m->hand_obs_dofid[h * nl + l] - base;
+      if (od < 0 || od >= nl) return bad("hand_obs_dofid outside the hand's dof range");
+      d.obs_dof[h][l] = od;
+    }
   }
   d.nhandgeom_total = order;
   if (order > 64) return bad("too many hand geoms for the contact sort key");
@@ -374,7 +557,7 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
   d.energy_coef = task->energy_penalty_coef;
   if (task->kind == 0) {
     if (m->nhand != 2) return bad("piano_with_shadow_hands needs two hands");
-    d.obs_dim = RP_NK + 1 + 2 * RP_NL + (d.lookahead + 1) * RP_GOAL_DIM + (d.disable_fingering_reward ? 0 : 10);
+    d.obs_dim = RP_NK + 1 + 2 * nl + (d.lookahead + 1) * RP_GOAL_DIM + (d.disable_fingering_reward ? 0 : 10);
   } else {
     if (nkey_act != RP_NK) return bad("self_actuated_piano needs key actuators");
     d.obs_dim = RP_NK + 1 + (d.lookahead + 1) * RP_GOAL_DIM;
@@ -384,6 +567,7 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
   M->goal.assign(task->goal, task->goal + (size_t)d.T * RP_GOAL_DIM);
   M->fingering.assign(task->fingering, task->fingering + (size_t)d.T * RP_NK);
   M->nv = m->nv; M->nu = m->nu; M->nhand = m->nhand; M->obs_dim = d.obs_dim; M->act_dim = d.act_dim;
+  M->nl = nl; M->nv_dev = RP_NK + m->nhand * RP_NL;
   return M;
 }
 
@@ -414,7 +598,7 @@ extern "C" rp_batch* rp_batch_create(const rp_model* model, int nenv, int device
   memset(b, 0, sizeof(*b));
   b->model = model; b->nenv = nenv; b->device = device; b->stream = (cudaStream_t)cuda_stream;
   b->iterations = -1; b->tolerance = -1.0;
-  size_t N = nenv, nv = model->nv, nu = model->nu;
+  size_t N = nenv, nv = model->nv_dev, nu = model->nu;
   cudaError_t e = cudaSuccess;
   // every allocation is skipped once one has failed (a batch too large for the device must not go on to ask for
   // hundreds of gigabytes of pinned host memory)
@@ -457,6 +641,7 @@ extern "C" int rp_batch_destroy(rp_batch* b) {
   cudaFree(b->act_force); cudaFree(b->site_xpos); cudaFree(b->t_idx); cudaFree(b->step_type_state);
   cudaFree(b->diag); cudaFree(b->activation); cudaFree(b->metrics); cudaFree(b->work); cudaFree(b->order); cudaFree(b->dbg); cudaFree(b->d_action); cudaFree(b->d_out);
   cudaFree(b->midi_events); cudaFree(b->midi_count); cudaFree(b->ot_scratch);
+  cudaFree(b->hand_offset); cudaFree(b->rng_state);
   cudaFreeHost(b->h_action); cudaFreeHost(b->h_out);
   delete b;
   return 0;
@@ -482,7 +667,7 @@ extern "C" int rp_set_song(rp_batch* b, const uint8_t* goal, const int8_t* finge
 }
 
 extern "C" int rp_set_block_envs(rp_batch* b, int block_envs) {
-  if (block_envs != 0 && block_envs != 1 && block_envs != RP_BLOCK_ENVS) return fail("block_envs must be 0 (auto), 1 or RP_BLOCK_ENVS");
+  if (block_envs != 0 && block_envs != 1 && block_envs != RP_EPB) return fail("block_envs must be 0 (auto), 1 or RP_BLOCK_ENVS");
   b->block_envs = block_envs;
   return 0;
 }
@@ -503,6 +688,7 @@ static RpKernelArgs base_args(rp_batch* b, int mode) {
   a.diag = b->diag; a.act_force = b->act_force; a.site_xpos = b->site_xpos; a.activation = b->activation; a.metrics = b->metrics;
   a.midi_events = b->midi_events; a.midi_count = b->midi_count; a.midi_cap = b->midi_cap;
   a.work = b->work; a.order = b->order_valid ? b->order : nullptr;
+  a.hand_offset = b->hand_offset; a.rng_state = b->rng_state; a.hand_offset_fresh = b->hand_offset_fresh;
   a.dbg = b->dbg;
   return a;
 }
@@ -527,7 +713,7 @@ extern "C" int rp_step(rp_batch* b, const double* action_dev, double* obs_dev, d
   a.step_type = step_type_dev; a.reward_terms = reward_terms_dev;
   if (launch(b, a)) return 1;
   if (b->model->dm.ot_fingering && (reward_dev || reward_terms_dev)) {
-    CUDA_OK(rp_launch_ot_fingering(b->d_dm, b->nenv, b->t_idx, b->qpos, b->model->nv, b->site_xpos, b->d_goal, reward_dev,
+    CUDA_OK(rp_launch_ot_fingering(b->d_dm, b->nenv, b->t_idx, b->qpos, b->model->nv_dev, b->site_xpos, b->d_goal, reward_dev,
                                    reward_terms_dev, b->ot_scratch, b->stream));
     b->launches++;
   }
@@ -588,23 +774,37 @@ extern "C" int rp_physics_step(rp_batch* b, const double* ctrl_dev, int nsub) {
   return launch(b, a);
 }
 
+// Rows of the device state arrays are [keys 88 | hand 0: 26 | hand 1: 26]; the flat model's rows are
+// [keys 88 | hand 0: nl | hand 1: nl].  Equal when nl == 26; otherwise three strided copies per array.
+static cudaError_t copy_state(const rp_model* M, size_t N, double* dst, const double* src, bool to_host) {
+  const size_t nv = M->nv, nvd = M->nv_dev, B = sizeof(double);
+  const cudaMemcpyKind kind = to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+  if (nv == nvd) return cudaMemcpy(dst, src, B * N * nv, kind);
+  const size_t dpitch = (to_host ? nv : nvd) * B, spitch = (to_host ? nvd : nv) * B;
+  cudaError_t e = cudaMemcpy2D(dst, dpitch, src, spitch, B * RP_NK, N, kind);
+  for (int h = 0; h < M->nhand && e == cudaSuccess; h++) {
+    const size_t ho = RP_NK + (size_t)h * M->nl, hd = RP_NK + (size_t)h * RP_NL;
+    e = cudaMemcpy2D(dst + (to_host ? ho : hd), dpitch, src + (to_host ? hd : ho), spitch, B * M->nl, N, kind);
+  }
+  return e;
+}
 extern "C" int rp_get_state(rp_batch* b, double* qpos, double* qvel, double* qacc_ws, int32_t* t_idx) {
-  size_t N = b->nenv, nv = b->model->nv;
+  size_t N = b->nenv;
   CUDA_OK(cudaSetDevice(b->device));
   CUDA_OK(cudaStreamSynchronize(b->stream));
-  if (qpos) CUDA_OK(cudaMemcpy(qpos, b->qpos, sizeof(double) * N * nv, cudaMemcpyDeviceToHost));
-  if (qvel) CUDA_OK(cudaMemcpy(qvel, b->qvel, sizeof(double) * N * nv, cudaMemcpyDeviceToHost));
-  if (qacc_ws) CUDA_OK(cudaMemcpy(qacc_ws, b->qacc_ws, sizeof(double) * N * nv, cudaMemcpyDeviceToHost));
+  if (qpos) CUDA_OK(copy_state(b->model, N, qpos, b->qpos, true));
+  if (qvel) CUDA_OK(copy_state(b->model, N, qvel, b->qvel, true));
+  if (qacc_ws) CUDA_OK(copy_state(b->model, N, qacc_ws, b->qacc_ws, true));
   if (t_idx) CUDA_OK(cudaMemcpy(t_idx, b->t_idx, sizeof(int32_t) * N, cudaMemcpyDeviceToHost));
   return 0;
 }
 extern "C" int rp_set_state(rp_batch* b, const double* qpos, const double* qvel, const double* qacc_ws, const int32_t* t_idx) {
-  size_t N = b->nenv, nv = b->model->nv;
+  size_t N = b->nenv;
   CUDA_OK(cudaSetDevice(b->device));
   CUDA_OK(cudaStreamSynchronize(b->stream));
-  if (qpos) CUDA_OK(cudaMemcpy(b->qpos, qpos, sizeof(double) * N * nv, cudaMemcpyHostToDevice));
-  if (qvel) CUDA_OK(cudaMemcpy(b->qvel, qvel, sizeof(double) * N * nv, cudaMemcpyHostToDevice));
-  if (qacc_ws) CUDA_OK(cudaMemcpy(b->qacc_ws, qacc_ws, sizeof(double) * N * nv, cudaMemcpyHostToDevice));
+  if (qpos) CUDA_OK(copy_state(b->model, N, b->qpos, qpos, false));
+  if (qvel) CUDA_OK(copy_state(b->model, N, b->qvel, qvel, false));
+  if (qacc_ws) CUDA_OK(copy_state(b->model, N, b->qacc_ws, qacc_ws, false));
   if (t_idx) CUDA_OK(cudaMemcpy(b->t_idx, t_idx, sizeof(int32_t) * N, cudaMemcpyHostToDevice));
   return 0;
 }
@@ -634,6 +834,40 @@ extern "C" int rp_get_metrics(rp_batch* b, double* out) {
   CUDA_OK(cudaSetDevice(b->device));
   CUDA_OK(cudaStreamSynchronize(b->stream));
   CUDA_OK(cudaMemcpy(out, b->metrics, sizeof(double) * (size_t)b->nenv * RP_METRICS_STRIDE, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// randomize_hand_positions (piano_with_shadow_hands.py:64,491-499): from the next reset on, every episode start shifts
+// both hands along y by a draw from U(-0.05, 0.05) m, per environment; the shifts accumulate like the reference's
+// (its model is not recompiled between episodes).  The draws come from one splitmix64 stream per environment, seeded
+// from `seed` and the environment index — the reference's single numpy RandomState has no batched equivalent.
+// enable = 0 turns the feature off and clears the offsets; enable = 2: every episode starts from the unshifted pose (what
+// the reference does when asked to recompile its physics every episode).
+extern "C" int rp_randomize_hand_positions(rp_batch* b, int enable, uint64_t seed) {
+  if (b->model->nhand != 2) return fail("randomize_hand_positions needs the hands task");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  cudaFree(b->hand_offset); cudaFree(b->rng_state);
+  b->hand_offset = nullptr; b->rng_state = nullptr;
+  b->hand_offset_fresh = enable == 2;
+  if (!enable) return 0;
+  std::vector<uint64_t> st((size_t)b->nenv);
+  for (size_t i = 0; i < st.size(); i++) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    st[i] = z;
+  }
+  CUDA_OK(dalloc(&b->hand_offset, (size_t)b->nenv));
+  CUDA_OK(dalloc(&b->rng_state, (size_t)b->nenv));
+  CUDA_OK(cudaMemcpy(b->rng_state, st.data(), sizeof(uint64_t) * st.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+// current offsets [N] (host buffer); zeros when the feature is off
+extern "C" int rp_get_hand_offsets(rp_batch* b, double* out) {
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  if (!b->hand_offset) { memset(out, 0, sizeof(double) * (size_t)b->nenv); return 0; }
+  CUDA_OK(cudaMemcpy(out, b->hand_offset, sizeof(double) * (size_t)b->nenv, cudaMemcpyDeviceToHost));
   return 0;
 }
 

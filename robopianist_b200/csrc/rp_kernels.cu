@@ -32,18 +32,11 @@
 #ifndef RP_CH_UNROLL
 #define RP_CH_UNROLL 1
 #endif
-#ifndef RP_EPB
-#define RP_EPB RP_BLOCK_ENVS  // environments per thread block of the phase-locked variant (see rp_step_kernel)
-#endif
 #ifndef RP_EPB_MINBLOCKS
 #define RP_EPB_MINBLOCKS (RP_EPB <= 6 ? 6 / RP_EPB : 1)  // resident blocks per SM the register allocation has to allow (six environments per SM)
 #endif
-#ifndef RP_PHASE_EVERY
-#define RP_PHASE_EVERY 1  // block-wide phase barrier at the top of every RP_PHASE_EVERY-th substep (RP_EPB > 1)
-#endif
-#define RP_PHASE_AT(sub_) ((sub_) % (RP_PHASE_EVERY) == 0)
-#ifndef RP_PHASE_MASK
-#define RP_PHASE_MASK 0  // extra block-wide phase barriers per substep (RP_EPB > 1): 1 before collision, 2 before PGS, 4 after PGS
+#ifndef RP_PHASE_GROUP
+#define RP_PHASE_GROUP RP_EPB  // environments per phase group: the groups of a block are phase-locked separately (the last group takes the remainder)
 #endif
 #ifndef RP_NU
 #define RP_NU 8  // contacts whose M^-1 Jc^T is kept in shared memory (the others walk the kinematic chain)
@@ -54,7 +47,6 @@
 
 namespace {
 
-constexpr int kPhaseExtra = ((RP_PHASE_MASK) & 1) + (((RP_PHASE_MASK) >> 1) & 1) + (((RP_PHASE_MASK) >> 2) & 1);
 constexpr int kChUnroll = RP_CH_UNROLL;
 
 struct Contact {  // lives in shared memory
@@ -151,6 +143,17 @@ __device__ __forceinline__ void env_sync(int bar_id) {
 __device__ __forceinline__ void hand_pair_sync(int bar_id) {
   __syncwarp();
   asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+}
+// Phase barrier: the environments of one phase group (RP_PHASE_GROUP consecutive slots of the block; the last group
+// takes the remainder) start the substep together.  One group: barrier 0; several: named barriers EPB + 1 + group.
+template <int EPB>
+__device__ __forceinline__ void phase_sync(int slot) {
+  constexpr int PG = RP_PHASE_GROUP, NG = EPB / (PG > 0 ? PG : 1);
+  if (NG <= 1) { __syncthreads(); return; }
+  const int g = slot / PG < NG - 1 ? slot / PG : NG - 1;
+  const int gsize = g == NG - 1 ? EPB - PG * (NG - 1) : PG;
+  __syncwarp();
+  asm volatile("bar.sync %0, %1;" ::"r"(EPB + 1 + g), "r"(64 * gsize) : "memory");
 }
 __device__ __forceinline__ void rotq(double* r, const double* q, const double* v) {
   double m[9];
@@ -471,7 +474,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
   const int nsub_loop = a.mode == RP_MODE_RESET ? 0 : a.nsub;
   const int eidx = (int)blockIdx.x * EPB + slot;
   if (eidx >= a.nenv) {
-    if (EPB > 1) for (int s2 = 0; s2 <= nsub_loop; s2++) { if (RP_PHASE_AT(s2)) __syncthreads(); if (s2 < nsub_loop) for (int p = 0; p < kPhaseExtra; p++) __syncthreads(); }
+    if (EPB > 1) for (int s2 = 0; s2 <= nsub_loop; s2++) phase_sync<EPB>(slot);
     return;
   }
   // longest-expected-first launch order (rp_order_kernel) shortens the tail of the last wave
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
   } else if (a.mode == RP_MODE_RESET) {
     do_reset = a.reset_mask == nullptr ? true : (a.reset_mask[env] != 0);
     if (!do_reset) {
-      if (EPB > 1) for (int s2 = 0; s2 <= nsub_loop; s2++) { if (RP_PHASE_AT(s2)) __syncthreads(); if (s2 < nsub_loop) for (int p = 0; p < kPhaseExtra; p++) __syncthreads(); }
+      if (EPB > 1) for (int s2 = 0; s2 <= nsub_loop; s2++) phase_sync<EPB>(slot);
       return;
     }
   }
@@ -519,6 +522,24 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     for (int j = tid; j < nu; j += KT) sm.ctrl[j] = gctrl[j];
   }
   if (do_reset && tid == 0) { a.t_idx[env] = 0; a.sustain[env] = 0; }
+  // randomize_hand_positions (piano_with_shadow_hands.py:491-499): at every episode start both hands' attachment
+  // frames are shifted along y by one draw from U(-0.05, 0.05).  The reference shifts the frames of a model it does
+  // not recompile between episodes (suite/__init__.py:56,91), so the shifts accumulate over episodes; so do these.
+  // Every thread derives the same value from the environment's generator state; thread 0 stores the new state.
+  double hand_off = 0.0;
+  if (HANDS && a.hand_offset != nullptr) {
+    hand_off = a.hand_offset[env];
+    if (do_reset) {
+      uint64_t z = a.rng_state[env] + 0x9E3779B97F4A7C15ull;  // splitmix64
+      const uint64_t st = z;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z ^= z >> 31;
+      hand_off = (a.hand_offset_fresh ? 0.0 : hand_off) + (-0.05 + 0.1 * ((double)(z >> 11) * (1.0 / 9007199254740992.0)));
+      env_sync<NW, EPB>(bar_id);  // every thread has read the old state
+      if (tid == 0) { a.rng_state[env] = st; a.hand_offset[env] = hand_off; }
+    }
+  }
   // ---- MIDI event stream (models/piano/midi_module.py:47-98): activation changes per physics substep.
   // The previous activation is the one stored by the last step's epilogue; an episode start clears it.
   const bool midi_on = a.midi_events != nullptr && a.mode != RP_MODE_PHYSICS;
@@ -605,11 +626,8 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
   // =============================================================================================
   for (int sub = 0; sub <= (EPB > 1 ? nsub_loop : nsub); sub++) {
     if (EPB > 1) {
-      if (RP_PHASE_AT(sub)) __syncthreads();  // phase barrier: the environments of the block start the substep together
-      if (sub > nsub) {  // this environment is done (episode reset: no physics), only keeps the barrier count
-        if (sub < nsub_loop) for (int p = 0; p < kPhaseExtra; p++) __syncthreads();
-        continue;
-      }
+      phase_sync<EPB>(slot);  // phase barrier: the environments of the group start the substep together
+      if (sub > nsub) continue;  // this environment is done (episode reset: no physics), only keeps the barrier count
     }
     const long long t_sub = clock64();
     const bool last_pass = (sub == nsub);  // kinematics-only pass for the task epilogue / reset
@@ -645,6 +663,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
           double pos[3], quat[4], tmp[3];
           rotq(tmp, pq, lp);
           for (int k = 0; k < 3; k++) pos[k] = pp[k] + tmp[k];
+          if (lpar < 0) pos[1] += hand_off;
           rp::quat_mul(quat, pq, lq);
           rotq(tmp, quat, jp);
           for (int k = 0; k < 3; k++) xanchor[k] = pos[k] + tmp[k];
@@ -677,8 +696,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     }
     if (last_pass) {
       if (EPB == 1) break;
-      if (sub < nsub_loop) for (int p = 0; p < kPhaseExtra; p++) __syncthreads();  // an episode-reset env among stepping ones
-      continue;
+      continue;  // an episode-reset environment among stepping ones
     }
 
     TICK(0)
@@ -908,7 +926,6 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     const unsigned lm_mask = HANDS ? __ballot_sync(FULL, lm_on) : 0u;
 
     TICK(3)
-    if (EPB > 1 && ((RP_PHASE_MASK) & 1)) __syncthreads();
     // ------------------------------------------------------------------ collision (lane = geom of this warp's hand)
     if (tid == 0) { sm.nraw = 0; sm.ncon = 0; sm.overflow = 0; sm.nck = 0; sm.shared_key = 0; sm.nhc[0] = 0; sm.nhc[H1] = 0; }
     env_sync<NW, EPB>(bar_id);  // key arrays published; acc scratch of both hands dead (it aliases the contact lists)
@@ -1179,7 +1196,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         const double imp = rp::impedance(solimp, c_dist, incl);
         double K, B;
         rp::ref_KB(solref, solimp[1], hstep, &K, &B);
-        const double diag = dm->link_body_invw[ch][link] + (c_key >= 0 ? dm->key_body_invw[c_key] : 0.0);
+        const double diag = dm->geom_body_invw[ch][c_geom] + (c_key >= 0 ? dm->key_body_invw[c_key] : 0.0);
         const double Rn = fmax(RP_MINVAL, (1 - imp) * diag / imp);
         cn.R[r] = r == 0 ? Rn : Rn / fmax(RP_MINVAL, dm->impratio);
         mu_row = mu;
@@ -1400,7 +1417,6 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     env_sync<NW, EPB>(bar_id);
 
     TICK(7)
-    if (EPB > 1 && ((RP_PHASE_MASK) & 2)) __syncthreads();  // every environment of the block enters the solver together
     // =============================================================== PGS
     // Row order inside a sweep follows MuJoCo: friction-loss dofs, joint limits (keys, then hand
     // joints), contacts.  The two hands are independent islands unless they touch the same key, so
@@ -1429,7 +1445,6 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     niter_last = iter;
 
     TICK(12)
-    if (EPB > 1 && ((RP_PHASE_MASK) & 4)) __syncthreads();
     // =============================================================== dual -> primal, Euler
     // qacc = qacc_smooth + va ; qfrc_constraint = J^T f
     const double qacc = qacc_smooth + va;
@@ -1758,10 +1773,11 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       off += 1;
       if (HANDS) {
         // joints_pos in the reference's joint order
-        const int src = hl ? dm->obs_dof[h][lane] : 0;
+        const int nob = dm->nobs[h];
+        const int src = lane < nob ? dm->obs_dof[h][lane] : 0;
         const double v = shfl(qh, src);
-        if (hl) o[off + h * NL + lane] = v;
-        off += 2 * NL;
+        if (lane < nob) o[off + h * dm->nobs[0] + lane] = v;
+        off += dm->nobs[0] + dm->nobs[H1];
       }
     } else {
       // self-actuated piano observables: piano/activation (88), piano/sustain_activation (1)

@@ -4,7 +4,12 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "../../include/roboplay.h"
 #include "rp_model.h"
+
+#ifndef RP_EPB
+#define RP_EPB RP_BLOCK_ENVS  // environments per thread block of the phase-locked launch shape (tuning builds override it)
+#endif
 
 enum { RP_MODE_STEP = 0, RP_MODE_RESET = 1, RP_MODE_PHYSICS = 2 };
 enum { RP_STEP_FIRST_ = 0, RP_STEP_MID_ = 1, RP_STEP_LAST_ = 2 };
@@ -52,7 +57,9 @@ struct RpKernelArgs {
   double* metrics;           // [N][RP_METRICS_STRIDE]
   uint32_t* midi_events;     // [N][midi_cap] packed key / sustain events of the running episode (optional)
   int32_t* midi_count;       // [N] events emitted so far this episode (may exceed midi_cap: overflow)
-  int midi_cap, pad_midi;
+  int midi_cap, hand_offset_fresh;  // hand_offset_fresh: every episode starts from the unshifted pose (recompile_physics=True)
+  double* hand_offset;       // [N] y offset of both hands' attachment (randomize_hand_positions), optional
+  uint64_t* rng_state;       // [N] per-environment generator state of the offset draws (with hand_offset)
   int32_t* work;             // [N] work estimate of this step (out)
   const int32_t* order;      // [N] block -> environment (optional)
   double* dbg;

@@ -86,6 +86,7 @@ struct RpDevModel {
   double geom_pos[RP_NHMAX][RP_NGH][3], geom_axis[RP_NHMAX][RP_NGH][3];  // capsule axis (local z) in link frame
   double geom_size[RP_NHMAX][RP_NGH][2];
   RpGeomParams geom_gp[RP_NHMAX][RP_NGH];
+  double geom_body_invw[RP_NHMAX][RP_NGH];  // body_invweight0 of the geom's own body (differs from its link's when the body is fused into an ancestor)
   int nhandgeom_total, pad3;
   // hand colliders of the reference model the narrowphase does not handle (boxes, cylinders, forearm mesh): oriented
   // bounding boxes, checked every substep against the piano's bounding box -> diag flag 8 when one comes within reach
@@ -98,6 +99,7 @@ struct RpDevModel {
   double site_pos[RP_NHMAX][RP_NSITE][3];
   // observation order of hand joints (joints_pos observable)
   int obs_dof[RP_NHMAX][RP_NL];
+  int nobs[RP_NHMAX];  // observed (= real) dofs per hand; link slots beyond are inert padding
   // ---- task ----
   int T, lookahead, wrong_press_termination, disable_fingering_reward, disable_forearm_reward, reward_type;
   int obs_dim, act_dim;

@@ -22,6 +22,7 @@ EXPORTS = [
     "rp_reward_terms", "rp_batch_create", "rp_batch_destroy", "rp_set_option", "rp_reset", "rp_step",
     "rp_step_host", "rp_physics_step", "rp_get_state", "rp_set_state", "rp_get_diag", "rp_get_aux",
     "rp_launch_count", "rp_step_staged", "rp_host_buffers", "rp_get_metrics", "rp_midi_enable", "rp_get_midi", "rp_set_block_envs", "rp_set_song",
+    "rp_randomize_hand_positions", "rp_get_hand_offsets",
 ]
 
 
@@ -65,6 +66,8 @@ def lib():
         L.rp_midi_enable.argtypes = [vp, C.c_int]
         L.rp_set_song.argtypes = [vp, C.POINTER(C.c_uint8), C.POINTER(C.c_int8), C.c_int]
         L.rp_set_block_envs.argtypes = [vp, C.c_int]
+        L.rp_randomize_hand_positions.argtypes = [vp, C.c_int, C.c_uint64]
+        L.rp_get_hand_offsets.argtypes = [vp, dp]
         L.rp_get_midi.argtypes = [vp, C.POINTER(C.c_uint32), ip]
         L.rp_launch_count.restype = C.c_int64
         L.rp_launch_count.argtypes = [vp]
@@ -134,6 +137,16 @@ class Batch:
     def set_block_envs(self, block_envs=0):
         """Environments per thread block of the step kernel: 0 auto, 1, or BLOCK_ENVS (rp_set_block_envs)."""
         _check(lib().rp_set_block_envs(self.ptr, int(block_envs)))
+
+    def randomize_hand_positions(self, enable=True, seed=0):
+        """Per-episode random shift of the hands along y (rp_randomize_hand_positions); enable=2: shifts do not
+        accumulate over episodes."""
+        _check(lib().rp_randomize_hand_positions(self.ptr, int(enable), int(seed) & (2**64 - 1)))
+
+    def get_hand_offsets(self):
+        out = np.zeros(self.nenv, np.float64)
+        _check(lib().rp_get_hand_offsets(self.ptr, _dp(out)))
+        return out
 
     def reset(self, mask_ptr=None, obs_ptr=None):
         _check(lib().rp_reset(self.ptr, mask_ptr, obs_ptr))

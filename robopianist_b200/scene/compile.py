@@ -60,6 +60,10 @@ FOREARM_DOFS = {  # robopianist/models/hands/shadow_hand.py:41-52
 }
 FINGERTIP_BODIES = ("thdistal", "ffdistal", "mfdistal", "rfdistal", "lfdistal")
 FINGERTIP_OFFSET, THUMBTIP_OFFSET = 0.026, 0.0275
+# reduced action space (robopianist/models/hands/shadow_hand.py:73-79,162-182): these joints and their actuators are
+# removed from the hand (their bodies stay, rigidly attached to their parents), the THJ2 range shrinks
+REDUCED_ACTION_SPACE_EXCLUDED_DOFS = ("THJ5", "THJ1", "LFJ5")
+REDUCED_THUMB_RANGE = (0.0, 0.698132)
 
 DEFAULT_ASSET_DIR = Path(os.environ.get(
     "ROBOPIANIST_SHADOW_HAND_DIR", "/root/reference/third_party/mujoco_menagerie/shadow_hand"))
@@ -197,12 +201,28 @@ def _hand_total_mass(spec: mjcf.HandSpec) -> float:
 
 def _add_hand(b: _Builder, side: str, asset_dir: Path, piano_half_length: float,
               primitive_fingertip_collisions: bool, gravity_compensation: bool,
-              disable_hand_collisions: bool, forearm_dofs: Sequence[str], hand_index: int):
+              disable_hand_collisions: bool, forearm_dofs: Sequence[str], hand_index: int,
+              reduced_action_space: bool = False, attachment_yaw: float = 0.0):
     prefix = side + "_"
     spec = mjcf.parse_hand(asset_dir / ("right_hand.xml" if side == "rh" else "left_hand.xml"), prefix)
     ns = f"{side}_shadow_hand/"
     root = spec.bodies[0]
     assert root.name == prefix + "forearm"
+    if reduced_action_space:  # shadow_hand.py:162-179
+        for dof in REDUCED_ACTION_SPACE_EXCLUDED_DOFS:
+            jname, aname = prefix + dof, prefix + "A_" + dof
+            owners = [bd for bd in spec.bodies if any(j.name == jname for j in bd.joints)]
+            assert len(owners) == 1, jname
+            owners[0].joints = [j for j in owners[0].joints if j.name != jname]
+            assert any(a.name == aname for a in spec.actuators), aname
+            spec.actuators = [a for a in spec.actuators if a.name != aname]
+        for bd in spec.bodies:
+            for j in bd.joints:
+                if j.name == prefix + "THJ2":
+                    j.range = np.array(REDUCED_THUMB_RANGE, float)
+        for a in spec.actuators:
+            if a.name == prefix + "A_THJ2":
+                a.ctrlrange = np.array(REDUCED_THUMB_RANGE, float)
 
     # --- forearm dofs (shadow_hand.py:272-311). The joints are appended to the root body, whose
     # childclass supplies armature / frictionloss; damping is critical for the position servo:
@@ -236,7 +256,10 @@ def _add_hand(b: _Builder, side: str, asset_dir: Path, piano_half_length: float,
     root.joints = new_joints + root.joints
     # hand pose (base.py:173-183)
     root.pos = np.array(HAND_POS[side], float)
-    root.quat = mu.quat_normalize(HAND_QUAT)
+    # forearms turned inwards about z by attachment_yaw degrees (base.py:175-183: mju_mulQuat(rotate_by, quaternion))
+    ang = math.radians((1.0 if side == "rh" else -1.0) * float(attachment_yaw))
+    rotate_by = np.array([math.cos(0.5 * ang), 0.0, 0.0, math.sin(0.5 * ang)])
+    root.quat = mu.quat_normalize(mu.quat_mul(rotate_by, np.array(HAND_QUAT, float))) if attachment_yaw else mu.quat_normalize(HAND_QUAT)
 
     body_map = {}
     joint_map = {}
@@ -380,6 +403,8 @@ def compile_scene(
     iterations: int = 50,
     tolerance: float = 1e-8,
     asset_dir: Optional[Path] = None,
+    reduced_action_space: bool = False,
+    attachment_yaw: float = 0.0,
 ) -> FlatModel:
     """Flatten ``piano_with_shadow_hands`` or ``self_actuated_piano`` into SoA constants."""
     if task not in ("piano_with_shadow_hands", "self_actuated_piano"):
@@ -403,7 +428,8 @@ def compile_scene(
     if hands:
         for hi, side in enumerate(("rh", "lh")):
             info = _add_hand(b, side, asset_dir, BASE_SIZE[1], primitive_fingertip_collisions,
-                             gravity_compensation, disable_hand_collisions, forearm_dofs, hi)
+                             gravity_compensation, disable_hand_collisions, forearm_dofs, hi,
+                             reduced_action_space=reduced_action_space, attachment_yaw=attachment_yaw)
             hand_info.append(info)
             impratio = info["impratio"]  # <option impratio="10"> merged into the root on attach
 
@@ -557,6 +583,8 @@ def compile_scene(
         primitive_fingertip_collisions=bool(primitive_fingertip_collisions),
         gravity_compensation=bool(gravity_compensation),
         disable_hand_collisions=bool(disable_hand_collisions),
+        reduced_action_space=bool(reduced_action_space), attachment_yaw=float(attachment_yaw),
+        forearm_dofs=list(forearm_dofs),
         body_names=[bd["name"] for bd in bodies], joint_names=[j["name"] for j in joints],
         geom_names=[g["name"] for g in geoms], actuator_names=[a["name"] for a in acts],
         site_names=[s["name"] for s in b.sites],

@@ -43,14 +43,15 @@ def load(
 ):
     """Loads a RoboPianist environment backed by the CUDA rollout.
 
-    ``seed`` seeds the environment's ``numpy.random.RandomState`` (the reference's ``random_state``); the only draws are
-    those of the song augmentations (``task_kwargs['augmentations']``, suite/variations.py).  ``recompile_physics`` is meaningless here (the scene is
-    flattened once).  ``legacy_step=False`` is rejected: the kernel implements the reference's
+    ``seed`` seeds the environment's ``numpy.random.RandomState`` (the reference's ``random_state``): the draws of the
+    song augmentations (``task_kwargs['augmentations']``, suite/variations.py) and the seed of the per-environment
+    streams of ``randomize_hand_positions``.  The scene is flattened once, so ``recompile_physics`` only keeps its one
+    observable effect: with it the random hand shifts start from the unshifted pose every episode instead of
+    accumulating (the reference shifts a model it does not recompile).  ``legacy_step=False`` is rejected: the kernel implements the reference's
     default legacy ordering (mj_step2 + mj_step1; SURVEY.md §2 table, `Physics.step`).
     """
     if not legacy_step:
         raise NotImplementedError("only legacy_step=True (the reference default) is implemented")
-    del recompile_physics
     if midi_file is not None:
         midi = library.load(midi_file, stretch=stretch, shift=shift)
     else:
@@ -58,7 +59,8 @@ def load(
             raise ValueError(f"Unknown environment {environment_name}. Available environments: {ALL}")
         midi = library.load(_ALL_DICT[environment_name], stretch=stretch, shift=shift)
     batched = BatchedPianoEnv(midi, num_envs=num_envs, device=device, iterations=iterations,
-                              tolerance=tolerance, seed=seed, **dict(task_kwargs or {}))
+                              tolerance=tolerance, seed=seed, recompile_physics=recompile_physics,
+                              **dict(task_kwargs or {}))
     return PianoEnv(batched) if num_envs == 1 else batched
 
 

@@ -80,12 +80,6 @@ class BoundedArray(Array):
 
 def _unsupported(kw: Mapping[str, Any]):
     """Reference kwargs this path does not implement must fail loudly, not be ignored."""
-    if kw["randomize_hand_positions"]:
-        raise NotImplementedError("randomize_hand_positions is not implemented")
-    if kw["reduced_action_space"]:
-        raise NotImplementedError("reduced_action_space is not implemented")
-    if kw["attachment_yaw"] != 0.0:
-        raise NotImplementedError("attachment_yaw != 0 is not implemented")
     if not kw["primitive_fingertip_collisions"]:
         raise NotImplementedError(
             "mesh fingertip colliders need a convex-mesh narrowphase (SURVEY.md §8(f) row 1); pass "
@@ -94,6 +88,9 @@ def _unsupported(kw: Mapping[str, Any]):
         raise NotImplementedError(
             "hand-hand contacts are not implemented (SURVEY.md §8(f) row 1); pass "
             "task_kwargs=dict(disable_hand_collisions=True)")
+    bad = [d for d in kw["forearm_dofs"] if d not in ("forearm_tx", "forearm_ty")]
+    if bad:  # shadow_hand.py:41-52 also lists rotational forearm dofs; only the two slides are restated
+        raise NotImplementedError(f"forearm_dofs {bad} are not implemented (forearm_tx / forearm_ty are)")
 
 
 def derive_task_config(midi, hands: bool, kw: Mapping[str, Any]):
@@ -120,9 +117,10 @@ def derive_task_config(midi, hands: bool, kw: Mapping[str, Any]):
                 ot_fingering_reward=bool(hands and disable_fingering))
 
 
-def obs_layout(hands: bool, n_steps_lookahead: int, disable_fingering_reward: bool):
-    """Observation name -> slice of the flat observation row (SURVEY.md App. A order)."""
-    L, nl = n_steps_lookahead, 26
+def obs_layout(hands: bool, n_steps_lookahead: int, disable_fingering_reward: bool, hand_dofs: int = 26):
+    """Observation name -> slice of the flat observation row (SURVEY.md App. A order).  hand_dofs: joints per hand
+    (26 = 24 hand joints + 2 forearm slides; 23 with reduced_action_space, fewer with fewer forearm_dofs)."""
+    L, nl = n_steps_lookahead, hand_dofs
     out, off = collections.OrderedDict(), 0
 
     def add(name, n):
@@ -152,7 +150,7 @@ class BatchedPianoEnv:
 
     def __init__(self, midi, num_envs: int = 1, device: int = 0, task: str = "piano_with_shadow_hands",
                  iterations: Optional[int] = None, tolerance: Optional[float] = None,
-                 reward_type: int = 0, seed: Optional[int] = None, **task_kwargs):
+                 reward_type: int = 0, seed: Optional[int] = None, recompile_physics: bool = False, **task_kwargs):
         import torch
 
         unknown = set(task_kwargs) - set(_TASK_KWARGS)
@@ -186,7 +184,9 @@ class BatchedPianoEnv:
         self.flat = cache.load_scene(task, gravity_compensation=bool(kw["gravity_compensation"]),
                                      physics_timestep=float(kw["physics_timestep"]),
                                      control_timestep=self.control_timestep,
-                                     forearm_dofs=tuple(kw["forearm_dofs"]))
+                                     forearm_dofs=tuple(kw["forearm_dofs"]),
+                                     reduced_action_space=bool(kw["reduced_action_space"]),
+                                     attachment_yaw=float(kw["attachment_yaw"]))
         n_ign = int(self.flat.meta.get("n_ignored_colliders", 0))
         if hands and n_ign:
             import warnings
@@ -207,6 +207,9 @@ class BatchedPianoEnv:
             stream = torch.cuda.current_stream(self.device).cuda_stream
             self.batch = native.Batch(self.model, self.num_envs, device=device, stream=stream)
         import os
+        self.randomize_hand_positions = bool(hands and kw["randomize_hand_positions"])
+        if self.randomize_hand_positions:  # piano_with_shadow_hands.py:491-499, one generator stream per environment
+            self.batch.randomize_hand_positions(2 if recompile_physics else 1, self.random_state.randint(0, 2**31 - 1))
         if os.environ.get("ROBOPLAY_BLOCK_ENVS"):   # launch shape under test (results do not depend on it)
             self.batch.set_block_envs(int(os.environ["ROBOPLAY_BLOCK_ENVS"]))
         N, dev = self.num_envs, self.device
@@ -220,7 +223,8 @@ class BatchedPianoEnv:
 
     # ------------------------------------------------------------------ specs
     def _obs_layout(self):
-        out = obs_layout(self._hands, self.n_steps_lookahead, self.disable_fingering_reward)
+        hand_dofs = int(self.flat.arrays["hand_obs_dofid"].shape[1]) if self._hands else 0
+        out = obs_layout(self._hands, self.n_steps_lookahead, self.disable_fingering_reward, hand_dofs)
         off = next(reversed(out.values())).stop
         assert off == self.model.obs_dim, (off, self.model.obs_dim)
         return out

@@ -1,0 +1,116 @@
+"""Model-changing task kwargs of the reference (tasks/base.py:96-107, shadow_hand.py:162-182,272-311):
+reduced_action_space, attachment_yaw, forearm_dofs subsets.  CPU part: the flattened scenes, the oracle on them (its
+mass matrix against the independent numpy restatement, bodies without joints included), the C-ABI model packer
+accepting them (host only, no GPU)."""
+import numpy as np
+import pytest
+
+import helpers
+import np_ref
+from oracle import oracle as O
+from robopianist_b200 import native
+from robopianist_b200.scene import cache, compile as C
+from robopianist_b200.scene import mathutil as mu
+from robopianist_b200.suite import env as E
+
+VARIANTS = {
+    "ras": dict(reduced_action_space=True),
+    "yaw10": dict(attachment_yaw=10.0),
+    "fdx": dict(forearm_dofs=("forearm_tx",)),
+    "ras_fd": dict(forearm_dofs=(), reduced_action_space=True),
+}
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_variant_scene_layout(name):
+    kw = VARIANTS[name]
+    fm = cache.load_scene(gravity_compensation=True, **kw)
+    full = cache.load_scene(gravity_compensation=True)
+    ras = bool(kw.get("reduced_action_space"))
+    nfd = len(kw.get("forearm_dofs", ("forearm_tx", "forearm_ty")))
+    nl = 24 - (3 if ras else 0) + nfd
+    assert fm.meta["nv"] == 88 + 2 * nl and fm.meta["nu"] == 2 * (20 - (3 if ras else 0) + nfd)
+    assert fm.arrays["hand_obs_dofid"].shape == (2, nl)
+    names = fm.meta["joint_names"]
+    if ras:  # shadow_hand.py:73-79,162-179
+        for side in ("rh", "lh"):
+            for dof in C.REDUCED_ACTION_SPACE_EXCLUDED_DOFS:
+                assert f"{side}_shadow_hand/{side}_{dof}" not in names
+                assert f"{side}_shadow_hand/{side}_A_{dof}" not in fm.meta["actuator_names"]
+            j = names.index(f"{side}_shadow_hand/{side}_THJ2")
+            assert np.allclose(fm.jnt_range[j], C.REDUCED_THUMB_RANGE)
+            a = fm.meta["actuator_names"].index(f"{side}_shadow_hand/{side}_A_THJ2")
+            assert np.allclose(fm.actuator_ctrlrange[a], C.REDUCED_THUMB_RANGE)
+        # the bodies of the removed joints stay, without joints
+        jointless = [n for n, k in zip(fm.meta["body_names"], fm.body_dofnum) if k == 0 and "shadow_hand" in n]
+        assert sum(n.endswith(("lfmetacarpal", "thbase", "thdistal")) for n in jointless) == 6
+        assert fm.meta["nbody"] == full.meta["nbody"] and fm.meta["ngeom"] == full.meta["ngeom"]
+    if "attachment_yaw" in kw:  # base.py:175-183: rotate_by (about z, +yaw right / -yaw left) times the hand quaternion
+        for side, sign in (("rh", 1.0), ("lh", -1.0)):
+            b = fm.meta["body_names"].index(f"{side}_shadow_hand/{side}_forearm")
+            ang = np.radians(sign * kw["attachment_yaw"])
+            want = mu.quat_normalize(mu.quat_mul(np.array([np.cos(ang / 2), 0, 0, np.sin(ang / 2)]), np.array(C.HAND_QUAT, float)))
+            assert np.allclose(fm.body_quat[b], want, atol=1e-15)
+            assert not np.allclose(fm.body_quat[b], full.body_quat[b])
+    # observation joint order: XML joints first, forearm dofs last (shadow_hand.py:159-183)
+    for h, side in enumerate(("rh", "lh")):
+        obs_names = [names[j].split("/")[1] for j in fm.arrays["hand_obs_dofid"][h]]
+        assert obs_names[len(obs_names) - nfd:] == list(kw.get("forearm_dofs", ("forearm_tx", "forearm_ty")))
+        assert all(n.startswith(side + "_") for n in obs_names[: len(obs_names) - nfd])
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_oracle_mass_matrix_on_variants(name):
+    """Bodies without joints (reduced action space, a forearm without dofs) go through the oracle's general body
+    tree; its composite-inertia mass matrix has to equal the Jacobian-sum restatement."""
+    fm = cache.load_scene(gravity_compensation=True, **VARIANTS[name])
+    om = O.OracleModel(fm)
+    d = O.OracleData(om)
+    rng = np.random.default_rng(3)
+    nv = fm.meta["nv"]
+    q = fm.jnt_range[:, 0] + rng.random(nv) * (fm.jnt_range[:, 1] - fm.jnt_range[:, 0])
+    d.qpos[:] = q
+    for fn in ("orc_kinematics", "orc_crb"):
+        d.call(fn)
+    assert np.abs(np_ref.mass_matrix(fm, q) - d.M).max() < 1e-12
+    # and it steps (random controls, a few control steps) without leaving the finite range
+    d2 = O.OracleData(om); d2.reset()
+    lo, hi = fm.actuator_ctrlrange[:, 0], fm.actuator_ctrlrange[:, 1]
+    for _ in range(5):
+        d2.control_step(lo + (hi - lo) * rng.random(fm.meta["nu"]))
+    assert np.isfinite(d2.qpos).all() and np.isfinite(d2.qvel).all()
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_packer_accepts_variants(name):
+    """rp_model_create (host side, no GPU): variable dof count per hand, jointless bodies fused into their parents."""
+    fm = cache.load_scene(gravity_compensation=True, **VARIANTS[name])
+    goal, fing = helpers.song_tables()
+    model = native.Model(fm, goal, fing, kind=0, n_steps_lookahead=1)
+    nl = fm.arrays["hand_obs_dofid"].shape[1]
+    assert model.act_dim == fm.meta["nu"] + 1
+    assert model.obs_dim == 88 + 1 + 2 * nl + 2 * 89 + 10
+    lay = E.obs_layout(True, 1, False, nl)
+    assert lay["rh_shadow_hand/joints_pos"] == slice(89, 89 + nl) and next(reversed(lay.values())).stop == model.obs_dim
+
+
+def test_unsupported_kwargs_still_raise():
+    kw = dict(E._TASK_KWARGS, primitive_fingertip_collisions=True, disable_hand_collisions=True)
+    E._unsupported(dict(kw, reduced_action_space=True, attachment_yaw=5.0, randomize_hand_positions=True))  # accepted now
+    with pytest.raises(NotImplementedError):
+        E._unsupported(dict(kw, primitive_fingertip_collisions=False))
+    with pytest.raises(NotImplementedError):
+        E._unsupported(dict(kw, disable_hand_collisions=False))
+    with pytest.raises(NotImplementedError):
+        E._unsupported(dict(kw, forearm_dofs=("forearm_roll",)))
+
+
+def test_compile_matches_cached_variants():
+    """The committed variant scenes are what compile.py produces from the assets (build container only)."""
+    if not C.DEFAULT_ASSET_DIR.exists():
+        pytest.skip("Shadow Hand assets not present")
+    for name, kw in VARIANTS.items():
+        fresh = C.compile_scene(gravity_compensation=True, **kw)
+        cached = cache.load_scene(gravity_compensation=True, **kw)
+        for k, v in fresh.arrays.items():
+            assert np.array_equal(v, cached.arrays[k]), (name, k)
