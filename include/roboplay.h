@@ -67,6 +67,9 @@ typedef struct rp_flat_model {
   const double *key_qmax;                              /* [nkey] */
   const int32_t *hand_obs_dofid;                       /* [nhand, nobsdof] joints_pos order */
   int32_t nobsdof, reserved1;
+  /* <contact><exclude> body pairs [nexclude, 2] (only consulted when hand geoms may collide with each other) */
+  const int32_t *exclude_bodies;
+  int32_t nexclude, reserved2;
 } rp_flat_model;
 
 /* Task description: song tables + the PianoWithShadowHands / SelfActuatedPiano kwargs that

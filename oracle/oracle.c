@@ -44,6 +44,7 @@ typedef struct orc_model {
   int *tree_adr, *tree_num, *dof_treeid; /* contiguous dof blocks */
   int *body_chain_len, *body_chain;      /* [nbody], [nbody*MAXDEPTH] dof chain root->leaf */
   int nhandgeom, npianogeom, *handgeom, *pianogeom;
+  int npair, *pair_g1, *pair_g2; /* hand geom pairs that may collide (mj_collision's body-pair filters), MuJoCo order */
   int maxcon;
 } orc_model;
 
@@ -142,11 +143,44 @@ orc_model *orc_model_create(const rp_flat_model *src) {
     if (o->m.geom_hand[g] >= 0 && o->m.geom_collide[g]) o->handgeom[o->nhandgeom++] = g;
     if (o->m.geom_key[g] != -1) o->pianogeom[o->npianogeom++] = g;
   }
+  /* hand geom : hand geom pairs (self and cross hand).  mj_collision's filters: contype / conaffinity; same body or
+   * same weld body (a body without joints is welded to its parent: body_weldid); parent-child weld bodies unless one
+   * of them is welded to the world (filterparent); <exclude> pairs.  Pair order = (body1, body2, geom1, geom2) with
+   * body1 < body2, which for geoms numbered in body order is the lexicographic geom order. */
+  DUP(exclude_bodies, src->nexclude * 2, int32_t);
+  {
+    int *weld = (int *)calloc(nb + 1, sizeof(int));
+    for (int b = 1; b < nb; b++) weld[b] = o->m.body_dofnum[b] > 0 ? b : weld[o->m.body_parentid[b]];
+    o->pair_g1 = (int *)calloc((size_t)o->nhandgeom * o->nhandgeom + 1, sizeof(int));
+    o->pair_g2 = (int *)calloc((size_t)o->nhandgeom * o->nhandgeom + 1, sizeof(int));
+    for (int i1 = 0; i1 < o->nhandgeom; i1++)
+      for (int i2 = i1 + 1; i2 < o->nhandgeom; i2++) {
+        int g1 = o->handgeom[i1], g2 = o->handgeom[i2];
+        int b1 = o->m.geom_bodyid[g1], b2 = o->m.geom_bodyid[g2];
+        if (!((o->m.geom_contype[g1] & o->m.geom_conaffinity[g2]) || (o->m.geom_contype[g2] & o->m.geom_conaffinity[g1]))) continue;
+        int w1 = weld[b1], w2 = weld[b2];
+        if (b1 == b2 || w1 == w2) continue;
+        int wp1 = weld[o->m.body_parentid[w1]], wp2 = weld[o->m.body_parentid[w2]];
+        if (w1 != 0 && w2 != 0 && (w1 == wp2 || w2 == wp1)) continue;
+        int excl = 0;
+        for (int e = 0; e < src->nexclude; e++) {
+          int e1 = o->m.exclude_bodies[2 * e], e2 = o->m.exclude_bodies[2 * e + 1];
+          if ((e1 == b1 && e2 == b2) || (e1 == b2 && e2 == b1)) excl = 1;
+        }
+        if (excl) continue;
+        if (b1 > b2) { fprintf(stderr, "oracle: hand geoms are not in body order\n"); abort(); }
+        o->pair_g1[o->npair] = g1; o->pair_g2[o->npair] = g2; o->npair++;
+      }
+    free(weld);
+  }
   o->maxcon = 32;
   return o;
 }
 
+int orc_npair(const orc_model *o) { return o->npair; }
+void orc_pair_get(const orc_model *o, int i, int *g1, int *g2) { *g1 = o->pair_g1[i]; *g2 = o->pair_g2[i]; }
 void orc_model_destroy(orc_model *o) {
+  free(o->pair_g1); free(o->pair_g2);
   for (int i = 0; i < o->nblocks; i++) free(o->blocks[i]);
   free(o->tree_adr); free(o->tree_num); free(o->dof_treeid); free(o->body_chain_len);
   free(o->body_chain); free(o->handgeom); free(o->pianogeom); free(o);
@@ -671,6 +705,104 @@ static void collide_pair(const orc_model *o, orc_data *d, int gh, int gp) {
     add_contact(o, d, gh, gp, dist, n, p, margin, gap);
   }
 }
+/* ---- hand geom : hand geom narrowphase: MuJoCo's analytic routines for spheres and capsules
+ * (engine_collision_primitive.c: mjraw_SphereSphere, mjc_SphereCapsule, mjraw_CapsuleCapsule), restated.
+ * A "sphere" below is (centre, radius); the z axes are only used for the coincident-centre normal. */
+static int raw_sphere_sphere(double margin, const double *p1, const double *z1, double r1, const double *p2, const double *z2,
+                             double r2, double *dist, double *normal, double *pos) {
+  double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  double cd2 = dot3(dif, dif), mind = margin + r1 + r2;
+  if (cd2 > mind * mind) return 0;
+  double len = sqrt(cd2);
+  if (len < MINVAL) { dif[0] = 1; dif[1] = 0; dif[2] = 0; len = 0; } /* mju_normalize3 */
+  else for (int k = 0; k < 3; k++) dif[k] /= len;
+  *dist = len - r1 - r2;
+  for (int k = 0; k < 3; k++) normal[k] = dif[k];
+  if (len < MINVAL) { /* coincident centres: cross product of the z axes, or x */
+    cross3(normal, z1, z2);
+    if (normalize3(normal) < MINVAL) { normal[0] = 1; normal[1] = 0; normal[2] = 0; }
+  }
+  for (int k = 0; k < 3; k++) pos[k] = p1[k] + normal[k] * (r1 + 0.5 * *dist);
+  return 1;
+}
+static double clipd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+/* returns the number of contacts (0..2); outputs [2] */
+static int raw_capsule_capsule(double margin, const double *p1, const double *ax1, double r1, double h1, const double *p2,
+                               const double *ax2, double r2, double h2, double *dist, double *normal, double *pos) {
+  double dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+  double ma = dot3(ax1, ax1), mb = -dot3(ax1, ax2), mc = dot3(ax2, ax2);
+  double u = -dot3(ax1, dif), v = dot3(ax2, dif);
+  double det = ma * mc - mb * mb;
+  double v1[3], v2[3];
+  if (fabs(det) >= MINVAL) {
+    double x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+    if (x1 > h1) { x1 = h1; x2 = (v - mb * h1) / mc; }
+    else if (x1 < -h1) { x1 = -h1; x2 = (v + mb * h1) / mc; }
+    if (x2 > h2) { x2 = h2; x1 = clipd((u - mb * h2) / ma, -h1, h1); }
+    else if (x2 < -h2) { x2 = -h2; x1 = clipd((u + mb * h2) / ma, -h1, h1); }
+    for (int k = 0; k < 3; k++) { v1[k] = p1[k] + ax1[k] * x1; v2[k] = p2[k] + ax2[k] * x2; }
+    return raw_sphere_sphere(margin, v1, ax1, r1, v2, ax2, r2, dist, normal, pos);
+  }
+  /* parallel axes: both ends of capsule 1 against segment 2, then both ends of capsule 2 against segment 1, at most 2 */
+  int n = 0;
+  for (int pass = 0; pass < 4 && n < 2; pass++) {
+    double x1, x2;
+    if (pass == 0) { x1 = h1; x2 = clipd((v - mb * h1) / mc, -h2, h2); }
+    else if (pass == 1) { x1 = -h1; x2 = clipd((v + mb * h1) / mc, -h2, h2); }
+    else if (pass == 2) { x2 = h2; x1 = clipd((u - mb * h2) / ma, -h1, h1); }
+    else { x2 = -h2; x1 = clipd((u + mb * h2) / ma, -h1, h1); }
+    for (int k = 0; k < 3; k++) { v1[k] = p1[k] + ax1[k] * x1; v2[k] = p2[k] + ax2[k] * x2; }
+    n += raw_sphere_sphere(margin, v1, ax1, r1, v2, ax2, r2, dist + n, normal + 3 * n, pos + 3 * n);
+  }
+  return n;
+}
+static void add_pair_contact(const orc_model *o, orc_data *d, int g1, int g2, double dist, const double *normal,
+                             const double *pos, double margin, double gap) {
+  const rp_flat_model *m = &o->m;
+  if (d->ncon >= o->maxcon) { d->con_overflow = 1; return; }
+  orc_contact *c = &d->con[d->ncon++];
+  for (int k = 0; k < 3; k++) { c->frame[k] = normal[k]; c->pos[k] = pos[k]; }
+  make_frame(c->frame);
+  c->dist = dist;
+  c->includemargin = margin - gap;
+  c->geom1 = g1; c->geom2 = g2;
+  c->body1 = m->geom_bodyid[g1]; c->body2 = m->geom_bodyid[g2];
+  c->key = -1;
+  mix_solparams(m, g1, g2, c->solref, c->solimp, c->friction);
+  c->mu = c->friction[0];
+  c->efc_address = -1;
+}
+/* one hand geom pair; mj_collideGeoms orders the two geoms by type first (sphere before capsule) */
+static void collide_hand_pair(const orc_model *o, orc_data *d, int g1, int g2) {
+  const rp_flat_model *m = &o->m;
+  if (m->geom_type[g1] > m->geom_type[g2]) { int t = g1; g1 = g2; g2 = t; }
+  double margin = m->geom_margin[g1] > m->geom_margin[g2] ? m->geom_margin[g1] : m->geom_margin[g2];
+  double gap = m->geom_gap[g1] > m->geom_gap[g2] ? m->geom_gap[g1] : m->geom_gap[g2];
+  const double *p1 = d->geom_xpos + 3 * g1, *p2 = d->geom_xpos + 3 * g2;
+  double z1[3] = {d->geom_xmat[9 * g1 + 2], d->geom_xmat[9 * g1 + 5], d->geom_xmat[9 * g1 + 8]};
+  double z2[3] = {d->geom_xmat[9 * g2 + 2], d->geom_xmat[9 * g2 + 5], d->geom_xmat[9 * g2 + 8]};
+  double r1 = m->geom_size[3 * g1], r2 = m->geom_size[3 * g2];
+  double h1 = m->geom_type[g1] == G_CAPSULE ? m->geom_size[3 * g1 + 1] : 0.0, h2 = m->geom_type[g2] == G_CAPSULE ? m->geom_size[3 * g2 + 1] : 0.0;
+  /* bounding spheres (mj_collideGeoms' first filter) */
+  {
+    double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]}, bound = r1 + h1 + r2 + h2 + margin;
+    if (dot3(dif, dif) > bound * bound) return;
+  }
+  double dist[2], normal[6], pos[6];
+  int n;
+  if (m->geom_type[g1] == G_SPHERE && m->geom_type[g2] == G_SPHERE) {
+    n = raw_sphere_sphere(margin, p1, z1, r1, p2, z2, r2, dist, normal, pos);
+  } else if (m->geom_type[g1] == G_SPHERE) { /* mjc_SphereCapsule: nearest point of the segment, then sphere : sphere */
+    double vec[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+    double x = clipd(dot3(z2, vec), -h2, h2);
+    double q[3] = {p2[0] + z2[0] * x, p2[1] + z2[1] * x, p2[2] + z2[2] * x};
+    n = raw_sphere_sphere(margin, p1, z1, r1, q, z2, r2, dist, normal, pos);
+  } else {
+    n = raw_capsule_capsule(margin, p1, z1, r1, h1, p2, z2, r2, h2, dist, normal, pos);
+  }
+  for (int i = 0; i < n; i++)
+    if (dist[i] < margin) add_pair_contact(o, d, g1, g2, dist[i], normal + 3 * i, pos + 3 * i, margin, gap);
+}
 void orc_collision(const orc_model *o, orc_data *d) {
   const rp_flat_model *m = &o->m;
   d->ncon = 0;
@@ -686,6 +818,8 @@ void orc_collision(const orc_model *o, orc_data *d) {
       collide_pair(o, d, gh, gp);
     }
   }
+  /* hand bodies follow the piano bodies: their pairs come last */
+  for (int i = 0; i < o->npair; i++) collide_hand_pair(o, d, o->pair_g1[i], o->pair_g2[i]);
 }
 
 /* --------------------------------- mj_makeConstraint --------------------------------------- */

@@ -65,6 +65,33 @@ class RefEnv:
         self.midi_messages = []
 
     # ---------------------------------------------------------------- helpers
+    def _forearms_touch(self):
+        fm, d = self.fm, self.d
+        fore = [[g for g in range(fm.meta["ngeom"]) if fm.geom_forearm[g] and fm.geom_hand[g] == h] for h in (0, 1)]
+        if not fore[0] or not ((fm.geom_contype[fore[0][0]] & fm.geom_conaffinity[fore[1][0]])
+                               or (fm.geom_contype[fore[1][0]] & fm.geom_conaffinity[fore[0][0]])):
+            return False
+
+        def box(g):  # centre, axes (columns), half sizes; cylinders never occur on the forearm
+            return d.geom_xpos[g], d.geom_xmat[g].reshape(3, 3), fm.geom_size[g]
+
+        def overlap(a, b):  # separating-axis theorem, plain form: project both boxes on the 15 candidate axes
+            (ca, Ra, ha), (cb, Rb, hb) = a, b
+            axes = [Ra[:, i] for i in range(3)] + [Rb[:, j] for j in range(3)]
+            axes += [np.cross(Ra[:, i], Rb[:, j]) for i in range(3) for j in range(3)]
+            for ax in axes:
+                n = np.linalg.norm(ax)
+                if n < 1e-9:
+                    continue
+                ax = ax / n
+                ra = sum(ha[i] * abs(ax @ Ra[:, i]) for i in range(3))
+                rb = sum(hb[j] * abs(ax @ Rb[:, j]) for j in range(3))
+                if abs(ax @ (cb - ca)) > ra + rb:
+                    return False
+            return True
+
+        return any(overlap(box(g0), box(g1)) for g0 in fore[0] for g1 in fore[1])
+
     def _update_key_state(self):
         d = self.d
         if self.kind == 1:
@@ -206,7 +233,11 @@ class RefEnv:
                     ri, ci = linear_sum_assignment(dist)
                     terms["ot_fingering_reward"] = float(np.mean(tolerance(dist[ri, ci], (0, 0.01), 0.1)))
             if not self.disable_forearm_reward:
-                terms["forearm_reward"] = 0.5  # hands cannot touch each other with disable_hand_collisions=True
+                # _compute_forearm_reward (piano_with_shadow_hands.py:251-259): 0 when a geom of one root body touches a
+                # geom of the other.  With disable_hand_collisions=True the hands cannot touch each other.  Otherwise the
+                # forearm colliders (a box and a mesh, outside the narrowphase's coverage) are tested as oriented boxes
+                # (box / mesh bounding box), an approximation of MuJoCo's convex contact test.
+                terms["forearm_reward"] = 0.0 if self._forearms_touch() else 0.5
             reward = sum(terms.values())
         else:
             pred = np.concatenate([self.activation.astype(np.float64), [float(self.sustain_activation)]])

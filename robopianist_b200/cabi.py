@@ -48,6 +48,7 @@ class RpFlatModel(C.Structure):
         + [("gravity", C.c_double * 3)]
         + [(n, t) for n, t in _ARRAYS]
         + [("nobsdof", C.c_int32), ("reserved1", C.c_int32)]
+        + [("exclude_bodies", _I), ("nexclude", C.c_int32), ("reserved2", C.c_int32)]
     )
 
 
@@ -85,6 +86,11 @@ def pack_model(fm, iterations=None, tolerance=None):
         setattr(s, name, a.ctypes.data_as(typ))
     hod = fm.arrays["hand_obs_dofid"]
     s.nobsdof = int(hod.shape[1]) if hod.ndim == 2 and hod.shape[0] else 0
+    ex = np.ascontiguousarray(fm.arrays.get("exclude_bodies", np.zeros((0, 2), np.int32)), dtype=np.int32).reshape(-1, 2)
+    s.nexclude = int(ex.shape[0])
+    exr = ex.ravel() if ex.size else np.zeros(2, np.int32)
+    keep.append(exr)
+    s.exclude_bodies = exr.ctypes.data_as(_I)
     return s, keep
 
 

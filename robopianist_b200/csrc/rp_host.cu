@@ -315,6 +315,7 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
   int nact_hand = m->nhand ? (m->nu - nkey_act) / m->nhand : 0;
   int order = 0;
   d.nobs[0] = d.nobs[1] = nl;
+  int geom_flat[RP_NHMAX][RP_NGH];  // flat-model geom of the hand's n-th colliding primitive
   for (int h = 0; h < m->nhand; h++) {
     int base = RP_NK + h * nl;
     int maxdepth = 0;
@@ -480,6 +481,7 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
       if (l < 0 || l >= nl) return bad("a colliding hand geom sits on a body that is welded to the world");
       if (m->geom_type[g] != 2 && m->geom_type[g] != 3) return bad("only sphere/capsule hand colliders are supported");
       d.geom_link[h][ng] = l; d.geom_type[h][ng] = m->geom_type[g]; d.geom_order[h][ng] = order++;
+      geom_flat[h][ng] = g;
       double R[9], Rb[9], r[3], ax[3];
       quat_to_mat(m->geom_quat + 4 * g, R);
       rp::quat2mat(Rb, rel.q);
@@ -503,6 +505,10 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
       if (l < 0) continue;  // welded to the world (a forearm without dofs): its clearance never changes
       if (ni >= RP_NIGN) return bad("too many uncovered hand colliders");
       d.ign_link[h][ni] = l;
+      if (m->geom_forearm[g]) {
+        if (d.nfore[h] >= 2) return bad("more than two forearm colliders");
+        d.fore_ign[h][d.nfore[h]++] = ni;
+      }
       double Rb[9], Rg[9], r[3];
       rp::quat2mat(Rb, rel.q);
       rp::mat_vec(r, Rb, m->geom_pos + 3 * g);
@@ -533,6 +539,36 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
       if (od < 0 || od >= nl) return bad("hand_obs_dofid outside the hand's dof range");
       d.obs_dof[h][l] = od;
     }
+  }
+  // hand geom : hand geom pairs (self and cross hand), mj_collision's filters: contype / conaffinity, same body or same
+  // weld body (a jointless body is welded to its parent), parent-child weld bodies unless one is welded to the world,
+  // <exclude> pairs.
+  if (m->nhand == 2) {
+    std::vector<int> weld(m->nbody, 0);
+    for (int b = 1; b < m->nbody; b++) weld[b] = m->body_dofnum[b] > 0 ? b : weld[m->body_parentid[b]];
+    int np = 0;
+    for (int a1 = 0; a1 < 2 * RP_NGH; a1++)
+      for (int a2 = a1 + 1; a2 < 2 * RP_NGH; a2++) {
+        int h1 = a1 / RP_NGH, i1 = a1 % RP_NGH, h2 = a2 / RP_NGH, i2 = a2 % RP_NGH;
+        if (i1 >= d.ngeom[h1] || i2 >= d.ngeom[h2]) continue;
+        int g1 = geom_flat[h1][i1], g2 = geom_flat[h2][i2];
+        if (!((m->geom_contype[g1] & m->geom_conaffinity[g2]) || (m->geom_contype[g2] & m->geom_conaffinity[g1]))) continue;
+        int b1 = m->geom_bodyid[g1], b2 = m->geom_bodyid[g2], w1 = weld[b1], w2 = weld[b2];
+        if (b1 == b2 || w1 == w2) continue;
+        int wp1 = weld[m->body_parentid[w1]], wp2 = weld[m->body_parentid[w2]];
+        if (w1 != 0 && w2 != 0 && (w1 == wp2 || w2 == wp1)) continue;
+        bool excl = false;
+        for (int e = 0; e < m->nexclude; e++) {
+          int e1 = m->exclude_bodies[2 * e], e2 = m->exclude_bodies[2 * e + 1];
+          excl = excl || (e1 == b1 && e2 == b2) || (e1 == b2 && e2 == b1);
+        }
+        if (excl) continue;
+        if (g1 > g2 || b1 > b2) return bad("hand geoms must be numbered in body order");
+        if (np >= RP_HC_MAXPAIRS) return bad("too many hand geom pairs");
+        d.hc_pairs[np++] = (uint16_t)(a1 | (a2 << 8));
+      }
+    d.hc_npair = np;
+    d.hc_enabled = np > 0;
   }
   d.nhandgeom_total = order;
   if (order > 64) return bad("too many hand geoms for the contact sort key");
@@ -694,7 +730,7 @@ static RpKernelArgs base_args(rp_batch* b, int mode) {
 }
 static int launch(rp_batch* b, const RpKernelArgs& a) {
   CUDA_OK(cudaSetDevice(b->device));
-  CUDA_OK(rp_launch_step(a, b->model->nhand, b->stream, b->block_envs));
+  CUDA_OK(rp_launch_step(a, b->model->nhand, b->stream, b->block_envs, b->model->dm.hc_enabled));
   b->launches++;
   return 0;
 }

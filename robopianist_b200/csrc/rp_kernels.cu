@@ -56,7 +56,8 @@ struct Contact {  // lives in shared memory
   double R[3], b[3], f[3];
   double mu, invMk;
   rp::EllInv inv;            // sweep-invariant part of the elliptic block update (1/A00, friction block at lambda = 0, ...)
-  int hand, link, key, dep;  // key = -1: piano base (static); dep: chain depth, bit 8: friction block regular (qcqp ok)
+  int hand, link, key, dep;  // key = -1: piano base (static), -2 / -3: the two records of a hand : hand contact (the block lives in
+                             // the first, the second carries the other body's Jacobian); dep: chain depth, bit 8: friction block regular (qcqp ok)
   signed char chain[16];     // dof (lane) at depth d of the hand chain
 };
 struct CKey {  // limit row of a key that is coupled to a hand through a contact
@@ -65,7 +66,7 @@ struct CKey {  // limit row of a key that is coupled to a hand through a contact
 };
 struct RawContact {  // narrowphase output before sorting
   double dist, pos[3], n[3];
-  int hand, geom, key, sub;
+  int hand, geom, key, sub;  // hand : hand contacts take two entries: key = -2 (geom 1's side) / -3 (geom 2's side), sub = partner's hand * 32 + geom
   unsigned sortkey, pad;
 };
 
@@ -103,9 +104,13 @@ struct Smem {
     double acc[RP_NHMAX][NL][16];  // upward accumulation scratch: F (6) + composite inertia (10)
     Contact con[MAXCON];           // constraint blocks of the contacts (sorted)
     RawContact raw[MAXCON];        // narrowphase output; moved to registers before con[] is written
+    struct {                       // hand : hand collisions: the raw list plus the world-frame primitives of both hands
+      RawContact raw[MAXCON];
+      double gw[RP_NHMAX][RP_NGH][8];  // centre, axis, radius, half length
+    } col;
   } u;
   int ncon, nraw, overflow, pad;
-  int near_uncovered, pad2;  // some collider outside the narrowphase's coverage came within reach of the piano (this launch)
+  int near_uncovered, npairc;  // near_uncovered: some collider outside the narrowphase's coverage came within reach of the piano (this launch); npairc: hand : hand contacts of this substep (each takes two records)
 };
 
 constexpr size_t kSmemStride = (sizeof(Smem) + 15) / 16 * 16;  // per-environment shared memory (RP_EPB > 1: slot stride)
@@ -432,6 +437,176 @@ __device__ __noinline__ int pgs_solve(Smem* smp, const int h, const int bar_id, 
   return iter;
 }
 
+// The solver of models whose hand geoms may collide with each other (disable_hand_collisions=False).  Same sweep as
+// pgs_solve — friction rows, limit rows of coupled keys, hand limit rows, contacts in sorted order (this copy loads
+// the Jacobian entries on demand instead of a contact ahead).  A hand : hand contact occupies two adjacent records:
+// the first (key = -2) holds the block and the Jacobian of geom 1's body, the second (key = -3) the Jacobian of geom
+// 2's body; both mirror the force.  Same-hand pair: the warp of that hand adds both records' entries per dof.  Cross-hand
+// pair: sm.shared_key is set, the rows are stepped in global order, each warp reduces its own half of J * va, the
+// halves are exchanged through shared memory, both warps evaluate the (identical) block update and apply it to their own
+// dofs; the warp of geom 1 accounts for the cost change.
+__device__ __noinline__ int pgs_solve_hc(Smem* smp, const int h, const int bar_id, const int ncon, const int maxiter, const double tol,
+                                         const double scale, const double improvement0, const double fr_R, const double fr_b,
+                                         const double fr_AR, const double fr_hi, const double lm_J, const double lm_R,
+                                         const double lm_b, const double lm_AR, const unsigned lm_mask, const int lsub,
+                                         const int ldc, PgsLane* io) {
+  Smem& sm = *smp;
+  int lane;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+  const bool hl = lane < NL;
+  const int lc = hl ? lane : 0;
+  const double* const Ah = sm.A[h];
+  const double* const pcol = Ah + lc;
+  double fr_f = io->fr_f, lm_f = io->lm_f, va = io->va;
+  const int nck = sm.nck, shared_key = sm.shared_key, nmine = sm.nhc[h];
+  const double fr_ARi = 1.0 / fr_AR, lm_ARi = ((lm_mask >> lane) & 1u) ? 1.0 / lm_AR : 0.0;
+  const double fr_lo = -fr_hi;
+  unsigned ckmask = 0;
+  for (int c = 0; c < nck; c++) {
+    const bool mine = shared_key ? (h == 0) : (sm.ckown[c] == h);
+    if (mine && sm.ck[c].active) ckmask |= 1u << c;
+  }
+  const signed char* const hlist = sm.hlist[h];
+  Contact* const con = sm.u.con;
+  const int ntrip = shared_key ? ncon : nmine;
+  const double imp0 = warp_sum(improvement0);
+  int iter = 0;
+  while (iter < maxiter) {
+    double improvement = iter == 0 ? imp0 : 0.0;
+    {  // friction-loss rows (see pgs_solve)
+      const double fbase = fr_b + fr_R * fr_f;
+      double res = fbase + va;
+      double x = fr_f - res * fr_ARi;
+      double fx = x < fr_lo ? fr_lo : x;
+      fx = x > fr_hi ? fr_hi : fx;
+      unsigned m = __ballot_sync(FULL, hl && fx != fr_f);
+      while (m != 0u) {
+        const int i = __ffs(m) - 1;
+        const double col = pcol[i * RS];
+        const double dl = fx - fr_f;
+        const double imp = dl * (0.5 * dl * fr_AR + res);
+        const double dbc = shfl(dl, i), ibc = shfl(imp, i);
+        va -= col * dbc;
+        improvement -= ibc;
+        if (lane == i) fr_f = fx;
+        res = fbase + va;
+        x = fr_f - res * fr_ARi;
+        fx = x < fr_lo ? fr_lo : x;
+        fx = x > fr_hi ? fr_hi : fx;
+        m = __ballot_sync(FULL, hl && lane > i && fx != fr_f);
+      }
+    }
+    for (unsigned mm = ckmask; mm; mm &= mm - 1) {  // limit rows of keys that carry contacts
+      CKey& ck = sm.ck[__ffs(mm) - 1];
+      const int key = ck.key;
+      const double vak = sm.vak[key], f = ck.f;
+      const double res = ck.b + ck.R * f + ck.J * vak;
+      double fn = f - res * ck.ARi;
+      fn = fn < 0 ? 0.0 : fn;
+      const double dl = fn - f;
+      __syncwarp();
+      improvement -= dl * (0.5 * dl * ck.AR + res);
+      ck.f = fn;
+      sm.vak[key] = vak + ck.J * dl * ck.invM;
+      __syncwarp();
+    }
+    if (shared_key) hand_pair_sync(bar_id);
+    {  // hand limit rows
+      const double lbase = lm_b + lm_R * lm_f;
+      for (unsigned m2 = lm_mask; m2; m2 &= m2 - 1) {
+        const int i = __ffs(m2) - 1;
+        const double res = lbase + lm_J * va;
+        const double x = lm_f - res * lm_ARi;
+        const double fn = x < 0 ? 0.0 : x;
+        const double dl = fn - lm_f;
+        const double imp = dl * (0.5 * dl * lm_AR + res);
+        const double dbc = shfl(lm_J * dl, i), ibc = shfl(imp, i);
+        va -= Ah[i * RS + lc] * dbc;
+        improvement -= ibc;
+        if (lane == i) lm_f = fn;
+      }
+    }
+    // contacts, sorted order
+    for (int ci = 0; ci < ntrip; ci++) {
+      const int c = shared_key ? ci : (int)hlist[ci];
+      Contact& cn = con[c];
+      const int kind = cn.key;  // >= -1: hand : piano; -2 / -3: first / second record of a hand : hand contact
+      if (kind != -3) {         // the second record is handled together with the first
+        const bool pair = kind == -2;
+        Contact& cs = con[pair ? c + 1 : c];
+        const bool mineP = cn.hand == h, mineS = pair && cs.hand == h;
+        const bool cross = pair && cs.hand != cn.hand;
+        if (mineP || mineS) {  // warp-uniform
+          double j0 = 0, j1 = 0, j2 = 0, k0 = 0, k1 = 0, k2 = 0;
+          if (mineP) { const int link = cn.link; if (lane <= link && link < lane + lsub) { j0 = cn.Jc[0][ldc]; j1 = cn.Jc[1][ldc]; j2 = cn.Jc[2][ldc]; } }
+          if (mineS) { const int link = cs.link; if (lane <= link && link < lane + lsub) { k0 = cs.Jc[0][ldc]; k1 = cs.Jc[1][ldc]; k2 = cs.Jc[2][ldc]; } }
+          double p0 = (j0 + k0) * va, p1 = (j1 + k1) * va, p2 = (j2 + k2) * va;
+          const int key = cn.key, depq = cn.dep;
+          double Ab[9], fold[3], rbase[3];
+#pragma unroll
+          for (int k = 0; k < 9; k++) Ab[k] = cn.A[k];
+          const double cmu = cn.mu;
+          const rp::EllInv inv = cn.inv;
+          const double vak = sm.vak[key >= 0 ? key : 0], jkm0 = key >= 0 ? 1.0 : 0.0;
+          const double jk0 = cn.Jk[0], jk1 = cn.Jk[1], jk2 = cn.Jk[2], invMk = cn.invMk;
+#pragma unroll
+          for (int r = 0; r < 3; r++) { fold[r] = cn.f[r]; rbase[r] = cn.b[r] + cn.R[r] * fold[r] + jkm0 * cn.Jk[r] * vak; }
+          int den_ok;
+          const double rden = rp::pgs_elliptic_ray(Ab, fold, &den_ok);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            p0 += __shfl_xor_sync(FULL, p0, o);
+            p1 += __shfl_xor_sync(FULL, p1, o);
+            p2 += __shfl_xor_sync(FULL, p2, o);
+          }
+          if (cross) {  // both warps are here: exchange the halves of J * va (the block and the old force are already read)
+            if (lane == 0) { double* r = sm.red[0][h]; r[2] = p0; r[3] = p1; r[4] = p2; }
+            hand_pair_sync(bar_id);
+            p0 = sm.red[0][0][2] + sm.red[0][H1][2]; p1 = sm.red[0][0][3] + sm.red[0][H1][3]; p2 = sm.red[0][0][4] + sm.red[0][H1][4];
+          }
+          const double res[3] = {rbase[0] + p0, rbase[1] + p1, rbase[2] + p2};
+          double f[3] = {fold[0], fold[1], fold[2]};
+          const double change = rp::pgs_elliptic_apply(inv, depq >> 8, rden, den_ok, Ab, res, f, cmu);
+          const double df0 = f[0] - fold[0], df1 = f[1] - fold[1], df2 = f[2] - fold[2];
+          __syncwarp();
+          if (mineP) improvement -= change;
+          cn.f[0] = f[0]; cn.f[1] = f[1]; cn.f[2] = f[2];  // identical on every lane (and in both warps of a cross-hand pair)
+          if (pair) { cs.f[0] = f[0]; cs.f[1] = f[1]; cs.f[2] = f[2]; }
+          if (df0 != 0.0 || df1 != 0.0 || df2 != 0.0) {
+            if (key >= 0) sm.vak[key] = vak + (jk0 * df0 + jk1 * df1 + jk2 * df2) * invMk;
+            // hand side, per record of this hand: w = Jc^T df on the chain, va += Minv[:, chain] w
+            if (mineP) {
+              const double w = j0 * df0 + j1 * df1 + j2 * df2;
+              const int dep = depq & 0xff;
+              double acc = 0;
+#pragma unroll 1
+              for (int d = 0; d <= dep; d++) { const int j = cn.chain[d]; acc -= Ah[j * RS + lc] * shfl(w, j); }
+              va += acc;
+            }
+            if (mineS) {
+              const double w = k0 * df0 + k1 * df1 + k2 * df2;
+              const int dep = cs.dep & 0xff;
+              double acc = 0;
+#pragma unroll 1
+              for (int d = 0; d <= dep; d++) { const int j = cs.chain[d]; acc -= Ah[j * RS + lc] * shfl(w, j); }
+              va += acc;
+            }
+          }
+          __syncwarp();
+        }
+      }
+      if (shared_key) hand_pair_sync(bar_id);
+    }
+    if (lane == 0) sm.red[iter & 1][h][1] = improvement;
+    hand_pair_sync(bar_id);
+    improvement = (sm.red[iter & 1][0][1] + sm.red[iter & 1][H1][1]) * scale;
+    iter++;
+    if (improvement < tol) break;
+  }
+  io->fr_f = fr_f; io->lm_f = lm_f; io->va = va;
+  return iter;
+}
+
 }  // namespace
 
 // The kernel proper is large; it is written as one function so that lane-owned state stays in
@@ -440,9 +615,12 @@ __device__ __noinline__ int pgs_solve(Smem* smp, const int h, const int bar_id, 
 // a block-wide barrier at the top of every substep re-aligns their warps, so that the warps resident on an SM
 // run the same stage (the same instruction lines) at the same time instead of each streaming its own
 // position of a 370 KB program through the instruction caches.
-template <int NW, int EPB>
+// HC: the hand geoms may collide with each other (disable_hand_collisions=False): an instantiation of its own, so that the
+// default configuration's code is unchanged.
+template <int NW, int EPB, bool HC>
 __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (NW == 2 ? RP_MINBLOCKS : 8)) rp_step_kernel(RpKernelArgs a) {
   constexpr bool HANDS = NW == 2;
+  static_assert(!HC || HANDS, "hand : hand collisions need hands");
   constexpr int KT = 32 * NW;               // threads per environment
   constexpr int KS = (NK + KT - 1) / KT;    // keys per thread
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -927,7 +1105,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
 
     TICK(3)
     // ------------------------------------------------------------------ collision (lane = geom of this warp's hand)
-    if (tid == 0) { sm.nraw = 0; sm.ncon = 0; sm.overflow = 0; sm.nck = 0; sm.shared_key = 0; sm.nhc[0] = 0; sm.nhc[H1] = 0; }
+    if (tid == 0) { sm.nraw = 0; sm.ncon = 0; sm.overflow = 0; sm.nck = 0; sm.shared_key = 0; sm.nhc[0] = 0; sm.nhc[H1] = 0; sm.npairc = 0; }
     env_sync<NW, EPB>(bar_id);  // key arrays published; acc scratch of both hands dead (it aliases the contact lists)
     TICK(4)
     if (HANDS) {
@@ -1081,6 +1259,54 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         }
       }
       __syncwarp();
+      if (HC && isg) {  // world-frame primitive for the hand : hand pass
+        double* w = sm.u.col.gw[h][lane];
+        for (int k = 0; k < 3; k++) { w[k] = gc[k]; w[3 + k] = gax[k]; }
+        w[6] = rad; w[7] = half;
+      }
+    }
+    if (HC && dm->hc_enabled) {
+      // ---- hand geom : hand geom pairs (self and cross hand; host-filtered list in MuJoCo's pair order), one thread
+      // per pair: bounding spheres, then the analytic sphere / capsule routines.  A contact takes two adjacent raw
+      // entries (one per body), sorted behind every hand : piano contact.
+      env_sync<NW, EPB>(bar_id);
+      const int npairs = dm->hc_npair;
+      for (int p = tid; p < npairs; p += KT) {
+        const unsigned e = dm->hc_pairs[p];
+        int a1 = e & 0xff, a2 = e >> 8;
+        const double* w1 = &sm.u.col.gw[0][0][0] + 8 * a1;
+        const double* w2 = &sm.u.col.gw[0][0][0] + 8 * a2;
+        if (w1[7] > 0 && w2[7] == 0) { const double* t = w1; w1 = w2; w2 = t; const int ta = a1; a1 = a2; a2 = ta; }  // sphere before capsule
+        const int h1 = a1 / RP_NGH, g1 = a1 - h1 * RP_NGH, h2 = a2 / RP_NGH, g2 = a2 - h2 * RP_NGH;
+        const double margin = fmax(dm->geom_gp[h1][g1].margin, dm->geom_gp[h2][g2].margin);
+        const double dx = w2[0] - w1[0], dy = w2[1] - w1[1], dz = w2[2] - w1[2], bound = w1[6] + w1[7] + w2[6] + w2[7] + margin;
+        if (dx * dx + dy * dy + dz * dz > bound * bound) continue;
+        double dist[2], nrm[6], pos[6];
+        const int nc = rp::sphere_capsule_pair(margin, w1, w1 + 3, w1[6], w1[7], w2, w2 + 3, w2[6], w2[7], dist, nrm, pos);
+        for (int i = 0; i < nc; i++) {
+          if (!(dist[i] < margin)) continue;
+          const int slot = atomicAdd(&sm.nraw, 2);
+          if (slot + 1 < MAXCON) {
+            atomicAdd(&sm.npairc, 1);
+            for (int side = 0; side < 2; side++) {
+              RawContact& rc = sm.u.col.raw[slot + side];
+              rc.dist = dist[i];
+              for (int k = 0; k < 3; k++) { rc.n[k] = nrm[3 * i + k]; rc.pos[k] = pos[3 * i + k]; }
+              rc.hand = side ? h2 : h1; rc.geom = side ? g2 : g1; rc.key = -2 - side;
+              rc.sub = side ? h1 * 32 + g1 : h2 * 32 + g2;
+              rc.sortkey = 32768u + (unsigned)((p * 2 + i) * 2 + side);
+            }
+          } else {
+            sm.overflow = 1;
+            if (slot < MAXCON) {  // the odd slot left over: an inert record (the environment is flagged as overflowed)
+              RawContact& rc = sm.u.col.raw[slot];
+              rc.dist = 1.0; rc.n[0] = 0; rc.n[1] = 0; rc.n[2] = 1;
+              for (int k = 0; k < 3; k++) rc.pos[k] = w1[k];
+              rc.hand = h1; rc.geom = g1; rc.key = -1; rc.sub = 0; rc.sortkey = 32768u + (unsigned)((p * 2 + i) * 2);
+            }
+          }
+        }
+      }
     }
     if (HANDS) {
       // colliders outside the narrowphase's coverage (palm / knuckle / wrist boxes and cylinders, forearm): if the
@@ -1123,7 +1349,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     if (sm.nraw > MAXCON || sm.overflow) flags |= 1;
     // NOTE: on overflow the kept subset depends on atomic order; the flag marks the env invalid.
     const int ncon = nraw;
-    ncon_last = ncon;
+    ncon_last = HC ? ncon - sm.npairc : ncon;  // a hand : hand contact takes two records
     // ---- contact rows (rank-sorted into con[]): one thread per (contact, frame row), spread over both warps
     // (RP_MAXCON = 21 contacts = 63 rows)
     static_assert(!HANDS || 3 * MAXCON <= KT, "one thread per contact row");
@@ -1139,9 +1365,10 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       const int c = rowt ? tid / 3 : 0, r = tid - 3 * c;
       // contact geometry to registers: raw[] and con[] share the same shared memory
       double c_dist = 0, c_pos[3] = {0, 0, 0}, c_frame[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-      int ch = 0, c_geom = 0, c_key = -1;
+      int ch = 0, c_geom = 0, c_key = -1, c_sub = 0;
       if (rowt) {
         const RawContact rc = sm.u.raw[sm.perm[c]];
+        c_sub = rc.sub;
         c_dist = rc.dist;
         for (int k = 0; k < 3; k++) { c_pos[k] = rc.pos[k]; c_frame[k] = rc.n[k]; }
         const double nn = sqrt(rp::dot3(c_frame, c_frame));
@@ -1151,6 +1378,8 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       }
       env_sync<NW, EPB>(bar_id);
       double u[MAXD], arefr = 0, mu_row = 0;
+      double hc_sv = 0, hc_B = 0, hc_K = 0;  // hand : hand contacts: this side's row velocity, damping and stiffness term
+      const bool pairc = HC && c_key < -1;   // record of a hand : hand contact (-2: geom 1's body, -3: geom 2's)
       int link = 0, dep = 0;
       if (rowt) {
         Contact& cn = sm.u.con[c];
@@ -1171,7 +1400,8 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
           const double* S = sm.v.pre.S[ch][cidx[d]];
           double wxp[3];
           rp::cross3(wxp, S, c_pos);
-          const double v = d <= dep ? -(dir[0] * (S[3] + wxp[0]) + dir[1] * (S[4] + wxp[1]) + dir[2] * (S[5] + wxp[2])) : 0.0;
+          double v = d <= dep ? -(dir[0] * (S[3] + wxp[0]) + dir[1] * (S[4] + wxp[1]) + dir[2] * (S[5] + wxp[2])) : 0.0;
+          if (HC && c_key == -3) v = -v;  // body 2 of the pair enters with a plus sign
           jrow[d] = v;
           cn.Jc[r][d] = v;
         }
@@ -1188,7 +1418,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         cn.Jk[r] = jk;
         // mixed parameters, impedance / regularisation (evaluated by each of the three row threads)
         const RpGeomParams& g1 = dm->geom_gp[ch][c_geom];
-        const RpGeomParams& g2 = c_key < 0 ? dm->base_gp : dm->key_gp[c_key];
+        const RpGeomParams& g2 = pairc ? dm->geom_gp[c_sub >> 5][c_sub & 31] : (c_key < 0 ? dm->base_gp : dm->key_gp[c_key]);
         double solref[2], solimp[5], mu;
         rp::mix_params(g1.solref, g1.solimp, g1.friction, g1.solmix, g1.priority, g2.solref, g2.solimp, g2.friction,
                        g2.solmix, g2.priority, solref, solimp, &mu);
@@ -1196,7 +1426,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         const double imp = rp::impedance(solimp, c_dist, incl);
         double K, B;
         rp::ref_KB(solref, solimp[1], hstep, &K, &B);
-        const double diag = dm->geom_body_invw[ch][c_geom] + (c_key >= 0 ? dm->key_body_invw[c_key] : 0.0);
+        const double diag = dm->geom_body_invw[ch][c_geom] + (pairc ? dm->geom_body_invw[c_sub >> 5][c_sub & 31] : (c_key >= 0 ? dm->key_body_invw[c_key] : 0.0));
         const double Rn = fmax(RP_MINVAL, (1 - imp) * diag / imp);
         cn.R[r] = r == 0 ? Rn : Rn / fmax(RP_MINVAL, dm->impratio);
         mu_row = mu;
@@ -1224,8 +1454,14 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
             s3 += jrow[d] * sm.v.pre.wsb[ch][cidx[d]];
           }
           if (c_key >= 0) { s2 += jk * sm.vak[c_key]; s3 += jk * sm.kfc[c_key]; }
-          cn.b[r] = s2 - arefr;
-          cn.f[r] = s3 - arefr;
+          if (pairc) {  // partial sums of this body's chain; the first record combines both after the barrier
+            cn.b[r] = s2; cn.f[r] = s3;
+            if (c_key == -3) cn.R[r] = sv;
+            hc_sv = sv; hc_B = B; hc_K = r == 0 ? K * imp * (c_dist - incl) : 0.0;
+          } else {
+            cn.b[r] = s2 - arefr;
+            cn.f[r] = s3 - arefr;
+          }
         }
         if (r == 0) {
           cn.hand = ch; cn.link = link; cn.key = c_key; cn.mu = mu;
@@ -1235,7 +1471,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         }
       }
       env_sync<NW, EPB>(bar_id);
-      if (rowt) {
+      if (rowt && !pairc) {
         Contact& cn = sm.u.con[c];
         // A[s2][r] = Jc_s2 Minv Jc_r^T + Jk_s2 Jk_r / Mk + R (diagonal)
         for (int s2 = 0; s2 < 3; s2++) {
@@ -1246,13 +1482,48 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
           cn.A[3 * s2 + r] = v;
         }
       }
+      if (HC && rowt && c_key == -2) {
+        // hand : hand contact, first record (P) with its partner (S = c + 1).  Reference acceleration from the row velocity
+        // of both bodies; b and the warm-start jar from both partial sums; the block from J = [J_P J_S]:
+        // A[s2][r] = J_s2 Minv J_r^T with Minv block diagonal per hand — the cross terms P x S only when both bodies belong
+        // to the same hand.
+        Contact& cn = sm.u.con[c];
+        Contact& cs = sm.u.con[c + 1];
+        const double sv = hc_sv + cs.R[r];
+        const double ar = -hc_B * sv - hc_K;
+        cn.b[r] = cn.b[r] + cs.b[r] - ar;
+        cn.f[r] = cn.f[r] + cs.f[r] - ar;
+        const bool same = cs.hand == ch;
+        const double* AP = sm.A[ch];
+        const double* AS = sm.A[cs.hand];
+        double uP[MAXD], uS[MAXD];
+        for (int d = 0; d < MAXD; d++) {
+          const int iP = cn.chain[d], iS = cs.chain[d];
+          double aP = u[d], aS = 0;
+          for (int e = 0; e < MAXD; e++) {
+            const int eP = cn.chain[e], eS = cs.chain[e];
+            const double jP = cn.Jc[r][e], jS = cs.Jc[r][e];  // zero beyond the chains
+            aS -= AS[iS * RS + eS] * jS;
+            if (same) { aP -= AP[iP * RS + eS] * jS; aS -= AP[iS * RS + eP] * jP; }
+          }
+          uP[d] = aP; uS[d] = aS;
+        }
+        for (int s2 = 0; s2 < 3; s2++) {
+          double v = 0;
+          for (int d = 0; d < MAXD; d++) v += cn.Jc[s2][d] * uP[d] + cs.Jc[s2][d] * uS[d];
+          if (r == s2) v += cn.R[r];
+          cn.A[3 * s2 + r] = v;
+        }
+        cs.R[r] = 0; cs.b[r] = 0;  // the second record carries no row of its own
+      }
       env_sync<NW, EPB>(bar_id);
-      if (rowt && r == 0) {
+      if (rowt && r == 0 && !(HC && c_key == -3)) {
         Contact& cn = sm.u.con[c];
         double jar[3] = {cn.f[0], cn.f[1], cn.f[2]}, D[3] = {1.0 / cn.R[0], 1.0 / cn.R[1], 1.0 / cn.R[2]};
         rp::elliptic_primal_force(jar, D, cn.mu * sqrt(cn.R[1] / cn.R[0]), cn.mu, cn.f);
       }
-      if (rowt && r == 1) {  // what the Gauss-Seidel update of this block needs in every sweep but that never changes
+      if (HC && rowt && r == 1 && c_key == -3) sm.u.con[c].dep = dep;
+      if (rowt && r == 1 && !(HC && c_key == -3)) {  // what the Gauss-Seidel update of this block needs in every sweep but that never changes
         Contact& cn = sm.u.con[c];
         double Ab[9];
         for (int k = 0; k < 9; k++) Ab[k] = cn.A[k];
@@ -1275,6 +1546,14 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
           firstc = mykey >= 0 && !samekey;
           sharedc = mykey >= 0 && samekey && sm.u.con[lane - 1].hand != myhand;
         }
+        bool crossc = false;
+        if (HC && lane < ncon && mykey == -3) {  // second record of a hand : hand contact: mirrors the warm-start force
+          Contact& cs = sm.u.con[lane];
+          const Contact& cp = sm.u.con[lane - 1];
+          cs.f[0] = cp.f[0]; cs.f[1] = cp.f[1]; cs.f[2] = cp.f[2];
+          crossc = cp.hand != myhand;
+        }
+        const unsigned xmask = HC ? __ballot_sync(FULL, crossc) : 0u;  // a cross-hand pair couples the two warps like a shared key
         const unsigned fmask = __ballot_sync(FULL, firstc);
         const unsigned smask = __ballot_sync(FULL, sharedc);
         const unsigned h0mask = __ballot_sync(FULL, myhand == 0), h1mask = __ballot_sync(FULL, myhand == 1);
@@ -1282,7 +1561,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         if (firstc) { const int slot = __popc(fmask & lt); sm.keyslot[mykey] = (signed char)slot; sm.ckown[slot] = (signed char)myhand; }
         if (myhand == 0) sm.hlist[0][__popc(h0mask & lt)] = (signed char)lane;
         if (myhand == 1) sm.hlist[H1][__popc(h1mask & lt)] = (signed char)lane;
-        if (lane == 0) { sm.nck = __popc(fmask); sm.shared_key = smask != 0; sm.nhc[0] = __popc(h0mask); sm.nhc[H1] = __popc(h1mask); }
+        if (lane == 0) { sm.nck = __popc(fmask); sm.shared_key = smask != 0 || xmask != 0; sm.nhc[0] = __popc(h0mask); sm.nhc[H1] = __popc(h1mask); }
       }
     }
     TICK(6)
@@ -1426,7 +1705,9 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     int iter = 0;
     if (HANDS) {
       PgsLane io = {fr_f, lm_f, va};
-      iter = pgs_solve(&sm, h, bar_id, ncon, maxiter, tol, dm->solver_scale, improvement0, fr_R, fr_b, fr_AR,
+      if (HC) iter = pgs_solve_hc(&sm, h, bar_id, ncon, maxiter, tol, dm->solver_scale, improvement0, fr_R, fr_b, fr_AR,
+                                  fr_on ? fr_loss : 0.0, lm_J, lm_R, lm_b, lm_AR, lm_mask, lsub, ldc, &io);
+      else iter = pgs_solve(&sm, h, bar_id, ncon, maxiter, tol, dm->solver_scale, improvement0, fr_R, fr_b, fr_AR,
                             fr_on ? fr_loss : 0.0, lm_J, lm_R, lm_b, lm_AR, lm_mask, lsub, ldc, &io
 #ifdef RP_PROFILE
                             , tacc, &tlast
@@ -1656,6 +1937,40 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       }
     }
   }
+  // forearm reward with hand : hand collisions enabled (piano_with_shadow_hands.py:251-259: has_collision between the two
+  // root bodies' geoms).  The forearm colliders are a box and a mesh, outside the narrowphase's coverage: the test is an
+  // oriented-box overlap of the box / the mesh's bounding box (separating axes) — an approximation of MuJoCo's convex
+  // contact test, conservative for the mesh.
+  bool forearms_touch = false;
+  if (HC) {
+    const int nf = dm->nfore[h];
+    const bool isf = lane < nf;
+    const int fi = isf ? dm->fore_ign[h][lane] : 0;
+    const int il = dm->ign_link[h][fi];
+    double lp[3], lq[4];
+#pragma unroll
+    for (int k = 0; k < 3; k++) lp[k] = shfl(xp[k], il);
+#pragma unroll
+    for (int k = 0; k < 4; k++) lq[k] = shfl(xq[k], il);
+    if (isf) {
+      double Rl[9], tmp[3], gp[3] = {dm->ign_pos[h][fi][0], dm->ign_pos[h][fi][1], dm->ign_pos[h][fi][2]};
+      rp::quat2mat(Rl, lq);
+      rp::mat_vec(tmp, Rl, gp);
+      double* o = &sm.wbuf[h][15 * lane];  // centre 3, rotation 9, half sizes 3
+      for (int k = 0; k < 3; k++) { o[k] = lp[k] + tmp[k]; o[12 + k] = dm->ign_half[h][fi][k]; }
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) o[3 + 3 * i + j] = Rl[3 * i] * dm->ign_mat[h][fi][j] + Rl[3 * i + 1] * dm->ign_mat[h][fi][3 + j] + Rl[3 * i + 2] * dm->ign_mat[h][fi][6 + j];
+    }
+    if (tid == 0) sm.nraw = 0;
+    env_sync<NW, EPB>(bar_id);
+    if (tid < dm->nfore[0] * dm->nfore[H1]) {
+      const int i = tid / dm->nfore[H1], j = tid - i * dm->nfore[H1];
+      const double *A_ = &sm.wbuf[0][15 * i], *B_ = &sm.wbuf[H1][15 * j];
+      if (rp::obb_overlap(A_, A_ + 3, A_ + 12, B_, B_ + 3, B_ + 12)) atomicOr(&sm.nraw, 1);
+    }
+    env_sync<NW, EPB>(bar_id);
+    forearms_touch = sm.nraw != 0;
+  }
   double reward = 0, terms[5] = {0, 0, 0, 0, 0}, discount = 1.0;
   int step_type = first ? RP_STEP_FIRST_ : RP_STEP_MID_;
   if (!first) {
@@ -1736,7 +2051,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         }
         r_fing = fn > 0 ? fsum / fn : 0.0;
       }
-      const double r_fore = dm->disable_forearm_reward ? 0.0 : 0.5;  // hands never collide with each other here
+      const double r_fore = dm->disable_forearm_reward ? 0.0 : ((HC && forearms_touch) ? 0.0 : 0.5);  // without hand : hand collisions the forearms never touch
       terms[0] = r_key; terms[1] = r_sus; terms[2] = r_en; terms[3] = r_fing; terms[4] = r_fore;
       reward = r_key + r_sus + r_en;
       if (!dm->disable_fingering_reward) reward += r_fing;
@@ -1858,23 +2173,24 @@ static int current_device_slot() {
   return dev >= 0 && dev < 64 ? dev : 0;
 }
 
-template <int EPB>
+template <int EPB, bool HC>
 static cudaError_t launch_hands(const RpKernelArgs& a, cudaStream_t stream) {
   static bool configured[64] = {};
   const int dev = current_device_slot();
   const size_t smem = kSmemStride * EPB + kSchedBytes;
   if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(rp_step_kernel<2, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rp_step_kernel<2, EPB, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
-  rp_step_kernel<2, EPB><<<(a.nenv + EPB - 1) / EPB, 64 * EPB, smem, stream>>>(a);
+  rp_step_kernel<2, EPB, HC><<<(a.nenv + EPB - 1) / EPB, 64 * EPB, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
 // block_envs: environments per thread block for the hands kernel (1 or RP_EPB; 0 = choose by batch size: the
 // phase-locked RP_EPB-environment blocks need at least two full waves of blocks to pay off).
-cudaError_t rp_launch_step(const RpKernelArgs& a, int nhand, cudaStream_t stream, int block_envs) {
+// hand_collisions: the model's hand geoms may collide with each other (RpDevModel::hc_enabled): the HC instantiation.
+cudaError_t rp_launch_step(const RpKernelArgs& a, int nhand, cudaStream_t stream, int block_envs, int hand_collisions) {
   if (nhand == 2) {
     int epb = block_envs;
     if (epb <= 0) {
@@ -1883,16 +2199,17 @@ cudaError_t rp_launch_step(const RpKernelArgs& a, int nhand, cudaStream_t stream
       epb = a.nenv >= 2 * sms * 6 ? RP_EPB : 1;  // two waves at six environments per SM
     }
     if (epb != 1 && epb != RP_EPB) return cudaErrorInvalidValue;
-    return epb == 1 ? launch_hands<1>(a, stream) : launch_hands<RP_EPB>(a, stream);
+    if (hand_collisions) return epb == 1 ? launch_hands<1, true>(a, stream) : launch_hands<RP_EPB, true>(a, stream);
+    return epb == 1 ? launch_hands<1, false>(a, stream) : launch_hands<RP_EPB, false>(a, stream);
   }
   static bool configured[64] = {};
   const int dev = current_device_slot();
   const size_t smem = kSmemStride;
   if (!configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(rp_step_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rp_step_kernel<1, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
-  rp_step_kernel<1, 1><<<a.nenv, 32, smem, stream>>>(a);
+  rp_step_kernel<1, 1, false><<<a.nenv, 32, smem, stream>>>(a);
   return cudaGetLastError();
 }

@@ -66,7 +66,7 @@ struct RpKernelArgs {
 };
 
 size_t rp_kernel_smem_bytes();
-cudaError_t rp_launch_step(const RpKernelArgs& a, int nhand, cudaStream_t stream, int block_envs);
+cudaError_t rp_launch_step(const RpKernelArgs& a, int nhand, cudaStream_t stream, int block_envs, int hand_collisions);
 cudaError_t rp_launch_order(const int32_t* work, int32_t* order, int n, cudaStream_t stream);
 // optimal-transport fingering reward (rp_task_kernels.cu; per-environment scratch: RP_OT_SCRATCH_DOUBLES of rp_task.cuh)
 cudaError_t rp_launch_ot_fingering(const RpDevModel* dm, int nenv, const int32_t* t_idx, const double* qpos, int nvtot,

@@ -179,6 +179,92 @@ RP_HD double sphere_box(const double* c, double r, const double* s, double* n, d
   }
   return dist;
 }
+// ---- hand geom : hand geom narrowphase (spheres and capsules): MuJoCo's analytic routines
+// (engine_collision_primitive.c: mjraw_SphereSphere, mjc_SphereCapsule, mjraw_CapsuleCapsule), restated.
+// A capsule is (centre, unit axis, radius, half length); outputs: signed distance, unit normal from
+// geom 1 to geom 2, contact point mid-way between the surfaces.  Return the number of contacts.
+RP_HD int sphere_sphere(double margin, const double* p1, const double* z1, double r1, const double* p2, const double* z2, double r2,
+                        double* dist, double* normal, double* pos) {
+  double dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  const double cd2 = dot3(dif, dif), mind = margin + r1 + r2;
+  if (cd2 > mind * mind) return 0;
+  double len = sqrt(cd2);
+  if (len < RP_MINVAL) { dif[0] = 1; dif[1] = 0; dif[2] = 0; len = 0; }
+  else for (int k = 0; k < 3; k++) dif[k] /= len;
+  *dist = len - r1 - r2;
+  for (int k = 0; k < 3; k++) normal[k] = dif[k];
+  if (len < RP_MINVAL) {  // coincident centres: cross product of the z axes, or x
+    cross3(normal, z1, z2);
+    const double nn = sqrt(dot3(normal, normal));
+    if (nn < RP_MINVAL) { normal[0] = 1; normal[1] = 0; normal[2] = 0; }
+    else for (int k = 0; k < 3; k++) normal[k] /= nn;
+  }
+  for (int k = 0; k < 3; k++) pos[k] = p1[k] + normal[k] * (r1 + 0.5 * *dist);
+  return 1;
+}
+RP_HD double clipd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+RP_HD int capsule_capsule(double margin, const double* p1, const double* ax1, double r1, double h1, const double* p2, const double* ax2,
+                          double r2, double h2, double* dist, double* normal, double* pos) {  // outputs [2]
+  const double dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+  const double ma = dot3(ax1, ax1), mb = -dot3(ax1, ax2), mc = dot3(ax2, ax2);
+  const double u = -dot3(ax1, dif), v = dot3(ax2, dif);
+  const double det = ma * mc - mb * mb;
+  double v1[3], v2[3];
+  if (fabs(det) >= RP_MINVAL) {
+    double x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+    if (x1 > h1) { x1 = h1; x2 = (v - mb * h1) / mc; }
+    else if (x1 < -h1) { x1 = -h1; x2 = (v + mb * h1) / mc; }
+    if (x2 > h2) { x2 = h2; x1 = clipd((u - mb * h2) / ma, -h1, h1); }
+    else if (x2 < -h2) { x2 = -h2; x1 = clipd((u + mb * h2) / ma, -h1, h1); }
+    for (int k = 0; k < 3; k++) { v1[k] = p1[k] + ax1[k] * x1; v2[k] = p2[k] + ax2[k] * x2; }
+    return sphere_sphere(margin, v1, ax1, r1, v2, ax2, r2, dist, normal, pos);
+  }
+  int n = 0;  // parallel axes: the ends of capsule 1 against segment 2, then the ends of capsule 2 against segment 1; at most two
+  for (int pass = 0; pass < 4 && n < 2; pass++) {
+    double x1, x2;
+    if (pass == 0) { x1 = h1; x2 = clipd((v - mb * h1) / mc, -h2, h2); }
+    else if (pass == 1) { x1 = -h1; x2 = clipd((v + mb * h1) / mc, -h2, h2); }
+    else if (pass == 2) { x2 = h2; x1 = clipd((u - mb * h2) / ma, -h1, h1); }
+    else { x2 = -h2; x1 = clipd((u + mb * h2) / ma, -h1, h1); }
+    for (int k = 0; k < 3; k++) { v1[k] = p1[k] + ax1[k] * x1; v2[k] = p2[k] + ax2[k] * x2; }
+    n += sphere_sphere(margin, v1, ax1, r1, v2, ax2, r2, dist + n, normal + 3 * n, pos + 3 * n);
+  }
+  return n;
+}
+// One pair; geom 1 must not be a capsule when geom 2 is a sphere (mj_collideGeoms orders by type).  h = 0: sphere.
+RP_HD int sphere_capsule_pair(double margin, const double* p1, const double* z1, double r1, double h1, const double* p2, const double* z2,
+                              double r2, double h2, double* dist, double* normal, double* pos) {
+  if (h1 == 0 && h2 == 0) return sphere_sphere(margin, p1, z1, r1, p2, z2, r2, dist, normal, pos);
+  if (h1 == 0) {  // mjc_SphereCapsule: nearest point of the segment, then sphere : sphere
+    const double vec[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+    const double x = clipd(dot3(z2, vec), -h2, h2);
+    const double q[3] = {p2[0] + z2[0] * x, p2[1] + z2[1] * x, p2[2] + z2[2] * x};
+    return sphere_sphere(margin, p1, z1, r1, q, z2, r2, dist, normal, pos);
+  }
+  return capsule_capsule(margin, p1, z1, r1, h1, p2, z2, r2, h2, dist, normal, pos);
+}
+// separating-axis test of two oriented boxes (centre, rotation with the box axes as columns, row major; half sizes)
+RP_HD bool obb_overlap(const double* ca, const double* Ra, const double* ha, const double* cb, const double* Rb, const double* hb) {
+  double R[9], AR[9], t[3];
+  const double d[3] = {cb[0] - ca[0], cb[1] - ca[1], cb[2] - ca[2]};
+  for (int i = 0; i < 3; i++) {
+    t[i] = d[0] * Ra[i] + d[1] * Ra[3 + i] + d[2] * Ra[6 + i];
+    for (int j = 0; j < 3; j++) {
+      R[3 * i + j] = Ra[i] * Rb[j] + Ra[3 + i] * Rb[3 + j] + Ra[6 + i] * Rb[6 + j];
+      AR[3 * i + j] = fabs(R[3 * i + j]) + 1e-12;
+    }
+  }
+  for (int i = 0; i < 3; i++) if (fabs(t[i]) > ha[i] + hb[0] * AR[3 * i] + hb[1] * AR[3 * i + 1] + hb[2] * AR[3 * i + 2]) return false;
+  for (int j = 0; j < 3; j++)
+    if (fabs(t[0] * R[j] + t[1] * R[3 + j] + t[2] * R[6 + j]) > hb[j] + ha[0] * AR[j] + ha[1] * AR[3 + j] + ha[2] * AR[6 + j]) return false;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const double ra = ha[i1] * AR[3 * i2 + j] + ha[i2] * AR[3 * i1 + j], rb = hb[j1] * AR[3 * i + j2] + hb[j2] * AR[3 * i + j1];
+      if (fabs(t[i2] * R[3 * i1 + j] - t[i1] * R[3 * i2 + j]) > ra + rb) return false;
+    }
+  return true;
+}
 RP_HD double point_box_d2(const double* c, const double* s) {
   double d2 = 0;
   for (int k = 0; k < 3; k++) {

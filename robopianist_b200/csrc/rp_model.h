@@ -14,6 +14,7 @@
 #define RP_MAXD 10    // max chain length (depth+1)
 #define RP_NGH 20     // colliding primitive geoms per hand (capsules / spheres), max
 #define RP_NAH 24     // actuators per hand, max
+#define RP_HC_MAXPAIRS 640  // hand geom pairs that may collide with each other (sphere / capsule pairs of both hands: 596)
 #define RP_NIGN 32    // hand colliders outside the narrowphase's coverage (per hand), max
 #define RP_NSITE 5    // fingertip sites per hand
 #ifndef RP_MAXCON
@@ -100,6 +101,11 @@ struct RpDevModel {
   // observation order of hand joints (joints_pos observable)
   int obs_dof[RP_NHMAX][RP_NL];
   int nobs[RP_NHMAX];  // observed (= real) dofs per hand; link slots beyond are inert padding
+  // ---- hand : hand collisions (disable_hand_collisions=False): sphere / capsule geom pairs that pass mj_collision's
+  // body-pair filters, in MuJoCo's pair order; a | b << 8 with a = hand1 * RP_NGH + geom1 < b = hand2 * RP_NGH + geom2
+  int hc_enabled, hc_npair;
+  uint16_t hc_pairs[RP_HC_MAXPAIRS];
+  int nfore[RP_NHMAX], fore_ign[RP_NHMAX][2];  // the forearm's colliders among ign_* (forearm reward: oriented-box overlap)
   // ---- task ----
   int T, lookahead, wrong_press_termination, disable_fingering_reward, disable_forearm_reward, reward_type;
   int obs_dim, act_dim;

@@ -414,10 +414,6 @@ def compile_scene(
         raise NotImplementedError(
             "mesh fingertip colliders (convex-mesh narrowphase) are not implemented; pass "
             "primitive_fingertip_collisions=True (reference kwarg, tasks/base.py:101)")
-    if hands and not disable_hand_collisions:
-        raise NotImplementedError(
-            "hand-hand / hand-self collisions are not implemented; pass "
-            "disable_hand_collisions=True (reference kwarg, piano_with_shadow_hands.py:60)")
     asset_dir = Path(asset_dir) if asset_dir is not None else DEFAULT_ASSET_DIR
     b = _Builder()
     # key solref hardened to (2*dt, 1) (base.py:60-66)
@@ -571,6 +567,10 @@ def compile_scene(
         A["hand_obs_dofid"] = np.zeros((0, 0), np.int32)
         A["hand_actuatorid"] = np.zeros((0, 0), np.int32)
         A["hand_rootbody"] = np.zeros(0, np.int32)
+    # <contact><exclude> body pairs of the hand models (right_hand.xml:299-302); only matter when hand geoms may
+    # collide with each other (disable_hand_collisions=False)
+    ex = [pair for h in hand_info for pair in h["excludes"]] if hands else []
+    A["exclude_bodies"] = np.array(ex, np.int32).reshape(-1, 2)
     A["opt_gravity"] = np.array([0.0, 0.0, -9.81])
     A["qpos0"] = np.zeros(nv)
 

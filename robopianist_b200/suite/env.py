@@ -84,10 +84,6 @@ def _unsupported(kw: Mapping[str, Any]):
         raise NotImplementedError(
             "mesh fingertip colliders need a convex-mesh narrowphase (SURVEY.md §8(f) row 1); pass "
             "task_kwargs=dict(primitive_fingertip_collisions=True) — the north_star configuration")
-    if not kw["disable_hand_collisions"]:
-        raise NotImplementedError(
-            "hand-hand contacts are not implemented (SURVEY.md §8(f) row 1); pass "
-            "task_kwargs=dict(disable_hand_collisions=True)")
     bad = [d for d in kw["forearm_dofs"] if d not in ("forearm_tx", "forearm_ty")]
     if bad:  # shadow_hand.py:41-52 also lists rotational forearm dofs; only the two slides are restated
         raise NotImplementedError(f"forearm_dofs {bad} are not implemented (forearm_tx / forearm_ty are)")
@@ -186,6 +182,7 @@ class BatchedPianoEnv:
                                      control_timestep=self.control_timestep,
                                      forearm_dofs=tuple(kw["forearm_dofs"]),
                                      reduced_action_space=bool(kw["reduced_action_space"]),
+                                     disable_hand_collisions=bool(kw["disable_hand_collisions"]),
                                      attachment_yaw=float(kw["attachment_yaw"]))
         n_ign = int(self.flat.meta.get("n_ignored_colliders", 0))
         if hands and n_ign:
@@ -194,7 +191,11 @@ class BatchedPianoEnv:
                 f"{n_ign} hand colliders of the reference model (palm / knuckle / wrist boxes and cylinders, forearm "
                 "mesh) are outside the narrowphase's coverage and do not collide with the piano; environments in "
                 "which one of them comes within reach of the piano are flagged (rp_get_diag flags bit 3, "
-                "BatchedPianoEnv.uncovered_collider_flags())", RuntimeWarning, stacklevel=3)
+                "BatchedPianoEnv.uncovered_collider_flags())"
+                + ("" if kw["disable_hand_collisions"] else "; with hand collisions enabled the sphere / capsule geoms of the fingers "
+                   "and thumbs collide with each other (within a hand and across the hands), pairs that involve one of the "
+                   "uncovered colliders do not, and the forearm reward tests the forearms' oriented boxes"),
+                RuntimeWarning, stacklevel=3)
         self.model = native.Model(
             self.flat, goal, fing, kind=0 if hands else 1, iterations=iterations, tolerance=tolerance,
             n_steps_lookahead=L, wrong_press_termination=bool(kw["wrong_press_termination"]),

@@ -13,7 +13,11 @@ configs = [("piano_with_shadow_hands", False, {}), ("piano_with_shadow_hands", T
            # test fixtures of the other model-changing kwargs (tasks/base.py:102-107)
            ("piano_with_shadow_hands", True, dict(attachment_yaw=10.0)),
            ("piano_with_shadow_hands", True, dict(forearm_dofs=("forearm_tx",))),
-           ("piano_with_shadow_hands", True, dict(forearm_dofs=(), reduced_action_space=True))]
+           ("piano_with_shadow_hands", True, dict(forearm_dofs=(), reduced_action_space=True)),
+           # hand geoms may collide with each other (the reference's default: disable_hand_collisions=False)
+           ("piano_with_shadow_hands", True, dict(disable_hand_collisions=False)),
+           ("piano_with_shadow_hands", False, dict(disable_hand_collisions=False)),
+           ("piano_with_shadow_hands", True, dict(disable_hand_collisions=False, reduced_action_space=True))]
 for task, gc, extra in configs:
     fm = C.compile_scene(task=task, gravity_compensation=gc, **extra)
     path = cache._DIR / cache._name(task, gc, 0.005, 0.05, **extra)

@@ -220,3 +220,86 @@ def test_assignment_solver_and_ot_reward_against_scipy(tmp_path):
         ri, ci = linear_sum_assignment(dist)
         ref = float(np.mean(tolerance(dist[ri, ci], (0, 0.01), 0.1)))
         assert abs(got - ref) < 1e-14, (trial, K, got, ref)
+
+
+def _run_pairs(tmp_path, lines):
+    exe = tmp_path / "hd_pairs"
+    subprocess.check_call(["g++", "-O2", f"-I{ROOT / 'robopianist_b200' / 'csrc'}", "-o", str(exe),
+                           str(ROOT / "tests" / "csrc" / "hd_pairs.cpp")])
+    out = subprocess.run([str(exe)], input="\n".join(lines) + "\n", capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return out.stdout.strip().split("\n")
+
+
+def test_hand_pair_narrowphase_is_geometrically_consistent(tmp_path):
+    """sphere / capsule pairs (rp::sphere_capsule_pair, the kernel's hand : hand narrowphase): the reported distance is the
+    brute-force distance between the two segments minus the radii, the normal is the unit vector between the closest
+    points (geom 1 -> geom 2), the position lies mid-way between the surfaces; nothing beyond the margin."""
+    rng = np.random.default_rng(4)
+    cases, lines = [], []
+    for i in range(400):
+        kind = i % 3  # sphere-sphere, sphere-capsule, capsule-capsule
+        r1, r2 = rng.uniform(0.005, 0.015, 2)
+        h1 = 0.0 if kind < 2 else rng.uniform(0.005, 0.03)
+        h2 = 0.0 if kind < 1 else rng.uniform(0.005, 0.03)
+        z1, z2 = rng.normal(size=3), rng.normal(size=3)
+        z1 /= np.linalg.norm(z1); z2 /= np.linalg.norm(z2)
+        p1 = rng.normal(size=3) * 0.01
+        p2 = p1 + rng.normal(size=3) * 0.02
+        margin = 0.002 if i % 5 == 0 else 0.0
+        cases.append((margin, p1, z1, r1, h1, p2, z2, r2, h2))
+        lines.append("P " + " ".join(repr(float(x)) for x in np.hstack([margin, p1, z1, r1, h1, p2, z2, r2, h2])))
+    outs = _run_pairs(tmp_path, lines)
+    hits = 0
+    ts = np.linspace(-1, 1, 2001)
+    for (margin, p1, z1, r1, h1, p2, z2, r2, h2), line in zip(cases, outs):
+        v = [float(x) for x in line.split()]
+        a = p1[None] + ts[:, None] * h1 * z1[None]
+        b = p2[None] + ts[:, None] * h2 * z2[None]
+        d2 = ((a[:, None, :] - b[None, :, :]) ** 2).sum(-1) if h1 > 0 else ((a[:1, None, :] - b[None, :, :]) ** 2).sum(-1)
+        ia, ib = np.unravel_index(np.argmin(d2), d2.shape)
+        dmin = np.sqrt(d2[ia, ib])
+        if dmin - r1 - r2 > margin + 1e-4:
+            assert int(v[0]) == 0
+            continue
+        if int(v[0]) == 0:
+            assert dmin - r1 - r2 > margin - 1e-4
+            continue
+        hits += 1
+        dist, n, pos = v[1], np.array(v[2:5]), np.array(v[5:8])
+        assert abs(dist - (dmin - r1 - r2)) < 2e-5, (dist, dmin - r1 - r2)
+        assert abs(np.linalg.norm(n) - 1) < 1e-12
+        want = (b[ib] - a[ia]) / dmin
+        assert np.abs(n - want).max() < 5e-2 or dmin < 1e-4
+        # mid-way between the surfaces along the normal, seen from both bodies' closest points
+        assert np.abs(pos - (a[ia] + n * (r1 + 0.5 * dist))).max() < 1e-4
+    assert hits > 100
+
+
+def test_obb_overlap_matches_a_plain_separating_axis_test(tmp_path):
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(9)
+    cases, lines = [], []
+    for i in range(300):
+        Ra, Rb = Rotation.random(random_state=rng.integers(1 << 30)).as_matrix(), Rotation.random(random_state=rng.integers(1 << 30)).as_matrix()
+        ha, hb = rng.uniform(0.01, 0.05, 3), rng.uniform(0.01, 0.05, 3)
+        ca = rng.normal(size=3) * 0.01
+        cb = ca + rng.normal(size=3) * 0.05
+        cases.append((ca, Ra, ha, cb, Rb, hb))
+        lines.append("B " + " ".join(repr(float(x)) for x in np.hstack([ca, Ra.ravel(), ha, cb, Rb.ravel(), hb])))
+    outs = _run_pairs(tmp_path, lines)
+
+    def overlap(ca, Ra, ha, cb, Rb, hb):
+        axes = [Ra[:, i] for i in range(3)] + [Rb[:, j] for j in range(3)] + [np.cross(Ra[:, i], Rb[:, j]) for i in range(3) for j in range(3)]
+        for ax in axes:
+            n = np.linalg.norm(ax)
+            if n < 1e-9:
+                continue
+            ax = ax / n
+            if abs(ax @ (cb - ca)) > sum(ha[i] * abs(ax @ Ra[:, i]) for i in range(3)) + sum(hb[j] * abs(ax @ Rb[:, j]) for j in range(3)):
+                return False
+        return True
+
+    got = [int(x) for x in outs]
+    want = [int(overlap(*c)) for c in cases]
+    assert got == want and 30 < sum(want) < 270

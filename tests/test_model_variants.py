@@ -18,6 +18,8 @@ VARIANTS = {
     "yaw10": dict(attachment_yaw=10.0),
     "fdx": dict(forearm_dofs=("forearm_tx",)),
     "ras_fd": dict(forearm_dofs=(), reduced_action_space=True),
+    "hc": dict(disable_hand_collisions=False),
+    "hc_ras": dict(disable_hand_collisions=False, reduced_action_space=True),
 }
 
 
@@ -99,8 +101,7 @@ def test_unsupported_kwargs_still_raise():
     E._unsupported(dict(kw, reduced_action_space=True, attachment_yaw=5.0, randomize_hand_positions=True))  # accepted now
     with pytest.raises(NotImplementedError):
         E._unsupported(dict(kw, primitive_fingertip_collisions=False))
-    with pytest.raises(NotImplementedError):
-        E._unsupported(dict(kw, disable_hand_collisions=False))
+    E._unsupported(dict(kw, disable_hand_collisions=False))  # accepted now (sphere / capsule pairs collide)
     with pytest.raises(NotImplementedError):
         E._unsupported(dict(kw, forearm_dofs=("forearm_roll",)))
 
@@ -114,3 +115,44 @@ def test_compile_matches_cached_variants():
         cached = cache.load_scene(gravity_compensation=True, **kw)
         for k, v in fresh.arrays.items():
             assert np.array_equal(v, cached.arrays[k]), (name, k)
+
+
+def test_hand_collision_scene_and_pair_filters():
+    """disable_hand_collisions=False (the reference default; piano_with_shadow_hands.py:476-489 is what switches it off):
+    hand geoms keep contype = conaffinity = 1; the oracle's pair list obeys mj_collision's body-pair filters."""
+    import ctypes as Ct
+    fm = cache.load_scene(gravity_compensation=True, disable_hand_collisions=False)
+    off = cache.load_scene(gravity_compensation=True)
+    hand = fm.geom_hand >= 0
+    assert (fm.geom_contype[hand] == 1).all() and (fm.geom_conaffinity[hand] == 1).all()
+    assert (off.geom_contype[hand] == 1).all() and (off.geom_conaffinity[hand] == 0).all()
+    names = fm.meta["body_names"]
+    ex = {tuple(sorted((names[a].split("/")[1], names[b].split("/")[1]))) for a, b in fm.arrays["exclude_bodies"]}
+    assert ex == {("rh_forearm", "rh_wrist"), ("rh_thmiddle", "rh_thproximal"), ("lh_forearm", "lh_wrist"), ("lh_thmiddle", "lh_thproximal")}
+    om = O.OracleModel(fm)
+    L = O.lib()
+    L.orc_npair.argtypes = [Ct.c_void_p]; L.orc_pair_get.argtypes = [Ct.c_void_p, Ct.c_int, Ct.POINTER(Ct.c_int), Ct.POINTER(Ct.c_int)]
+    n = L.orc_npair(om.ptr)
+    pairs = []
+    for i in range(n):
+        a, b = Ct.c_int(), Ct.c_int()
+        L.orc_pair_get(om.ptr, i, Ct.byref(a), Ct.byref(b))
+        pairs.append((a.value, b.value))
+    assert pairs == sorted(pairs) and len(set(pairs)) == n
+    cov = [g for g in range(fm.meta["ngeom"]) if fm.geom_hand[g] >= 0 and fm.geom_collide[g]]
+    assert len(cov) == 36
+    parent = fm.body_parentid
+    want = 0
+    for i, g1 in enumerate(cov):
+        for g2 in cov[i + 1:]:
+            b1, b2 = fm.geom_bodyid[g1], fm.geom_bodyid[g2]
+            ok = b1 != b2 and parent[b1] != b2 and parent[b2] != b1  # every hand body of this model has a joint: weld == body
+            ok = ok and tuple(sorted((names[b1].split("/")[1], names[b2].split("/")[1]))) not in ex
+            want += ok
+            assert ((g1, g2) in pairs) == ok, (fm.meta["geom_names"][g1], fm.meta["geom_names"][g2])
+    assert n == want == 596
+    assert L.orc_npair(O.OracleModel(off).ptr) == 0
+    # with the reduced action space three bodies per hand are welded to their parents: more filtered pairs
+    ras = cache.load_scene(gravity_compensation=True, disable_hand_collisions=False, reduced_action_space=True)
+    n_ras = L.orc_npair(O.OracleModel(ras).ptr)
+    assert 0 < n_ras < n
