@@ -5,6 +5,8 @@ behaviour itself."""
 import numpy as np
 import pytest
 
+from robopianist_b200 import native
+
 from robopianist_b200 import suite
 from robopianist_b200.music import trajectory
 from robopianist_b200.music.sequence import NoteSeq
@@ -38,8 +40,10 @@ def test_unsupported_kwargs_fail_loudly():
     name = suite.DEBUG[0]
     with pytest.raises(NotImplementedError):
         suite.load(name)  # reference default = mesh fingertips: not implemented, must not be silently replaced
-    with pytest.raises(NotImplementedError):
-        suite.load(name, task_kwargs=dict(primitive_fingertip_collisions=True))  # hand-hand contacts
+    try:  # hand collisions enabled (the reference default) are accepted: past the kwargs check the only obstacle is the device
+        suite.load(name, task_kwargs=dict(primitive_fingertip_collisions=True)).close()
+    except native.NativeError as e:
+        assert "CUDA" in str(e)
     with pytest.raises(TypeError):
         suite.load(name, task_kwargs=dict(KW, no_such_kwarg=1))
     with pytest.raises(NotImplementedError):
