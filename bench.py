@@ -34,7 +34,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 ENVS_PER_GPU = 4096
-NCU_DRAM_BYTES_PER_LAUNCH = 64.6e6  # profiles/r02_ncu_final.csv: dram__bytes_read.sum (23.4 MB) + dram__bytes_write.sum (41.2 MB) of one captured launch, 4096 envs
+NCU_DRAM_BYTES_PER_LAUNCH = 49.6e6  # profiles/r02_ncu_end.csv: dram__bytes_read.sum (24.1 MB) + dram__bytes_write.sum (25.5 MB) of one captured launch, 4096 envs
 SONG = "TwinkleTwinkleRousseau"
 METRIC = "env-steps/sec at 4096 envs/GPU (piano_with_shadow_hands, 10 substeps/step)"
 
@@ -172,6 +172,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-episode", action="store_true", help="skip the second measurement with episode phases staggered across the batch")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: whatever else a library writes there (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, ...) is sent to stderr; the line itself goes out through the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -203,7 +212,7 @@ def main():
                                  "single_core_value": r.get("single_core_value"), "segment_spread": r["spread"],
                                  "note": "CPU restatement of the reference's MuJoCo path (MuJoCo itself is not installable here and would be several times faster per core)"},
                 "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -359,7 +368,7 @@ def main():
                          "fp64_peak_source": "DFMA issue rate measured on B200 (scratch/ubench3.cu: 1.8 warp-instr/clk/SM x 148 SMs x 1.965 GHz)",
                          "fp64_frac": fl * N / (kernel_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
                          "arithmetic_intensity_flop_per_byte": fl / abytes})
-    print(json.dumps(line))
+    emit(line)
     env.close()
     if world > 1:
         dist.destroy_process_group()

@@ -575,21 +575,38 @@ __device__ __noinline__ int pgs_solve_hc(Smem* smp, const int h, const int bar_i
           if (df0 != 0.0 || df1 != 0.0 || df2 != 0.0) {
             if (key >= 0) sm.vak[key] = vak + (jk0 * df0 + jk1 * df1 + jk2 * df2) * invMk;
             // hand side, per record of this hand: w = Jc^T df on the chain, va += Minv[:, chain] w
+            // (the first RP_NU records have M^-1 Jc^T in shared memory, lane-major: three loads instead of the chain walk)
             if (mineP) {
-              const double w = j0 * df0 + j1 * df1 + j2 * df2;
-              const int dep = depq & 0xff;
-              double acc = 0;
+#if RP_NU > 0
+              if (c < RP_NU) {
+                const double* Uc = &sm.v.U[c][0][lc];
+                va += fma(Uc[2 * NL], df2, fma(Uc[NL], df1, Uc[0] * df0));
+              } else
+#endif
+              {
+                const double w = j0 * df0 + j1 * df1 + j2 * df2;
+                const int dep = depq & 0xff;
+                double acc = 0;
 #pragma unroll 1
-              for (int d = 0; d <= dep; d++) { const int j = cn.chain[d]; acc -= Ah[j * RS + lc] * shfl(w, j); }
-              va += acc;
+                for (int d = 0; d <= dep; d++) { const int j = cn.chain[d]; acc -= Ah[j * RS + lc] * shfl(w, j); }
+                va += acc;
+              }
             }
             if (mineS) {
-              const double w = k0 * df0 + k1 * df1 + k2 * df2;
-              const int dep = cs.dep & 0xff;
-              double acc = 0;
+#if RP_NU > 0
+              if (c + 1 < RP_NU) {
+                const double* Uc = &sm.v.U[c + 1][0][lc];
+                va += fma(Uc[2 * NL], df2, fma(Uc[NL], df1, Uc[0] * df0));
+              } else
+#endif
+              {
+                const double w = k0 * df0 + k1 * df1 + k2 * df2;
+                const int dep = cs.dep & 0xff;
+                double acc = 0;
 #pragma unroll 1
-              for (int d = 0; d <= dep; d++) { const int j = cs.chain[d]; acc -= Ah[j * RS + lc] * shfl(w, j); }
-              va += acc;
+                for (int d = 0; d <= dep; d++) { const int j = cs.chain[d]; acc -= Ah[j * RS + lc] * shfl(w, j); }
+                va += acc;
+              }
             }
           }
           __syncwarp();

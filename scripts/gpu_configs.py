@@ -16,16 +16,17 @@ sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 import helpers  # noqa: E402
 
 
-def run(task, song, N, steps, iterations=None, warm=3, seed=12345):
-    fm, model, b = helpers.make_native(task, song=song, nenv=N)
+def run(task, song, N, steps, iterations=None, warm=3, seed=12345, scene_kw=None):
+    fm, model, b = helpers.make_native(task, song=song, nenv=N, scene_kw=scene_kw)
     if iterations is not None:
         b.set_option(iterations=iterations)
     lo = np.concatenate([fm.actuator_ctrlrange[:, 0], [0.0]]); hi = np.concatenate([fm.actuator_ctrlrange[:, 1], [1.0]])
     rng = np.random.default_rng(seed)
     total = warm + steps
     if task == "piano_with_shadow_hands":
-        base = helpers.twinkle_actions()
-        acts = np.stack([np.clip(base[t % 158] + rng.normal(0, 0.05, (N, 45)) * (hi - lo) / 2, lo, hi) for t in range(total)])
+        from robopianist_b200.scene import cache
+        base = helpers.reduced_actions(cache.load_scene(gravity_compensation=True), fm, helpers.twinkle_actions())
+        acts = np.stack([np.clip(base[t % 158] + rng.normal(0, 0.05, (N, model.act_dim)) * (hi - lo) / 2, lo, hi) for t in range(total)])
     else:
         acts = rng.uniform(lo, hi, size=(total, N, model.act_dim))
     a = torch.tensor(acts, dtype=torch.float64, device="cuda")
@@ -46,7 +47,8 @@ def run(task, song, N, steps, iterations=None, warm=3, seed=12345):
     q = b.get_state()[0]
     out = dict(task=task, song=song, envs=N, pgs_iterations=iterations if iterations is not None else int(fm.meta.get("iterations", 50)),
                steps=steps, ms_per_step=ms, env_steps_per_s=N / ms * 1e3, mean_sweeps_last_substep=float(d["niter"].mean()),
-               mean_contacts=float(d["ncon"].mean()), max_contacts=int(d["ncon"].max()), flagged_envs=int((d["flags"] != 0).sum()))
+               mean_contacts=float(d["ncon"].mean()), max_contacts=int(d["ncon"].max()), flagged_envs=int(((d["flags"] & 7) != 0).sum()),
+               scene=dict(scene_kw or {}))
     b.close()
     return out, q
 
@@ -64,3 +66,8 @@ if __name__ == "__main__":
             ref_q = q
         r["qpos_linf_vs_100_iterations"] = float(np.abs(q - ref_q).max())
         print(json.dumps(dict(config=5, **r)), flush=True)
+    # beyond BASELINE.json: the same 4096-env replay with the hand geoms colliding with each other (the reference's default)
+    # and in the reference's RL training configuration (reduced action space + hand collisions + gravity compensation)
+    for kw in (dict(disable_hand_collisions=False), dict(disable_hand_collisions=False, reduced_action_space=True)):
+        r, _ = run("piano_with_shadow_hands", "TwinkleTwinkleRousseau", 4096, steps, iterations=50, scene_kw=kw)
+        print(json.dumps(dict(config="3+" + "+".join(sorted(kw)), **r)), flush=True)

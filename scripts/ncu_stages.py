@@ -3,24 +3,48 @@
 Inputs: `ncu -i X.ncu-rep --page source --csv --print-source sass > src.csv`; `nvdisasm --print-line-info kernels.cubin >
 k.sass` (same build).  An instruction is charged to the outermost rp_kernels.cu line of its inline chain; the two
 __noinline__ functions (sweep_inverse, pgs_solve) are split by their own source lines.
-usage: ncu_stages.py src.csv k.sass kernel_mangled_prefix"""
+usage: ncu_stages.py src.csv k.sass kernel_mangled_prefix rp_kernels.cu"""
 import csv, re, sys
 from collections import defaultdict
 
-src_csv, dis, kname = sys.argv[1:4]
-KERNEL = [(431, 600, "prologue + phase barrier"), (601, 676, "kinematics"), (677, 769, "RNE / CRB / scatter M"), (770, 853, "actuation, smooth, key rows"),
-          (854, 889, "hand friction / limit row setup"), (890, 1047, "collision"), (1048, 1201, "contact rows + lists"),
-          (1202, 1333, "warm start, U, cost"), (1334, 1362, "solver call"), (1363, 1445, "dual->primal, Euler"), (1446, 1487, "integrate, midi"),
-          (1488, 1525, "store state"), (1526, 1745, "task epilogue")]
-PGS = [(229, 261, "pgs: prologue"), (262, 294, "pgs: friction rows"), (295, 311, "pgs: coupled key rows"), (312, 328, "pgs: hand limit rows"),
-       (329, 412, "pgs: contacts"), (413, 425, "pgs: per-sweep barrier + test")]
+src_csv, dis, kname, cu_src = sys.argv[1:5]
+# stage boundaries from marker text in the kernel source of the captured build (first line containing the marker)
+src_lines = open(cu_src).read().split("\n")
+
+
+def line_of(marker, after=0):
+    for i, l in enumerate(src_lines):
+        if i + 1 > after and marker in l:
+            return i + 1
+    raise SystemExit(f"marker not found: {marker}")
+
+
+def ranges(marks, end):
+    starts = []
+    for m, name in marks:
+        starts.append((line_of(m, starts[-1][0] if starts else 0), name))
+    return [(lo, (starts[i + 1][0] - 1) if i + 1 < len(starts) else end, name) for i, (lo, name) in enumerate(starts)]
+
+
+k0 = line_of("rp_step_kernel(RpKernelArgs a) {")
+KERNEL = ranges([("rp_step_kernel(RpKernelArgs a) {", "prologue + phase barrier"), ("hand kinematics (by level)", "kinematics"),
+                 ("publish S, velocities", "RNE / CRB / scatter M"), ("actuation (lane = actuator)", "actuation, smooth, key rows"),
+                 ("hand friction + limit rows", "hand friction / limit row setup"), ("collision (lane = geom of this warp's hand)", "collision"),
+                 ("publish what the contact rows read from the other warp", "contact rows + lists"), ("== warm start", "warm start, U, cost"),
+                 ("== PGS", "solver call"), ("dual -> primal, Euler", "dual->primal, Euler"), ("    // integrate", "integrate, midi"),
+                 ("--- store state", "store state"), ("task epilogue: after_step", "task epilogue")], line_of("Launch order for the next step") - 1)
+p0 = line_of("__device__ __noinline__ int pgs_solve(")
+PGS = ranges([("__device__ __noinline__ int pgs_solve(", "pgs: prologue"), ("---- friction-loss rows", "pgs: friction rows"),
+              ("---- limit rows of keys that carry contacts", "pgs: coupled key rows"), ("---- hand limit rows", "pgs: hand limit rows"),
+              ("---- contacts of this hand", "pgs: contacts"), ("if (lane == 0) sm.red[iter & 1][h][1] = improvement;", "pgs: per-sweep barrier + test")],
+             line_of("io->fr_f = fr_f; io->lm_f = lm_f; io->va = va;", p0) + 2)
 lines = open(dis).read().split("\n")
 start = [i for i, l in enumerate(lines) if l.startswith(".text." + kname)][0]
 end = next(i for i in range(start + 1, len(lines)) if lines[i].startswith("//--------------------- "))
 func, off2, pend, cur = "kernel", {}, [], None
 for l in lines[start:end]:
     if l.startswith("$") and l.endswith(":"):
-        func = "pgs_solve" if "pgs_solve" in l else ("sweep_inverse" if "sweep_inverse" in l else "library routine")
+        func = "pgs_solve" if ("pgs_solve" in l and "pgs_solve_hc" not in l) else ("sweep_inverse" if "sweep_inverse" in l else "library routine")
         continue
     m = re.search(r'//## File "(.*?)", line (\d+)( inlined at)?', l)
     if m:
