@@ -151,8 +151,10 @@ __device__ __forceinline__ void hand_pair_sync(int bar_id) {
 }
 // Phase barrier: the environments of one phase group (RP_PHASE_GROUP consecutive slots of the block; the last group
 // takes the remainder) start the substep together.  One group: barrier 0; several: named barriers EPB + 1 + group.
+// A function of its own (not inlined): every thread of the block — stepping, finished or without an environment — waits
+// on the same barrier instruction.
 template <int EPB>
-__device__ __forceinline__ void phase_sync(int slot) {
+__device__ __noinline__ void phase_sync(int slot) {
   constexpr int PG = RP_PHASE_GROUP, NG = EPB / (PG > 0 ? PG : 1);
   if (NG <= 1) { __syncthreads(); return; }
   const int g = slot / PG < NG - 1 ? slot / PG : NG - 1;
