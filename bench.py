@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--total-envs", type=int, default=0, help="strong scaling: fixed global batch split over the ranks (BASELINE config 4: 16384)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-episode", action="store_true", help="skip the second measurement with episode phases staggered across the batch")
+    ap.add_argument("--no-hand-collisions", action="store_true", help="skip the extra measurement with the hand geoms colliding with each other")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: whatever else a library writes there (NCCL's version banner under
     # NCCL_DEBUG=VERSION, ...) is sent to stderr; the line itself goes out through the saved descriptor
@@ -318,6 +319,38 @@ def main():
                 "flagged_envs": int((dg["flags"] != 0).sum()),
                 "how": "episode phases staggered uniformly (env i reset at lead-in step i mod 159): every timed step sees the whole song's contact mix"}
 
+    # ---- protocol C: the same window with the hand geoms colliding with each other (disable_hand_collisions=False, the
+    # reference's default for that kwarg; SURVEY.md 8(d) config 3 leaves it at the default): a second batch on the same
+    # device, same actions, same protocol.  Reported next to the headline, which stays on north_star's configuration.
+    hc = None
+    if not args.no_hand_collisions:
+        from robopianist_b200.suite.env import BatchedPianoEnv
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            env_hc = BatchedPianoEnv(library.load(SONG), num_envs=N, device=local_rank, trim_silence=True, gravity_compensation=True,
+                                     primitive_fingertip_collisions=True, disable_hand_collisions=False, n_steps_lookahead=1)
+        env_hc.reset()
+        for t in range(args.warmup):
+            env_hc.step(actions[t % pool])
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for k in range(args.steps):
+            flush.zero_()
+            evs[k][0].record()
+            env_hc.step(actions[(args.warmup + k) % pool])
+            evs[k][1].record()
+        barrier()
+        t_hc = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_hc, op=dist.ReduceOp.MAX)
+        dg = env_hc.batch.get_diag()
+        hc = {"ms_per_step": float(t_hc.item()) / args.steps, "value": N * world * args.steps / (float(t_hc.item()) * 1e-3), "steps": args.steps,
+              "mean_contacts": float(dg["ncon"].mean()), "mean_pgs_iters_last_substep": float(dg["niter"].mean()),
+              "flagged_envs": int(((dg["flags"] & 7) != 0).sum()),
+              "workload": "as config.workload with disable_hand_collisions=False: the finger / thumb spheres and capsules of both hands also "
+                          "collide with each other (596 pairs); kernel instantiation rp_step_kernel<2, 3, true>"}
+        env_hc.close()
+
     if rank != 0:
         env.close()
         if world > 1:
@@ -351,6 +384,8 @@ def main():
                        "mean_contacts": float(diag["ncon"].mean()), "flagged_envs": int((diag["flags"] != 0).sum())}}
     if full is not None:
         line["full_episode"] = full
+    if hc is not None:
+        line["hand_collisions"] = hc
     if world > 1:
         line["collective"] = {"op": "all_gather_into_tensor (NCCL), async, overlapped with the next step's kernel", "dtype": "float32",
                               "bytes_received_per_rank_per_step": env.gather_bytes_per_step}

@@ -185,6 +185,7 @@ extern "C" rp_model* rp_model_create(const rp_flat_model* m, const rp_task* task
   if (nl < 0 || nl > RP_NL) { fail("a hand may have at most 26 dofs"); return nullptr; }
   if (m->nv != RP_NK + m->nhand * nl) { fail("unexpected nv (need 88 + nhand * dofs per hand)"); return nullptr; }
   if (!task->goal || !task->fingering) { fail("task goal / fingering tables must not be null"); return nullptr; }
+  if (m->nexclude < 0 || (m->nexclude > 0 && !m->exclude_bodies)) { fail("exclude_bodies must list nexclude body pairs"); return nullptr; }
   if (task->n_steps < 1) { fail("task n_steps must be >= 1"); return nullptr; }
   if (task->n_steps_lookahead < 0 || task->n_steps_lookahead > 1024) { fail("task n_steps_lookahead out of range [0, 1024]"); return nullptr; }
   if (task->kind != 0 && task->kind != 1) { fail("task kind must be 0 (piano_with_shadow_hands) or 1 (self_actuated_piano)"); return nullptr; }
@@ -730,7 +731,8 @@ static RpKernelArgs base_args(rp_batch* b, int mode) {
 }
 static int launch(rp_batch* b, const RpKernelArgs& a) {
   CUDA_OK(cudaSetDevice(b->device));
-  CUDA_OK(rp_launch_step(a, b->model->nhand, b->stream, b->block_envs, b->model->dm.hc_enabled));
+  static const int force_hc = getenv("ROBOPLAY_FORCE_HC") != nullptr;  // measurement hook: the hand-collision instantiation on a model without pairs
+  CUDA_OK(rp_launch_step(a, b->model->nhand, b->stream, b->block_envs, b->model->dm.hc_enabled || (force_hc && b->model->nhand == 2)));
   b->launches++;
   return 0;
 }
