@@ -4,6 +4,8 @@
 in the build container or on the GPU boxes, which is why DESIGN.md says "parity unpinned".
 
     python scripts/dump_mjmodel.py [--out tests/golden/mujoco_reference.npz] [--gravcomp 1]
+    python scripts/dump_mjmodel.py --hand-collisions --hands-together --out tests/golden/mujoco_reference_hc.npz
+    python scripts/dump_mjmodel.py --reduced-action-space --out tests/golden/mujoco_reference_ras.npz
 
 Writes one .npz with
   * the compiled mjModel fields the scene flattener restates (scene/compile.py): sizes, body / joint / dof / geom /
@@ -39,6 +41,11 @@ def main():
     ap.add_argument("--out", default=str(Path(__file__).resolve().parents[1] / "tests" / "golden" / "mujoco_reference.npz"))
     ap.add_argument("--gravcomp", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100, help="control steps (x10 physics substeps)")
+    ap.add_argument("--hand-collisions", action="store_true", help="disable_hand_collisions=False (the reference default): the sphere / "
+                    "capsule pair routines restated here are MuJoCo's own, so hand : hand contacts can be pinned exactly")
+    ap.add_argument("--hands-together", action="store_true", help="overwrite the forearm_tx actions so that the hands run into each other "
+                    "(cross-hand contacts; with the piano far below the crossed thumbs no capsule : box contact interferes at first)")
+    ap.add_argument("--reduced-action-space", action="store_true")
     args = ap.parse_args()
 
     import mujoco
@@ -47,7 +54,8 @@ def main():
     env = suite.load(
         "RoboPianist-debug-TwinkleTwinkleRousseau-v0",
         task_kwargs=dict(trim_silence=True, gravity_compensation=bool(args.gravcomp), primitive_fingertip_collisions=True,
-                         disable_hand_collisions=True, n_steps_lookahead=1, control_timestep=0.05))
+                         disable_hand_collisions=not args.hand_collisions, reduced_action_space=args.reduced_action_space,
+                         n_steps_lookahead=1, control_timestep=0.05))
     physics = env.physics
     m, d = physics.model.ptr, physics.data.ptr
     m.opt.solver = mujoco.mjtSolver.mjSOL_PGS
@@ -63,7 +71,17 @@ def main():
     # action replay (canonical [-1, 1] -> spec, as CanonicalSpecWrapper / the tutorial do)
     acts = np.load(Path(suite.__file__).resolve().parents[2] / "examples" / "twinkle_twinkle_actions.npy")
     spec = env.action_spec()
+    names = [mujoco.mj_id2name(m, mujoco.mjtObj.mjOBJ_ACTUATOR, i) for i in range(m.nu)]
+    if args.reduced_action_space:  # the fixture has the full 45 columns: drop the removed actuators' (matched by name on the full model)
+        full = suite.load("RoboPianist-debug-TwinkleTwinkleRousseau-v0", task_kwargs=dict(primitive_fingertip_collisions=True))
+        fm_ = full.physics.model.ptr
+        full_names = [mujoco.mj_id2name(fm_, mujoco.mjtObj.mjOBJ_ACTUATOR, i) for i in range(fm_.nu)]
+        acts = acts[:, [full_names.index(n) for n in names] + [acts.shape[1] - 1]]
     acts = spec.minimum + (acts + 1) / 2 * (spec.maximum - spec.minimum)
+    if args.hands_together:
+        for i, n in enumerate(names):
+            if n.endswith("forearm_tx"):
+                acts[:, i] = (-0.2 if "rh_" in n else 0.2) * np.minimum(1.0, np.arange(acts.shape[0]) / 20.0)
     ts = env.reset()
     qpos, qvel, ncon, niter, rew = [np.array(d.qpos)], [np.array(d.qvel)], [d.ncon], [0], [0.0]
     for t in range(min(args.steps, acts.shape[0])):
@@ -71,6 +89,7 @@ def main():
         qpos.append(np.array(d.qpos)); qvel.append(np.array(d.qvel)); ncon.append(d.ncon)
         niter.append(int(d.solver_niter[0]) if hasattr(d.solver_niter, "__len__") else int(d.solver_niter))
         rew.append(float(ts.reward or 0.0))
+    out["flags"] = np.array([int(args.hand_collisions), int(args.hands_together), int(args.reduced_action_space), int(args.gravcomp)])
     out.update(traj_qpos=np.array(qpos), traj_qvel=np.array(qvel), traj_ncon=np.array(ncon), traj_niter=np.array(niter),
                traj_reward=np.array(rew), traj_actions=acts[:args.steps], obs_keys=np.array(list(ts.observation.keys())),
                mujoco_version=np.array(mujoco.__version__))

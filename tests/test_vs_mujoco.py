@@ -99,3 +99,31 @@ def test_1000_substep_rollout_within_north_star_tolerance(ref, fm):
     rq = np.abs(q - ref["traj_qpos"][:n + 1]).max(axis=1) / np.maximum(1.0, np.abs(ref["traj_qpos"][:n + 1]).max(axis=1))
     print("max relative qpos deviation per control step:", rq.max(), "contacts ours / mujoco:", nc.sum(), ref["traj_ncon"][:n + 1].sum())
     assert rq.max() < 1e-5
+
+
+# ---- optional dumps of the model variants (scripts/dump_mjmodel.py --hand-collisions --hands-together / --reduced-action-space)
+@pytest.mark.parametrize("name,kw", [("mujoco_reference_hc.npz", dict(disable_hand_collisions=False)),
+                                     ("mujoco_reference_ras.npz", dict(reduced_action_space=True))])
+def test_variant_rollouts_against_mujoco(name, kw):
+    """Hand : hand contacts go through restatements of MuJoCo's own sphere / capsule routines and body-pair filters, and the
+    reduced action space only changes the model: with a dump of the corresponding MuJoCo rollout the oracle has to reproduce the
+    contact counts exactly and the state to 1e-9 as long as no capsule : box (piano) contact is active, and
+    the compile-time constants of the variant model have to agree."""
+    path = helpers.GOLDEN / name
+    if not path.exists():
+        pytest.skip(f"no {name} (scripts/dump_mjmodel.py on a machine with MuJoCo)")
+    ref = np.load(path, allow_pickle=False)
+    fm = cache.load_scene(gravity_compensation=bool(ref["flags"][3]), **kw)
+    assert int(ref["nv"]) == fm.meta["nv"] and int(ref["nu"]) == fm.meta["nu"]
+    assert np.allclose(ref["dof_invweight0"], fm.dof_invweight0, rtol=1e-9) and np.allclose(ref["body_mass"], fm.body_mass)
+    om = O.OracleModel(fm); om.set_option(maxcon=60)
+    od = O.OracleData(om); od.reset()
+    acts = ref["traj_actions"]
+    for t in range(acts.shape[0]):
+        od.control_step(acts[t, :fm.meta["nu"]])
+        piano = any(fm.geom_hand[c["geom2"]] < 0 or fm.geom_hand[c["geom1"]] < 0 for c in od.contacts())
+        if piano:
+            break
+        assert od.ncon == int(ref["traj_ncon"][t + 1]), t
+        assert np.abs(od.qpos - ref["traj_qpos"][t + 1]).max() < 1e-9, t
+    assert t > 5
