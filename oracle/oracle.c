@@ -46,6 +46,7 @@ typedef struct orc_model {
   int nhandgeom, npianogeom, *handgeom, *pianogeom;
   int npair, *pair_g1, *pair_g2; /* hand geom pairs that may collide (mj_collision's body-pair filters), MuJoCo order */
   int maxcon;
+  int record_cap; /* > 0: emulate the kernel's contact-record capacity (see prune_to_record_cap) */
 } orc_model;
 
 typedef struct orc_contact {
@@ -185,6 +186,11 @@ void orc_model_destroy(orc_model *o) {
   free(o->tree_adr); free(o->tree_num); free(o->dof_treeid); free(o->body_chain_len);
   free(o->body_chain); free(o->handgeom); free(o->pianogeom); free(o);
 }
+/* The CUDA kernel holds a fixed number of contact records (a hand : piano contact takes one, a hand : hand contact two).  When
+ * a step needs more, it keeps the deepest: records ordered by (distance in whole nanometres, contact order), kept while their position is below
+ * the capacity, a hand : hand contact as a unit — and flags the environment.  MuJoCo has no such limit; this switch only
+ * exists so that the kernel's behaviour beyond its capacity can be tested against the same rule. */
+void orc_set_record_cap(orc_model *o, int cap) { o->record_cap = cap; }
 void orc_set_option(orc_model *o, int iterations, double tolerance, int maxcon) {
   if (iterations > 0) o->m.iterations = iterations;
   if (tolerance >= 0) o->m.tolerance = tolerance;
@@ -820,6 +826,30 @@ void orc_collision(const orc_model *o, orc_data *d) {
   }
   /* hand bodies follow the piano bodies: their pairs come last */
   for (int i = 0; i < o->npair; i++) collide_hand_pair(o, d, o->pair_g1[i], o->pair_g2[i]);
+  if (o->record_cap > 0) {
+    const rp_flat_model *mm = &o->m;
+    int nrec = 0;
+    for (int c = 0; c < d->ncon; c++) nrec += mm->geom_hand[d->con[c].geom2] >= 0 ? 2 : 1; /* geom2 is a piano geom for hand : piano contacts */
+    if (nrec > o->record_cap) {
+      int order[MAXCON], keep[MAXCON];
+      for (int c = 0; c < d->ncon; c++) order[c] = c;
+      for (int a = 1; a < d->ncon; a++) { /* insertion sort by (dist, index): stable */
+        int x = order[a], b = a - 1;
+        while (b >= 0 && floor(d->con[order[b]].dist * 1e9) > floor(d->con[x].dist * 1e9)) { order[b + 1] = order[b]; b--; } /* whole nanometres */
+        order[b + 1] = x;
+      }
+      int pos = 0;
+      for (int a = 0; a < d->ncon; a++) {
+        int c = order[a], pair = mm->geom_hand[d->con[c].geom2] >= 0;
+        keep[c] = (pair ? pos + 1 : pos) < o->record_cap;
+        pos += pair ? 2 : 1;
+      }
+      int n = 0;
+      for (int c = 0; c < d->ncon; c++) if (keep[c]) d->con[n++] = d->con[c];
+      d->ncon = n;
+      d->con_overflow = 1;
+    }
+  }
 }
 
 /* --------------------------------- mj_makeConstraint --------------------------------------- */

@@ -34,6 +34,7 @@ def lib():
         L.orc_model_create.argtypes = [C.POINTER(cabi.RpFlatModel)]
         L.orc_model_destroy.argtypes = [C.c_void_p]
         L.orc_set_option.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
+        L.orc_set_record_cap.argtypes = [C.c_void_p, C.c_int]
         L.orc_data_create.restype = C.c_void_p
         L.orc_data_create.argtypes = [C.c_void_p]
         L.orc_data_destroy.argtypes = [C.c_void_p]
@@ -74,6 +75,10 @@ class OracleModel:
 
     def set_option(self, iterations=-1, tolerance=-1.0, maxcon=-1):
         lib().orc_set_option(self.ptr, iterations, tolerance, maxcon)
+
+    def set_record_cap(self, cap):
+        """Emulate the kernel's contact-record capacity (deepest records kept; oracle.c: orc_set_record_cap)."""
+        lib().orc_set_record_cap(self.ptr, int(cap))
 
     def __del__(self):
         try:

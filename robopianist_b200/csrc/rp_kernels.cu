@@ -26,6 +26,7 @@
 #define NK RP_NK
 #define MAXD RP_MAXD
 #define MAXCON RP_MAXCON
+#define RAWCAP 40  // raw narrowphase entries of the hand-collision instantiation (more than MAXCON: the deepest MAXCON records are kept)
 #define RS 27  // row stride of the hand matrices (odd: lane-per-row accesses are bank-conflict free)
 #define H1 (RP_NHMAX - 1)
 // tuning knobs (DESIGN.md §5 lists what was measured, including the variants that were removed again)
@@ -105,7 +106,7 @@ struct Smem {
     Contact con[MAXCON];           // constraint blocks of the contacts (sorted)
     RawContact raw[MAXCON];        // narrowphase output; moved to registers before con[] is written
     struct {                       // hand : hand collisions: the raw list plus the world-frame primitives of both hands
-      RawContact raw[MAXCON];
+      RawContact raw[RAWCAP];
       double gw[RP_NHMAX][RP_NGH][8];  // centre, axis, radius, half length
     } col;
   } u;
@@ -1257,8 +1258,8 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
             const double dist = rp::sphere_box(pts[ti], prad, bhalf, n, p);
             if (dist < margin) {
               const int slot = atomicAdd(&sm.nraw, 1);
-              if (slot < MAXCON) {
-                RawContact& rc = sm.u.raw[slot];
+              if (slot < (HC ? RAWCAP : MAXCON)) {
+                RawContact& rc = sm.u.col.raw[slot];  // (same storage as u.raw)
                 double nw[3] = {n[0], n[1], n[2]}, pw[3] = {p[0], p[1], p[2]};
                 if (iskey) {
                   double pr[3] = {p[0] - jp[0], p[1] - jp[1], p[2] - jp[2]};
@@ -1305,7 +1306,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         for (int i = 0; i < nc; i++) {
           if (!(dist[i] < margin)) continue;
           const int slot = atomicAdd(&sm.nraw, 2);
-          if (slot + 1 < MAXCON) {
+          if (slot + 1 < RAWCAP) {
             atomicAdd(&sm.npairc, 1);
             for (int side = 0; side < 2; side++) {
               RawContact& rc = sm.u.col.raw[slot + side];
@@ -1317,7 +1318,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
             }
           } else {
             sm.overflow = 1;
-            if (slot < MAXCON) {  // the odd slot left over: an inert record (the environment is flagged as overflowed)
+            if (slot < RAWCAP) {  // the odd slot left over: an inert record (the environment is flagged as overflowed)
               RawContact& rc = sm.u.col.raw[slot];
               rc.dist = 1.0; rc.n[0] = 0; rc.n[1] = 0; rc.n[2] = 1;
               for (int k = 0; k < 3; k++) rc.pos[k] = w1[k];
@@ -1364,19 +1365,44 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     for (int s = 0; s < KS; s++) { const int k = tid + KT * s; if (k < NK) { sm.vak[k] = ks_qacc[s]; sm.kfc[k] = wk[s]; } }
     env_sync<NW, EPB>(bar_id);
     TICK(4)
-    const int nraw = min(sm.nraw, MAXCON);
-    if (sm.nraw > MAXCON || sm.overflow) flags |= 1;
-    // NOTE: on overflow the kept subset depends on atomic order; the flag marks the env invalid.
-    const int ncon = nraw;
-    ncon_last = HC ? ncon - sm.npairc : ncon;  // a hand : hand contact takes two records
+    const int nraw = min(sm.nraw, HC ? RAWCAP : MAXCON);
+    if (sm.nraw > (HC ? RAWCAP : MAXCON) || sm.overflow) flags |= 1;
+    // NOTE: beyond the raw capacity the kept subset depends on atomic order; the flag marks the env invalid.
+    int ncon = nraw, npairc = HC ? sm.npairc : 0;
+    // Hand-collision instantiation: more raw records than contact records (hands flailing over their whole joint ranges can
+    // need 30).  The deepest are kept — ordered by (distance in nm, sort key), a hand : hand contact's two records as a unit — the
+    // shallow ones dropped, and the environment is flagged (bit 0) all the same.  Deterministic, unlike the atomics' order.
+    const bool select = HC && nraw > MAXCON;
+    signed char* const keepf = &sm.hlist[0][0];  // RAWCAP <= 2 * MAXCON bytes, free until the contact lists are built
+    static_assert(!HC || (RAWCAP <= RP_NHMAX * MAXCON && RAWCAP <= KT), "keep flags live in hlist; one thread per raw record");
+    if (select) {
+      flags |= 1;
+      if (tid < nraw) {
+        // depth in whole nanometres: geometrically equal distances (two capsules of one finger meeting at a joint, seen
+        // from a neighbouring finger) differ in their last bits, and must not be ordered by them
+        const RawContact& me = sm.u.col.raw[tid];
+        const long long myq = (long long)floor(me.dist * 1e9);
+        int rank = 0;
+        for (int j = 0; j < nraw; j++) {
+          const RawContact& o = sm.u.col.raw[j];
+          const long long oq = (long long)floor(o.dist * 1e9);
+          rank += (oq < myq || (oq == myq && o.sortkey < me.sortkey)) ? 1 : 0;
+        }
+        keepf[tid] = (signed char)((me.key == -2 ? rank + 1 : rank) < MAXCON ? (me.key == -2 ? 2 : 1) : 0);  // 2: kept first record of a pair
+      }
+      env_sync<NW, EPB>(bar_id);
+      ncon = 0; npairc = 0;
+      for (int j = 0; j < nraw; j++) { ncon += keepf[j] != 0; npairc += keepf[j] == 2; }
+    }
+    ncon_last = HC ? ncon - npairc : ncon;  // a hand : hand contact takes two records
     // ---- contact rows (rank-sorted into con[]): one thread per (contact, frame row), spread over both warps
     // (RP_MAXCON = 21 contacts = 63 rows)
     static_assert(!HANDS || 3 * MAXCON <= KT, "one thread per contact row");
     if (HANDS && ncon > 0) {
-      if (tid < nraw) {
-        const unsigned mykey = sm.u.raw[tid].sortkey;
+      if (tid < nraw && (!select || keepf[tid])) {
+        const unsigned mykey = sm.u.col.raw[tid].sortkey;
         int rank = 0;
-        for (int j = 0; j < nraw; j++) rank += (sm.u.raw[j].sortkey < mykey) ? 1 : 0;
+        for (int j = 0; j < nraw; j++) rank += (sm.u.col.raw[j].sortkey < mykey && (!select || keepf[j])) ? 1 : 0;
         sm.perm[rank] = (signed char)tid;
       }
       env_sync<NW, EPB>(bar_id);
@@ -1386,7 +1412,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       double c_dist = 0, c_pos[3] = {0, 0, 0}, c_frame[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
       int ch = 0, c_geom = 0, c_key = -1, c_sub = 0;
       if (rowt) {
-        const RawContact rc = sm.u.raw[sm.perm[c]];
+        const RawContact rc = sm.u.col.raw[sm.perm[c]];
         c_sub = rc.sub;
         c_dist = rc.dist;
         for (int k = 0; k < 3; k++) { c_pos[k] = rc.pos[k]; c_frame[k] = rc.n[k]; }

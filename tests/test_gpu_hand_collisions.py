@@ -124,3 +124,47 @@ def test_suite_load_with_the_reference_default_hand_collisions():
     assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
     assert (env.batch.get_diag()["flags"] & 3 == 0).all()
     env.close()
+
+
+def test_beyond_the_record_capacity_the_deepest_contacts_are_kept():
+    """Hands flailing over their whole joint ranges need up to 29 contact records; the kernel holds 21.  It keeps the deepest
+    (records ordered by distance, a hand : hand contact as a unit), drops the shallow ones and flags the environment (diag bit 0)
+    — deterministically; the oracle emulates the same rule (orc_set_record_cap), so the trajectories still agree."""
+    fm, model, batch = helpers.make_native("piano_with_shadow_hands", nenv=2, scene_kw=HC)
+    om = O.OracleModel(fm); om.set_option(maxcon=60); om.set_record_cap(21)
+    od = O.OracleData(om); od.reset()
+    nv, nu = fm.meta["nv"], fm.meta["nu"]
+    batch.set_state(np.zeros((2, nv)), np.zeros((2, nv)), np.zeros((2, nv)))
+    od.qpos[:] = 0; od.qvel[:] = 0; od.qacc_warmstart[:] = 0
+    names = fm.meta["actuator_names"]
+    lo, hi = fm.actuator_ctrlrange[:, 0], fm.actuator_ctrlrange[:, 1]
+    rng = np.random.default_rng(3)
+    target = rng.random(nu)
+    worst = 0.0
+    overflowed = 0
+    for t in range(700):
+        if t % 100 == 0:
+            target = rng.random(nu)
+        if t % 10 == 0:
+            ctrl = lo + (hi - lo) * target  # full-range targets
+            for i, n in enumerate(names):
+                if n.endswith("forearm_tx"):
+                    ctrl[i] = (-0.2 if "rh_" in n else 0.2) * min(1.0, t / 200.0)
+                if n.endswith("forearm_ty"):
+                    ctrl[i] = 0.0
+            ct = _dev(np.tile(ctrl, (2, 1)))
+        if t % 25 == 0 and t:
+            batch.set_state(np.tile(od.qpos, (2, 1)), np.tile(od.qvel, (2, 1)), np.tile(od.qacc_warmstart, (2, 1)))
+        batch.physics_step(ct.data_ptr(), 1)
+        od.mj_step(ctrl)
+        q, v, _, _ = batch.get_state()
+        worst = max(worst, np.abs(q[0] - od.qpos).max())
+        dg = batch.get_diag()
+        over_dev, over_ref = bool(dg["flags"][0] & 1), bool(od.con_overflow)
+        assert over_dev == over_ref, (t, dg["flags"][0], od.con_overflow, dg["ncon"][0], od.ncon)
+        assert dg["ncon"][0] == od.ncon and dg["niter"][0] == od.solver_niter, (t, dg["ncon"][0], od.ncon, dg["niter"][0], od.solver_niter)
+        overflowed += over_dev
+        assert (q[0] == q[1]).all()
+    assert overflowed > 10, overflowed
+    assert worst < 1e-9, worst
+    batch.close()
