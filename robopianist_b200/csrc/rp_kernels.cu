@@ -36,6 +36,9 @@
 #ifndef RP_EPB_MINBLOCKS
 #define RP_EPB_MINBLOCKS (RP_EPB <= 6 ? 6 / RP_EPB : 1)  // resident blocks per SM the register allocation has to allow (six environments per SM)
 #endif
+#ifndef RP_PHASE_EVERY
+#define RP_PHASE_EVERY 1  // phase barrier at the top of every RP_PHASE_EVERY-th substep (RP_EPB > 1)
+#endif
 #ifndef RP_PHASE_GROUP
 #define RP_PHASE_GROUP RP_EPB  // environments per phase group: the groups of a block are phase-locked separately (the last group takes the remainder)
 #endif
@@ -672,7 +675,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
   const int nsub_loop = a.mode == RP_MODE_RESET ? 0 : a.nsub;
   const int eidx = (int)blockIdx.x * EPB + slot;
   if (eidx >= a.nenv) {
-    if (EPB > 1) for (int s2 = 0; s2 <= nsub_loop; s2++) phase_sync<EPB>(slot);
+    if (EPB > 1) for (int s2 = 0; s2 <= nsub_loop; s2++) if (s2 % RP_PHASE_EVERY == 0) phase_sync<EPB>(slot);
     return;
   }
   // longest-expected-first launch order (rp_order_kernel) shortens the tail of the last wave
@@ -695,7 +698,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
   } else if (a.mode == RP_MODE_RESET) {
     do_reset = a.reset_mask == nullptr ? true : (a.reset_mask[env] != 0);
     if (!do_reset) {
-      if (EPB > 1) for (int s2 = 0; s2 <= nsub_loop; s2++) phase_sync<EPB>(slot);
+      if (EPB > 1) for (int s2 = 0; s2 <= nsub_loop; s2++) if (s2 % RP_PHASE_EVERY == 0) phase_sync<EPB>(slot);
       return;
     }
   }
@@ -824,7 +827,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
   // =============================================================================================
   for (int sub = 0; sub <= (EPB > 1 ? nsub_loop : nsub); sub++) {
     if (EPB > 1) {
-      phase_sync<EPB>(slot);  // phase barrier: the environments of the group start the substep together
+      if (sub % RP_PHASE_EVERY == 0) phase_sync<EPB>(slot);  // phase barrier: the environments of the group start the substep together
       if (sub > nsub) continue;  // this environment is done (episode reset: no physics), only keeps the barrier count
     }
     const long long t_sub = clock64();
