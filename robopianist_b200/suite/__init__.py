@@ -1,8 +1,9 @@
 """RoboPianist suite over the B200 step kernel — mirror of ``robopianist.suite`` (suite/__init__.py).
 
 ``load()`` keeps the reference signature (suite/__init__.py:50-59) and adds keyword-only
-``num_envs`` / ``device`` / solver overrides.  ``num_envs=1`` returns a ``dm_env``-shaped
-``PianoEnv``; ``num_envs>1`` returns a ``BatchedPianoEnv`` working on CUDA tensors.
+``num_envs`` / ``device`` / ``devices`` / solver overrides.  ``num_envs=1`` returns a ``dm_env``-shaped
+``PianoEnv``; ``num_envs>1`` returns a ``BatchedPianoEnv`` working on CUDA tensors; ``devices=[0, 1, ...]`` a
+``MultiDevicePianoEnv`` (one process, the batch split over the listed GPUs; one process per GPU: ``ShardedPianoEnv``).
 
 The PIG-dataset names (``REPERTOIRE_150`` / ``ETUDE_12``) need the PIG ``.proto`` files the reference
 downloads separately (cli.py:231-288); they are not distributable, so those lists are empty here and
@@ -12,7 +13,7 @@ only the programmatic debug songs (music/library.py) are registered.  Any ``.mid
 from __future__ import annotations
 
 from pathlib import Path
-from typing import Any, Mapping, Optional
+from typing import Any, Mapping, Optional, Sequence
 
 from ..music import library
 from .env import BatchedPianoEnv, PianoEnv, StepType, TimeStep  # noqa: F401
@@ -38,6 +39,7 @@ def load(
     *,
     num_envs: int = 1,
     device: int = 0,
+    devices: Optional[Sequence[int]] = None,
     iterations: Optional[int] = None,
     tolerance: Optional[float] = None,
 ):
@@ -58,6 +60,12 @@ def load(
         if environment_name not in ALL:
             raise ValueError(f"Unknown environment {environment_name}. Available environments: {ALL}")
         midi = library.load(_ALL_DICT[environment_name], stretch=stretch, shift=shift)
+    if devices is not None and len(devices) > 1:   # one process, several GPUs: the batch split into contiguous ranges
+        from .multidevice import MultiDevicePianoEnv
+        return MultiDevicePianoEnv(midi, num_envs, devices, iterations=iterations, tolerance=tolerance, seed=seed,
+                                   recompile_physics=recompile_physics, **dict(task_kwargs or {}))
+    if devices is not None:
+        device = int(devices[0])
     batched = BatchedPianoEnv(midi, num_envs=num_envs, device=device, iterations=iterations,
                               tolerance=tolerance, seed=seed, recompile_physics=recompile_physics,
                               **dict(task_kwargs or {}))

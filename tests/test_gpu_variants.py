@@ -173,3 +173,27 @@ def test_suite_load_with_the_reference_training_kwargs():
     torch.cuda.synchronize()
     assert torch.isfinite(obs).all() and torch.isfinite(rew).all() and (st == 1).all()
     env.close()
+
+
+def test_multi_device_env_matches_one_device():
+    """`suite.load(..., devices=[0, 1])`: one process, the batch split over two GPUs — bitwise the same results as the whole
+    batch on one (environments are independent; needs two devices)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from robopianist_b200 import suite
+    kw = dict(primitive_fingertip_collisions=True, disable_hand_collisions=True, gravity_compensation=True, trim_silence=True)
+    N = 64
+    one = suite.load("RoboPianist-debug-TwinkleTwinkleRousseau-v0", num_envs=N, task_kwargs=kw)
+    two = suite.load("RoboPianist-debug-TwinkleTwinkleRousseau-v0", num_envs=N, devices=[0, 1], task_kwargs=kw)
+    assert [e.device.index for e in two.envs] == [0, 1] and two.ranges == [(0, 32), (32, 64)]
+    acts = helpers.twinkle_actions()
+    rng = np.random.default_rng(0)
+    one.reset(); two.reset()
+    for t in range(12):
+        a = np.tile(acts[t], (N, 1)); a[:, :44] += rng.normal(0, 0.02, (N, 44))
+        at = torch.tensor(a, dtype=torch.float64, device="cuda:0")
+        o1, r1, d1, s1 = one.step(at)
+        o2, r2, d2, s2 = two.step(at)
+    torch.cuda.synchronize(0); two.synchronize()
+    assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2) and torch.equal(s1, s2)
+    one.close(); two.close()

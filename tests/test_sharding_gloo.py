@@ -117,3 +117,57 @@ def test_sharded_env_gathers_the_global_batch_world2():
             assert obs.dtype == np.float32 and obs.shape == (8, 5)
             assert (obs[:, 0] == 1000 * np.arange(8) + t).all() and (rew == 0.5 * np.arange(8)).all()
             assert (dis == 1).all() and (st == (1 if t else 0)).all()
+
+
+def test_multi_device_env_splits_and_collects_on_cpu_stand_ins():
+    """MultiDevicePianoEnv (`suite.load(..., devices=[...])`) over CPU stand-ins of the per-device environments: contiguous
+    ranges, actions sliced per range (one tensor or one block per device), outputs collected in global order."""
+    import torch
+    from robopianist_b200.suite.multidevice import MultiDevicePianoEnv
+
+    class Fake:
+        def __init__(self, n, lo, dev):
+            self.num_envs, self.lo = n, lo
+            self.device = torch.device("cpu")
+            self.model = type("M", (), dict(obs_dim=5, act_dim=3))()
+            self.obs = torch.zeros((n, 5), dtype=torch.float64); self.reward = torch.zeros(n, dtype=torch.float64)
+            self.discount = torch.ones(n, dtype=torch.float64); self.step_type = torch.zeros(n, dtype=torch.uint8)
+            self.closed = False
+
+        def reset(self):
+            self.obs[:] = (self.lo + torch.arange(self.num_envs, dtype=torch.float64))[:, None]
+            self.step_type.zero_()
+
+        def step(self, a):
+            assert a.shape == (self.num_envs, 3)
+            self.obs[:, :3] = a; self.reward[:] = a.sum(1); self.step_type.fill_(1)
+
+        def action_spec(self):
+            return "spec"
+
+        def observation_spec(self):
+            return "ospec"
+
+        def close(self):
+            self.closed = True
+
+    env = MultiDevicePianoEnv(None, 12, devices=[0, 1, 2], local_factory=lambda n, lo, d: Fake(n, lo, d))
+    assert env.ranges == [(0, 4), (4, 8), (8, 12)] and env.action_spec() == "spec"
+    obs, rew, dis, st = env.reset()
+    assert obs[:, 0].tolist() == list(map(float, range(12))) and st.sum() == 0
+    a = torch.arange(36, dtype=torch.float64).reshape(12, 3)
+    obs, rew, dis, st = env.step(a)
+    assert torch.equal(obs[:, :3], a) and torch.equal(rew, a.sum(1)) and (st == 1).all()
+    obs2, *_ = env.step([a[0:4] + 1, a[4:8] + 1, a[8:12] + 1])
+    assert torch.equal(obs2[:, :3], a + 1)
+    with pytest.raises(ValueError):
+        env.step([a[0:4], a[4:8]])
+    with pytest.raises(ValueError):
+        MultiDevicePianoEnv(None, 10, devices=[0, 1, 2], local_factory=lambda n, lo, d: Fake(n, lo, d))
+    with pytest.raises(ValueError):
+        MultiDevicePianoEnv(None, 12, devices=[0, 0], local_factory=lambda n, lo, d: Fake(n, lo, d))
+    per_dev = MultiDevicePianoEnv(None, 12, devices=[0, 1, 2], gather=False, local_factory=lambda n, lo, d: Fake(n, lo, d))
+    outs = per_dev.reset()
+    assert len(outs) == 3 and outs[1][0][0, 0] == 4.0
+    env.close()
+    assert all(e.closed for e in env.envs)
