@@ -186,7 +186,7 @@ void orc_model_destroy(orc_model *o) {
   free(o->tree_adr); free(o->tree_num); free(o->dof_treeid); free(o->body_chain_len);
   free(o->body_chain); free(o->handgeom); free(o->pianogeom); free(o);
 }
-/* The CUDA kernel holds a fixed number of contact records (a hand : piano contact takes one, a hand : hand contact two).  When
+/* The CUDA kernel holds a fixed number of contact records (a contact across the hands takes two, every other contact one).  When
  * a step needs more, it keeps the deepest: records ordered by (distance in whole nanometres, contact order), kept while their position is below
  * the capacity, a hand : hand contact as a unit — and flags the environment.  MuJoCo has no such limit; this switch only
  * exists so that the kernel's behaviour beyond its capacity can be tested against the same rule. */
@@ -829,7 +829,9 @@ void orc_collision(const orc_model *o, orc_data *d) {
   if (o->record_cap > 0) {
     const rp_flat_model *mm = &o->m;
     int nrec = 0;
-    for (int c = 0; c < d->ncon; c++) nrec += mm->geom_hand[d->con[c].geom2] >= 0 ? 2 : 1; /* geom2 is a piano geom for hand : piano contacts */
+    /* records: a contact across the hands takes two (one per body), every other contact one */
+#define ORC_CROSS(c_) (mm->geom_hand[d->con[c_].geom2] >= 0 && mm->geom_hand[d->con[c_].geom1] >= 0 && mm->geom_hand[d->con[c_].geom1] != mm->geom_hand[d->con[c_].geom2])
+    for (int c = 0; c < d->ncon; c++) nrec += ORC_CROSS(c) ? 2 : 1;
     if (nrec > o->record_cap) {
       int order[MAXCON], keep[MAXCON];
       for (int c = 0; c < d->ncon; c++) order[c] = c;
@@ -840,7 +842,7 @@ void orc_collision(const orc_model *o, orc_data *d) {
       }
       int pos = 0;
       for (int a = 0; a < d->ncon; a++) {
-        int c = order[a], pair = mm->geom_hand[d->con[c].geom2] >= 0;
+        int c = order[a], pair = ORC_CROSS(c);
         keep[c] = (pair ? pos + 1 : pos) < o->record_cap;
         pos += pair ? 2 : 1;
       }

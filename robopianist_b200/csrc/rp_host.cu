@@ -51,6 +51,7 @@ struct rp_batch {
   double* hand_offset;    // [N] accumulated attachment offset of the hands (rp_randomize_hand_positions)
   uint64_t* rng_state;    // [N] generator state of the offset draws
   int hand_offset_fresh;  // offsets do not accumulate over episodes (the reference with recompile_physics=True)
+  int record_cap;         // test hook: contact-record capacity below RP_MAXCON (rp_debug_set_record_cap)
   // staging for rp_step_host
   double *h_action, *h_out;  // pinned
   double *d_action, *d_out;
@@ -726,6 +727,7 @@ static RpKernelArgs base_args(rp_batch* b, int mode) {
   a.midi_events = b->midi_events; a.midi_count = b->midi_count; a.midi_cap = b->midi_cap;
   a.work = b->work; a.order = b->order_valid ? b->order : nullptr;
   a.hand_offset = b->hand_offset; a.rng_state = b->rng_state; a.hand_offset_fresh = b->hand_offset_fresh;
+  a.record_cap = b->record_cap;
   a.dbg = b->dbg;
   return a;
 }
@@ -939,6 +941,7 @@ extern "C" double rp_debug_ot_fingering_host(const rp_model* m, int t, const dou
 extern "C" int64_t rp_launch_count(const rp_batch* b) { return b->launches; }
 
 // Debug hooks (not part of the public header): stage dump of substep 0 for every env.
+extern "C" int rp_debug_set_record_cap(rp_batch* b, int cap) { b->record_cap = cap; return 0; }
 extern "C" int rp_debug_enable(rp_batch* b, int on) {
   CUDA_OK(cudaSetDevice(b->device));
   if (on && !b->dbg) CUDA_OK(dalloc(&b->dbg, (size_t)b->nenv * RP_DBG_STRIDE));

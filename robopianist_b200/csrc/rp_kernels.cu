@@ -60,8 +60,10 @@ struct Contact {  // lives in shared memory
   double R[3], b[3], f[3];
   double mu, invMk;
   rp::EllInv inv;            // sweep-invariant part of the elliptic block update (1/A00, friction block at lambda = 0, ...)
-  int hand, link, key, dep;  // key = -1: piano base (static), -2 / -3: the two records of a hand : hand contact (the block lives in
-                             // the first, the second carries the other body's Jacobian); dep: chain depth, bit 8: friction block regular (qcqp ok)
+  int hand, link, key, dep;  // key = -1: piano base (static); -2 / -3: the two records of a cross-hand contact (the block lives in the
+                             // first, the second carries the other body's Jacobian); -4: a contact between two bodies of one hand, one
+                             // record whose "chain" lists the dofs below the bodies' common ancestor (those above cancel exactly);
+                             // dep: chain length - 1, bit 8: friction block regular (qcqp ok)
   signed char chain[16];     // dof (lane) at depth d of the hand chain
 };
 struct CKey {  // limit row of a key that is coupled to a hand through a contact
@@ -70,7 +72,8 @@ struct CKey {  // limit row of a key that is coupled to a hand through a contact
 };
 struct RawContact {  // narrowphase output before sorting
   double dist, pos[3], n[3];
-  int hand, geom, key, sub;  // hand : hand contacts take two entries: key = -2 (geom 1's side) / -3 (geom 2's side), sub = partner's hand * 32 + geom
+  int hand, geom, key, sub;  // hand : hand contacts: across the hands two entries, key = -2 (geom 1's side) / -3 (geom 2's side); within a hand
+                             // one entry, key = -4; sub = partner's hand * 32 + geom
   unsigned sortkey, pad;
 };
 
@@ -443,12 +446,21 @@ __device__ __noinline__ int pgs_solve(Smem* smp, const int h, const int bar_id, 
   return iter;
 }
 
+// Jacobian entries of the lane's dof in a contact record whose chain is any list of dofs (hand-collision instantiation: the
+// chain of a same-hand contact is not a root path, so the lane's depth does not index it)
+__device__ __forceinline__ void lane_jac(const Contact& cn, int lane, double& j0, double& j1, double& j2) {
+  j0 = 0; j1 = 0; j2 = 0;
+  const int dep = cn.dep & 0xff;
+  for (int d = 0; d <= dep; d++)
+    if (cn.chain[d] == lane) { j0 = cn.Jc[0][d]; j1 = cn.Jc[1][d]; j2 = cn.Jc[2][d]; }
+}
+
 // The solver of models whose hand geoms may collide with each other (disable_hand_collisions=False).  Same sweep as
 // pgs_solve — friction rows, limit rows of coupled keys, hand limit rows, contacts in sorted order (this copy loads
-// the Jacobian entries on demand instead of a contact ahead).  A hand : hand contact occupies two adjacent records:
-// the first (key = -2) holds the block and the Jacobian of geom 1's body, the second (key = -3) the Jacobian of geom
-// 2's body; both mirror the force.  Same-hand pair: the warp of that hand adds both records' entries per dof.  Cross-hand
-// pair: sm.shared_key is set, the rows are stepped in global order, each warp reduces its own half of J * va, the
+// the Jacobian entries on demand instead of a contact ahead).  A contact between two bodies of one hand is one record over
+// the dofs below their common ancestor (key = -4), swept like any other by the warp of that hand.  A cross-hand contact
+// occupies two adjacent records: the first (key = -2) holds the block and the Jacobian of geom 1's body, the second
+// (key = -3) the Jacobian of geom 2's body; both mirror the force; sm.shared_key is set, the rows are stepped in global order, each warp reduces its own half of J * va, the
 // halves are exchanged through shared memory, both warps evaluate the (identical) block update and apply it to their own
 // dofs; the warp of geom 1 accounts for the cost change.
 __device__ __noinline__ int pgs_solve_hc(Smem* smp, const int h, const int bar_id, const int ncon, const int maxiter, const double tol,
@@ -544,8 +556,8 @@ __device__ __noinline__ int pgs_solve_hc(Smem* smp, const int h, const int bar_i
         const bool cross = pair && cs.hand != cn.hand;
         if (mineP || mineS) {  // warp-uniform
           double j0 = 0, j1 = 0, j2 = 0, k0 = 0, k1 = 0, k2 = 0;
-          if (mineP) { const int link = cn.link; if (lane <= link && link < lane + lsub) { j0 = cn.Jc[0][ldc]; j1 = cn.Jc[1][ldc]; j2 = cn.Jc[2][ldc]; } }
-          if (mineS) { const int link = cs.link; if (lane <= link && link < lane + lsub) { k0 = cs.Jc[0][ldc]; k1 = cs.Jc[1][ldc]; k2 = cs.Jc[2][ldc]; } }
+          if (mineP) lane_jac(cn, lane, j0, j1, j2);
+          if (mineS) lane_jac(cs, lane, k0, k1, k2);
           double p0 = (j0 + k0) * va, p1 = (j1 + k1) * va, p2 = (j2 + k2) * va;
           const int key = cn.key, depq = cn.dep;
           double Ab[9], fold[3], rbase[3];
@@ -1290,8 +1302,8 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     }
     if (HC && dm->hc_enabled) {
       // ---- hand geom : hand geom pairs (self and cross hand; host-filtered list in MuJoCo's pair order), one thread
-      // per pair: bounding spheres, then the analytic sphere / capsule routines.  A contact takes two adjacent raw
-      // entries (one per body), sorted behind every hand : piano contact.
+      // per pair: bounding spheres, then the analytic sphere / capsule routines.  A contact across the hands takes two
+      // adjacent raw entries (one per body), a contact within a hand one; all sorted behind every hand : piano contact.
       env_sync<NW, EPB>(bar_id);
       const int npairs = dm->hc_npair;
       for (int p = tid; p < npairs; p += KT) {
@@ -1308,14 +1320,15 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         const int nc = rp::sphere_capsule_pair(margin, w1, w1 + 3, w1[6], w1[7], w2, w2 + 3, w2[6], w2[7], dist, nrm, pos);
         for (int i = 0; i < nc; i++) {
           if (!(dist[i] < margin)) continue;
-          const int slot = atomicAdd(&sm.nraw, 2);
-          if (slot + 1 < RAWCAP) {
-            atomicAdd(&sm.npairc, 1);
-            for (int side = 0; side < 2; side++) {
+          const int cross = h1 != h2;
+          const int slot = atomicAdd(&sm.nraw, 1 + cross);
+          if (slot + cross < RAWCAP) {
+            if (cross) atomicAdd(&sm.npairc, 1);
+            for (int side = 0; side <= cross; side++) {
               RawContact& rc = sm.u.col.raw[slot + side];
               rc.dist = dist[i];
               for (int k = 0; k < 3; k++) { rc.n[k] = nrm[3 * i + k]; rc.pos[k] = pos[3 * i + k]; }
-              rc.hand = side ? h2 : h1; rc.geom = side ? g2 : g1; rc.key = -2 - side;
+              rc.hand = side ? h2 : h1; rc.geom = side ? g2 : g1; rc.key = cross ? -2 - side : -4;
               rc.sub = side ? h1 * 32 + g1 : h2 * 32 + g2;
               rc.sortkey = 32768u + (unsigned)((p * 2 + i) * 2 + side);
             }
@@ -1375,7 +1388,8 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
     // Hand-collision instantiation: more raw records than contact records (hands flailing over their whole joint ranges can
     // need 30).  The deepest are kept — ordered by (distance in nm, sort key), a hand : hand contact's two records as a unit — the
     // shallow ones dropped, and the environment is flagged (bit 0) all the same.  Deterministic, unlike the atomics' order.
-    const bool select = HC && nraw > MAXCON;
+    const int reccap = (HC && a.record_cap > 0 && a.record_cap < MAXCON) ? a.record_cap : MAXCON;
+    const bool select = HC && nraw > reccap;
     signed char* const keepf = &sm.hlist[0][0];  // RAWCAP <= 2 * MAXCON bytes, free until the contact lists are built
     static_assert(!HC || (RAWCAP <= RP_NHMAX * MAXCON && RAWCAP <= KT), "keep flags live in hlist; one thread per raw record");
     if (select) {
@@ -1391,7 +1405,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
           const long long oq = (long long)floor(o.dist * 1e9);
           rank += (oq < myq || (oq == myq && o.sortkey < me.sortkey)) ? 1 : 0;
         }
-        keepf[tid] = (signed char)((me.key == -2 ? rank + 1 : rank) < MAXCON ? (me.key == -2 ? 2 : 1) : 0);  // 2: kept first record of a pair
+        keepf[tid] = (signed char)((me.key == -2 ? rank + 1 : rank) < reccap ? (me.key == -2 ? 2 : 1) : 0);  // 2: kept first record of a cross-hand pair
       }
       env_sync<NW, EPB>(bar_id);
       ncon = 0; npairc = 0;
@@ -1427,7 +1441,8 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       env_sync<NW, EPB>(bar_id);
       double u[MAXD], arefr = 0, mu_row = 0;
       double hc_sv = 0, hc_B = 0, hc_K = 0;  // hand : hand contacts: this side's row velocity, damping and stiffness term
-      const bool pairc = HC && c_key < -1;   // record of a hand : hand contact (-2: geom 1's body, -3: geom 2's)
+      const bool pairc = HC && c_key < -1;   // record of a hand : hand contact (-2 / -3: cross-hand, geom 1's / geom 2's body; -4: within a hand)
+      const bool crossc = HC && (c_key == -2 || c_key == -3);
       int link = 0, dep = 0;
       if (rowt) {
         Contact& cn = sm.u.con[c];
@@ -1439,8 +1454,28 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         // through it and are fully unrolled (an index load in front of every element made this stage the longest
         // serial chain of the contact rows: depth^2 dependent load pairs per row)
         int cidx[MAXD];
+        unsigned plus = (HC && c_key == -3) ? 0xffffffffu : 0u;  // chain entries that enter with a plus sign (body 2 of a hand : hand contact)
+        if (HC && c_key == -4) {
+          // two bodies of one hand: the dofs of their common ancestors move the contact point of both bodies alike — those
+          // Jacobian entries cancel exactly — so the record's chain lists body 1's dofs below the branch point (minus), then
+          // body 2's (plus): at most 5 + 5 for two fingers of the Shadow Hand
+          const int link2 = dm->geom_link[ch][c_sub & 31], dep2 = sm.dep[ch][link2];
+          int b = 0;
+          while (b <= dep && b <= dep2 && sm.anc[ch][link][b] == sm.anc[ch][link2][b]) b++;
+          const int n1 = dep - b + 1, n = min(n1 + dep2 - b + 1, MAXD);
+          if (n1 + dep2 - b + 1 > MAXD) sm.overflow = 1;  // deeper than the record holds (not with this hand model): flagged
 #pragma unroll
-        for (int d = 0; d < MAXD; d++) cidx[d] = sm.anc[ch][link][d <= dep ? d : dep];
+          for (int d = 0; d < MAXD; d++) {
+            const int dd = d < n ? d : n - 1;
+            const bool first = dd < n1;
+            cidx[d] = sm.anc[ch][first ? link : link2][first ? b + dd : b + dd - n1];
+            if (!first) plus |= 1u << d;
+          }
+          dep = n - 1;
+        } else {
+#pragma unroll
+          for (int d = 0; d < MAXD; d++) cidx[d] = sm.anc[ch][link][d <= dep ? d : dep];
+        }
         // Jacobian row: frame direction r, body2 (key) minus body1 (hand link)
         double jrow[MAXD];
 #pragma unroll
@@ -1449,7 +1484,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
           double wxp[3];
           rp::cross3(wxp, S, c_pos);
           double v = d <= dep ? -(dir[0] * (S[3] + wxp[0]) + dir[1] * (S[4] + wxp[1]) + dir[2] * (S[5] + wxp[2])) : 0.0;
-          if (HC && c_key == -3) v = -v;  // body 2 of the pair enters with a plus sign
+          if (HC && ((plus >> d) & 1u)) v = -v;
           jrow[d] = v;
           cn.Jc[r][d] = v;
         }
@@ -1502,7 +1537,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
             s3 += jrow[d] * sm.v.pre.wsb[ch][cidx[d]];
           }
           if (c_key >= 0) { s2 += jk * sm.vak[c_key]; s3 += jk * sm.kfc[c_key]; }
-          if (pairc) {  // partial sums of this body's chain; the first record combines both after the barrier
+          if (crossc) {  // partial sums of this body's chain; the first record combines both after the barrier
             cn.b[r] = s2; cn.f[r] = s3;
             if (c_key == -3) cn.R[r] = sv;
             hc_sv = sv; hc_B = B; hc_K = r == 0 ? K * imp * (c_dist - incl) : 0.0;
@@ -1519,7 +1554,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         }
       }
       env_sync<NW, EPB>(bar_id);
-      if (rowt && !pairc) {
+      if (rowt && !crossc) {
         Contact& cn = sm.u.con[c];
         // A[s2][r] = Jc_s2 Minv Jc_r^T + Jk_s2 Jk_r / Mk + R (diagonal)
         for (int s2 = 0; s2 < 3; s2++) {
@@ -1531,7 +1566,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         }
       }
       if (HC && rowt && c_key == -2) {
-        // hand : hand contact, first record (P) with its partner (S = c + 1).  Reference acceleration from the row velocity
+        // cross-hand contact, first record (P) with its partner (S = c + 1).  Reference acceleration from the row velocity
         // of both bodies; b and the warm-start jar from both partial sums; the block from J = [J_P J_S]:
         // A[s2][r] = J_s2 Minv J_r^T with Minv block diagonal per hand — the cross terms P x S only when both bodies belong
         // to the same hand.
@@ -1669,7 +1704,8 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         for (int ci = 0; ci < nmine; ci++) {
           const Contact& cn = sm.u.con[sm.hlist[h][ci]];
           const int link = cn.link;
-          if (lane <= link && link < lane + lsub) wq += cn.Jc[0][ldc] * cn.f[0] + cn.Jc[1][ldc] * cn.f[1] + cn.Jc[2][ldc] * cn.f[2];
+          if (HC) { double j0, j1, j2; lane_jac(cn, lane, j0, j1, j2); wq += j0 * cn.f[0] + j1 * cn.f[1] + j2 * cn.f[2]; }
+          else if (lane <= link && link < lane + lsub) wq += cn.Jc[0][ldc] * cn.f[0] + cn.Jc[1][ldc] * cn.f[1] + cn.Jc[2][ldc] * cn.f[2];
         }
         sm.wbuf[h][lane] = wq;
       }
@@ -1783,7 +1819,8 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       for (int ci = 0; ci < nmine; ci++) {
         const Contact& cn = sm.u.con[sm.hlist[h][ci]];
         const int link = cn.link;
-        if (lane <= link && link < lane + lsub) qfrc_c += cn.Jc[0][ldc] * cn.f[0] + cn.Jc[1][ldc] * cn.f[1] + cn.Jc[2][ldc] * cn.f[2];
+        if (HC) { double j0, j1, j2; lane_jac(cn, lane, j0, j1, j2); qfrc_c += j0 * cn.f[0] + j1 * cn.f[1] + j2 * cn.f[2]; }
+        else if (lane <= link && link < lane + lsub) qfrc_c += cn.Jc[0][ldc] * cn.f[0] + cn.Jc[1][ldc] * cn.f[1] + cn.Jc[2][ldc] * cn.f[2];
       }
     }
     // constraint force on coupled keys: limit row + contacts, accumulated in contact order

@@ -60,6 +60,7 @@ struct RpKernelArgs {
   int midi_cap, hand_offset_fresh;  // hand_offset_fresh: every episode starts from the unshifted pose (recompile_physics=True)
   double* hand_offset;       // [N] y offset of both hands' attachment (randomize_hand_positions), optional
   uint64_t* rng_state;       // [N] per-environment generator state of the offset draws (with hand_offset)
+  int record_cap, pad_rc;    // > 0: contact-record capacity below RP_MAXCON (test hook of the deepest-first selection; hand-collision instantiation)
   int32_t* work;             // [N] work estimate of this step (out)
   const int32_t* order;      // [N] block -> environment (optional)
   double* dbg;

@@ -252,6 +252,11 @@ class Batch:
         return int(lib().rp_launch_count(self.ptr))
 
     # debug stage dump (substep 0 of the next launches)
+    def debug_set_record_cap(self, cap):
+        """Test hook: contact-record capacity below the built-in 21 (exercises the deepest-first selection)."""
+        lib().rp_debug_set_record_cap.argtypes = [C.c_void_p, C.c_int]
+        _check(lib().rp_debug_set_record_cap(self.ptr, int(cap)))
+
     def debug_enable(self, on=True):
         _check(lib().rp_debug_enable(self.ptr, int(on)))
 

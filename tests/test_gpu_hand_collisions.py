@@ -127,11 +127,14 @@ def test_suite_load_with_the_reference_default_hand_collisions():
 
 
 def test_beyond_the_record_capacity_the_deepest_contacts_are_kept():
-    """Hands flailing over their whole joint ranges need up to 29 contact records; the kernel holds 21.  It keeps the deepest
-    (records ordered by distance, a hand : hand contact as a unit), drops the shallow ones and flags the environment (diag bit 0)
-    — deterministically; the oracle emulates the same rule (orc_set_record_cap), so the trajectories still agree."""
+    """Beyond its contact-record capacity (21; a cross-hand contact takes two records, every other contact one) the kernel keeps
+    the deepest records (ordered by distance, a cross-hand contact as a unit), drops the shallow ones and flags the environment
+    (diag bit 0) — deterministically; the oracle emulates the same rule (orc_set_record_cap), so the trajectories still agree.
+    Hands flailing over their whole joint ranges need up to ~17 records: the capacity is lowered to 12 for the test."""
+    CAP = 12
     fm, model, batch = helpers.make_native("piano_with_shadow_hands", nenv=2, scene_kw=HC)
-    om = O.OracleModel(fm); om.set_option(maxcon=60); om.set_record_cap(21)
+    batch.debug_set_record_cap(CAP)
+    om = O.OracleModel(fm); om.set_option(maxcon=60); om.set_record_cap(CAP)
     od = O.OracleData(om); od.reset()
     nv, nu = fm.meta["nv"], fm.meta["nu"]
     batch.set_state(np.zeros((2, nv)), np.zeros((2, nv)), np.zeros((2, nv)))
