@@ -448,8 +448,13 @@ __device__ __noinline__ int pgs_solve(Smem* smp, const int h, const int bar_id, 
 
 // Jacobian entries of the lane's dof in a contact record whose chain is any list of dofs (hand-collision instantiation: the
 // chain of a same-hand contact is not a root path, so the lane's depth does not index it)
-__device__ __forceinline__ void lane_jac(const Contact& cn, int lane, double& j0, double& j1, double& j2) {
+__device__ __forceinline__ void lane_jac(const Contact& cn, int lane, int lsub, int ldc, double& j0, double& j1, double& j2) {
   j0 = 0; j1 = 0; j2 = 0;
+  if (cn.key != -4) {  // root path: the lane's depth indexes it
+    const int link = cn.link;
+    if (lane <= link && link < lane + lsub) { j0 = cn.Jc[0][ldc]; j1 = cn.Jc[1][ldc]; j2 = cn.Jc[2][ldc]; }
+    return;
+  }
   const int dep = cn.dep & 0xff;
   for (int d = 0; d <= dep; d++)
     if (cn.chain[d] == lane) { j0 = cn.Jc[0][d]; j1 = cn.Jc[1][d]; j2 = cn.Jc[2][d]; }
@@ -556,8 +561,8 @@ __device__ __noinline__ int pgs_solve_hc(Smem* smp, const int h, const int bar_i
         const bool cross = pair && cs.hand != cn.hand;
         if (mineP || mineS) {  // warp-uniform
           double j0 = 0, j1 = 0, j2 = 0, k0 = 0, k1 = 0, k2 = 0;
-          if (mineP) lane_jac(cn, lane, j0, j1, j2);
-          if (mineS) lane_jac(cs, lane, k0, k1, k2);
+          if (mineP) lane_jac(cn, lane, lsub, ldc, j0, j1, j2);
+          if (mineS) lane_jac(cs, lane, lsub, ldc, k0, k1, k2);
           double p0 = (j0 + k0) * va, p1 = (j1 + k1) * va, p2 = (j2 + k2) * va;
           const int key = cn.key, depq = cn.dep;
           double Ab[9], fold[3], rbase[3];
@@ -1704,7 +1709,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
         for (int ci = 0; ci < nmine; ci++) {
           const Contact& cn = sm.u.con[sm.hlist[h][ci]];
           const int link = cn.link;
-          if (HC) { double j0, j1, j2; lane_jac(cn, lane, j0, j1, j2); wq += j0 * cn.f[0] + j1 * cn.f[1] + j2 * cn.f[2]; }
+          if (HC) { double j0, j1, j2; lane_jac(cn, lane, lsub, ldc, j0, j1, j2); wq += j0 * cn.f[0] + j1 * cn.f[1] + j2 * cn.f[2]; }
           else if (lane <= link && link < lane + lsub) wq += cn.Jc[0][ldc] * cn.f[0] + cn.Jc[1][ldc] * cn.f[1] + cn.Jc[2][ldc] * cn.f[2];
         }
         sm.wbuf[h][lane] = wq;
@@ -1819,7 +1824,7 @@ __global__ void __launch_bounds__(32 * NW * EPB, EPB > 1 ? RP_EPB_MINBLOCKS : (N
       for (int ci = 0; ci < nmine; ci++) {
         const Contact& cn = sm.u.con[sm.hlist[h][ci]];
         const int link = cn.link;
-        if (HC) { double j0, j1, j2; lane_jac(cn, lane, j0, j1, j2); qfrc_c += j0 * cn.f[0] + j1 * cn.f[1] + j2 * cn.f[2]; }
+        if (HC) { double j0, j1, j2; lane_jac(cn, lane, lsub, ldc, j0, j1, j2); qfrc_c += j0 * cn.f[0] + j1 * cn.f[1] + j2 * cn.f[2]; }
         else if (lane <= link && link < lane + lsub) qfrc_c += cn.Jc[0][ldc] * cn.f[0] + cn.Jc[1][ldc] * cn.f[1] + cn.Jc[2][ldc] * cn.f[2];
       }
     }

@@ -18,3 +18,5 @@ for n in ("bench20", "bench40"):
         d = json.load(open("$OUT/%s.json" % n)); print(n, d["ms_per_step"], d["value"], d["e2e"]["value"], d.get("cpu_baseline", {}).get("value"), (d.get("full_episode") or {}).get("ms_per_step"))
     except Exception as e: print(n, "failed", e)
 PY
+echo "== contact-record overflow rate"; timeout 600 python scripts/gpu_overflow_rate.py 4096 200 > $OUT/overflow.txt 2>&1; cat $OUT/overflow.txt
+echo "== gpu tests"; timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?"; tail -2 $OUT/pytest.log

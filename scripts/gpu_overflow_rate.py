@@ -16,11 +16,11 @@ for kw in (dict(disable_hand_collisions=False), dict(disable_hand_collisions=Fal
     obs = torch.empty((N, model.obs_dim), dtype=torch.float64, device="cuda"); rew = torch.empty(N, dtype=torch.float64, device="cuda")
     dis = torch.empty_like(rew); st = torch.empty(N, dtype=torch.uint8, device="cuda")
     b.reset(None, obs.data_ptr())
-    over = np.zeros(N, bool); bad = np.zeros(N, bool); mx = 0; hist = []
+    over = np.zeros(N, bool); bad = np.zeros(N, bool); mx = 0; hist = []; nflag = 0
     for t in range(steps):
         a = lo_t + (hi_t - lo_t) * torch.rand((N, model.act_dim), generator=g, device="cuda", dtype=torch.float64)
         b.step(a.data_ptr(), obs.data_ptr(), rew.data_ptr(), dis.data_ptr(), st.data_ptr())
         d = b.get_diag()
-        over |= (d["flags"] & 1) != 0; bad |= (d["flags"] & 2) != 0; mx = max(mx, int(d["ncon"].max())); hist.append(float(d["ncon"].mean()))
-    print(kw, f"envs {N} steps {steps}: environments that ever overflowed {over.sum()} ({100*over.mean():.2f} %), diverged {bad.sum()}, max contacts {mx}, mean contacts {np.mean(hist):.2f}", flush=True)
+        nflag += int(((d["flags"] & 1) != 0).sum()); over |= (d["flags"] & 1) != 0; bad |= (d["flags"] & 2) != 0; mx = max(mx, int(d["ncon"].max())); hist.append(float(d["ncon"].mean()))
+    print(kw, f"envs {N} steps {steps}: control steps with an overflowing substep {100*nflag/(N*steps):.3f} % of {N*steps}, environments that ever overflowed {over.sum()} ({100*over.mean():.2f} %), diverged {bad.sum()}, max contacts {mx}, mean contacts {np.mean(hist):.2f}", flush=True)
     b.close()

@@ -27,7 +27,7 @@ def ranges(marks, end):
 
 
 k0 = line_of("rp_step_kernel(RpKernelArgs a) {")
-KERNEL = ranges([("rp_step_kernel(RpKernelArgs a) {", "prologue + phase barrier"), ("hand kinematics (by level)", "kinematics"),
+KERNEL = ranges([("rp_step_kernel(RpKernelArgs a) {", "prologue"), ("hand kinematics (by level)", "kinematics"),
                  ("publish S, velocities", "RNE / CRB / scatter M"), ("actuation (lane = actuator)", "actuation, smooth, key rows"),
                  ("hand friction + limit rows", "hand friction / limit row setup"), ("collision (lane = geom of this warp's hand)", "collision"),
                  ("publish what the contact rows read from the other warp", "contact rows + lists"), ("== warm start", "warm start, U, cost"),
@@ -44,7 +44,8 @@ end = next(i for i in range(start + 1, len(lines)) if lines[i].startswith("//---
 func, off2, pend, cur = "kernel", {}, [], None
 for l in lines[start:end]:
     if l.startswith("$") and l.endswith(":"):
-        func = "pgs_solve" if ("pgs_solve" in l and "pgs_solve_hc" not in l) else ("sweep_inverse" if "sweep_inverse" in l else "library routine")
+        func = ("pgs_solve" if ("pgs_solve" in l and "pgs_solve_hc" not in l) else "sweep_inverse" if "sweep_inverse" in l
+                else "phase barrier (phase_sync)" if "phase_sync" in l else "library routine")
         continue
     m = re.search(r'//## File "(.*?)", line (\d+)( inlined at)?', l)
     if m:
@@ -83,7 +84,7 @@ for r in rows[2:]:
     for h, k in stalls: a[h] += int(r[k] or 0)
 print(f"total warp-instr {tot_i:.3e}  samples {tot_s}")
 print(f"{'stage':34s} {'sass':>6s} {'inst%':>6s} {'samp%':>6s} {'rel':>5s}  top stalls (% of the stage's samples)")
-order = [n for _, _, n in KERNEL[:8]] + ["sweep_inverse"] + [n for _, _, n in PGS] + [n for _, _, n in KERNEL[8:]] + ["library routine", "other"]
+order = ["phase barrier (phase_sync)"] + [n for _, _, n in KERNEL[:8]] + ["sweep_inverse"] + [n for _, _, n in PGS] + [n for _, _, n in KERNEL[8:]] + ["library routine", "other"]
 for name in order:
     a = agg.get(name)
     if not a or not a["samp"]: continue
