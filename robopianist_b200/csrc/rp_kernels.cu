@@ -5,12 +5,13 @@
 // (robopianist/suite/tasks/piano_with_shadow_hands.py:176-220, tasks/base.py:28-31; the physics is
 // MuJoCo's mj_step, restated stage by stage) with a single launch.
 //
-// Mapping: rp_step_kernel<2> runs two warps per environment, warp h owning hand h (lane == link ==
-// dof of that hand, 26 of 32 lanes); the 88 keys are spread over the 64 threads (thread t owns keys
-// t and t+64).  The two hands only interact through keys they both touch, so each warp runs its own
-// instruction stream — kinematics, RNE/CRB, M^-1, constraint rows, Gauss-Seidel — and the block
+// Mapping: rp_step_kernel<2, EPB, HC> runs two warps per environment, warp h owning hand h (lane == link ==
+// dof of that hand, up to 26 of 32 lanes; hands with fewer dofs are padded with inert links); the 88 keys are
+// spread over the 64 threads (thread t owns keys t and t+64).  The two hands only interact through keys they both
+// touch — and, in the HC instantiation (hand geoms colliding with each other), through cross-hand contacts — so each
+// warp runs its own instruction stream — kinematics, RNE/CRB, M^-1, constraint rows, Gauss-Seidel — and the block
 // synchronises where key / contact data crosses (a handful of barriers per substep plus one per
-// PGS iteration for the convergence test).  rp_step_kernel<1> is the keys-only variant
+// PGS iteration for the convergence test).  rp_step_kernel<1, 1, false> is the keys-only variant
 // (self_actuated_piano): one warp, lane l owns keys l, l+32, l+64.
 // Shared memory holds the per-hand inverse inertia, motion subspaces, contact blocks and key
 // arrays; everything lane-owned lives in registers across the stages of a substep.
