@@ -307,15 +307,15 @@ __device__ __noinline__ int pgs_solve(Smem* smp, const int h, const int bar_id, 
         const int i = __ffs(m) - 1;
         const double col = pcol[i * RS];
         const double dl = fx - fr_f;
+        const double dbc = shfl(dl, i);  // (the cost term is computed in the shadow of this shuffle and broadcast off the va chain)
         const double imp = dl * (0.5 * dl * fr_AR + res);
-        const double dbc = shfl(dl, i), ibc = shfl(imp, i);
         va -= col * dbc;
-        improvement -= ibc;
         if (lane == i) fr_f = fx;
         res = fbase + va;
         x = fr_f - res * fr_ARi;
         fx = x < fr_lo ? fr_lo : x;
         fx = x > fr_hi ? fr_hi : fx;
+        improvement -= shfl(imp, i);
         m = __ballot_sync(FULL, hl && lane > i && fx != fr_f);
       }
     }
@@ -345,10 +345,11 @@ __device__ __noinline__ int pgs_solve(Smem* smp, const int h, const int bar_id, 
         const double x = lm_f - res * lm_ARi;
         const double fn = x < 0 ? 0.0 : x;
         const double dl = fn - lm_f;
+        const double col = Ah[i * RS + lc];
+        const double dbc = shfl(lm_J * dl, i);
         const double imp = dl * (0.5 * dl * lm_AR + res);
-        const double dbc = shfl(lm_J * dl, i), ibc = shfl(imp, i);
-        va -= Ah[i * RS + lc] * dbc;
-        improvement -= ibc;
+        va -= col * dbc;
+        improvement -= shfl(imp, i);
         if (lane == i) lm_f = fn;
       }
     }
@@ -378,26 +379,40 @@ __device__ __noinline__ int pgs_solve(Smem* smp, const int h, const int bar_id, 
           double p0 = j0 * va, p1 = j1 * va, p2 = j2 * va;
           const int key = cn.key, depq = cn.dep;
           double Ab[9], fold[3], rbase[3];
+          // The J*va reduction (five shuffle stages, each followed by adds that wait ~25 cycles for the shuffles) interleaved by hand
+          // with the block's loads and the ray denominator: the compiler keeps shuffle sequences compact and neither hoists
+          // independent work into their latency nor overlaps the two chains (measured: the loads and the ray's dependent
+          // multiply-adds were issued first, the reduction after them).  Same operations as pgs_elliptic_ray.
+          double s0 = __shfl_xor_sync(FULL, p0, 16), s1 = __shfl_xor_sync(FULL, p1, 16), s2 = __shfl_xor_sync(FULL, p2, 16);
 #pragma unroll
           for (int k = 0; k < 9; k++) Ab[k] = cn.A[k];
+#pragma unroll
+          for (int r = 0; r < 3; r++) fold[r] = cn.f[r];
+          p0 += s0; p1 += s1; p2 += s2;
+          s0 = __shfl_xor_sync(FULL, p0, 8); s1 = __shfl_xor_sync(FULL, p1, 8); s2 = __shfl_xor_sync(FULL, p2, 8);
           const double cmu = cn.mu;
-          const rp::EllInv inv = cn.inv;
           const double vak = sm.vak[key >= 0 ? key : 0], jkm0 = key >= 0 ? 1.0 : 0.0;
           const double jk0 = cn.Jk[0], jk1 = cn.Jk[1], jk2 = cn.Jk[2], invMk = cn.invMk;
+          const double cb0 = cn.b[0], cb1 = cn.b[1], cb2 = cn.b[2], cR0 = cn.R[0], cR1 = cn.R[1], cR2 = cn.R[2];
+          p0 += s0; p1 += s1; p2 += s2;
+          s0 = __shfl_xor_sync(FULL, p0, 4); s1 = __shfl_xor_sync(FULL, p1, 4); s2 = __shfl_xor_sync(FULL, p2, 4);
+          double rv[3];
 #pragma unroll
-          for (int r = 0; r < 3; r++) { fold[r] = cn.f[r]; rbase[r] = cn.b[r] + cn.R[r] * fold[r] + jkm0 * cn.Jk[r] * vak; }
+          for (int r = 0; r < 3; r++) rv[r] = Ab[3 * r] * fold[0] + Ab[3 * r + 1] * fold[1] + Ab[3 * r + 2] * fold[2];
+          const rp::EllInv inv = cn.inv;
+          p0 += s0; p1 += s1; p2 += s2;
+          s0 = __shfl_xor_sync(FULL, p0, 2); s1 = __shfl_xor_sync(FULL, p1, 2); s2 = __shfl_xor_sync(FULL, p2, 2);
+          const double denom = rp::dot3(fold, rv);
+          const int den_ok = denom >= RP_MINVAL;
+          const double rden = rp::rcp(denom);
+          rbase[0] = cb0 + cR0 * fold[0] + jkm0 * jk0 * vak; rbase[1] = cb1 + cR1 * fold[1] + jkm0 * jk1 * vak; rbase[2] = cb2 + cR2 * fold[2] + jkm0 * jk2 * vak;
+          p0 += s0; p1 += s1; p2 += s2;
+          s0 = __shfl_xor_sync(FULL, p0, 1); s1 = __shfl_xor_sync(FULL, p1, 1); s2 = __shfl_xor_sync(FULL, p2, 1);
 #if RP_NU > 0
           double u0 = 0, u1 = 0, u2 = 0;
           if (c < RP_NU) { const double* Uc = &sm.v.U[c][0][lc]; u0 = Uc[0]; u1 = Uc[NL]; u2 = Uc[2 * NL]; }
 #endif
-          int den_ok;
-          const double rden = rp::pgs_elliptic_ray(Ab, fold, &den_ok);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            p0 += __shfl_xor_sync(FULL, p0, o);
-            p1 += __shfl_xor_sync(FULL, p1, o);
-            p2 += __shfl_xor_sync(FULL, p2, o);
-          }
+          p0 += s0; p1 += s1; p2 += s2;
           PTICK(16)
           const double res[3] = {rbase[0] + p0, rbase[1] + p1, rbase[2] + p2};
           double f[3] = {fold[0], fold[1], fold[2]};
@@ -508,15 +523,15 @@ __device__ __noinline__ int pgs_solve_hc(Smem* smp, const int h, const int bar_i
         const int i = __ffs(m) - 1;
         const double col = pcol[i * RS];
         const double dl = fx - fr_f;
+        const double dbc = shfl(dl, i);  // (the cost term is computed in the shadow of this shuffle and broadcast off the va chain)
         const double imp = dl * (0.5 * dl * fr_AR + res);
-        const double dbc = shfl(dl, i), ibc = shfl(imp, i);
         va -= col * dbc;
-        improvement -= ibc;
         if (lane == i) fr_f = fx;
         res = fbase + va;
         x = fr_f - res * fr_ARi;
         fx = x < fr_lo ? fr_lo : x;
         fx = x > fr_hi ? fr_hi : fx;
+        improvement -= shfl(imp, i);
         m = __ballot_sync(FULL, hl && lane > i && fx != fr_f);
       }
     }
@@ -543,10 +558,11 @@ __device__ __noinline__ int pgs_solve_hc(Smem* smp, const int h, const int bar_i
         const double x = lm_f - res * lm_ARi;
         const double fn = x < 0 ? 0.0 : x;
         const double dl = fn - lm_f;
+        const double col = Ah[i * RS + lc];
+        const double dbc = shfl(lm_J * dl, i);
         const double imp = dl * (0.5 * dl * lm_AR + res);
-        const double dbc = shfl(lm_J * dl, i), ibc = shfl(imp, i);
-        va -= Ah[i * RS + lc] * dbc;
-        improvement -= ibc;
+        va -= col * dbc;
+        improvement -= shfl(imp, i);
         if (lane == i) lm_f = fn;
       }
     }
@@ -567,22 +583,33 @@ __device__ __noinline__ int pgs_solve_hc(Smem* smp, const int h, const int bar_i
           double p0 = (j0 + k0) * va, p1 = (j1 + k1) * va, p2 = (j2 + k2) * va;
           const int key = cn.key, depq = cn.dep;
           double Ab[9], fold[3], rbase[3];
+          // reduction interleaved with the block's loads and the ray denominator (see pgs_solve)
+          double s0 = __shfl_xor_sync(FULL, p0, 16), s1 = __shfl_xor_sync(FULL, p1, 16), s2 = __shfl_xor_sync(FULL, p2, 16);
 #pragma unroll
           for (int k = 0; k < 9; k++) Ab[k] = cn.A[k];
+#pragma unroll
+          for (int r = 0; r < 3; r++) fold[r] = cn.f[r];
+          p0 += s0; p1 += s1; p2 += s2;
+          s0 = __shfl_xor_sync(FULL, p0, 8); s1 = __shfl_xor_sync(FULL, p1, 8); s2 = __shfl_xor_sync(FULL, p2, 8);
           const double cmu = cn.mu;
-          const rp::EllInv inv = cn.inv;
           const double vak = sm.vak[key >= 0 ? key : 0], jkm0 = key >= 0 ? 1.0 : 0.0;
           const double jk0 = cn.Jk[0], jk1 = cn.Jk[1], jk2 = cn.Jk[2], invMk = cn.invMk;
+          const double cb0 = cn.b[0], cb1 = cn.b[1], cb2 = cn.b[2], cR0 = cn.R[0], cR1 = cn.R[1], cR2 = cn.R[2];
+          p0 += s0; p1 += s1; p2 += s2;
+          s0 = __shfl_xor_sync(FULL, p0, 4); s1 = __shfl_xor_sync(FULL, p1, 4); s2 = __shfl_xor_sync(FULL, p2, 4);
+          double rv[3];
 #pragma unroll
-          for (int r = 0; r < 3; r++) { fold[r] = cn.f[r]; rbase[r] = cn.b[r] + cn.R[r] * fold[r] + jkm0 * cn.Jk[r] * vak; }
-          int den_ok;
-          const double rden = rp::pgs_elliptic_ray(Ab, fold, &den_ok);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            p0 += __shfl_xor_sync(FULL, p0, o);
-            p1 += __shfl_xor_sync(FULL, p1, o);
-            p2 += __shfl_xor_sync(FULL, p2, o);
-          }
+          for (int r = 0; r < 3; r++) rv[r] = Ab[3 * r] * fold[0] + Ab[3 * r + 1] * fold[1] + Ab[3 * r + 2] * fold[2];
+          const rp::EllInv inv = cn.inv;
+          p0 += s0; p1 += s1; p2 += s2;
+          s0 = __shfl_xor_sync(FULL, p0, 2); s1 = __shfl_xor_sync(FULL, p1, 2); s2 = __shfl_xor_sync(FULL, p2, 2);
+          const double denom = rp::dot3(fold, rv);
+          const int den_ok = denom >= RP_MINVAL;
+          const double rden = rp::rcp(denom);
+          rbase[0] = cb0 + cR0 * fold[0] + jkm0 * jk0 * vak; rbase[1] = cb1 + cR1 * fold[1] + jkm0 * jk1 * vak; rbase[2] = cb2 + cR2 * fold[2] + jkm0 * jk2 * vak;
+          p0 += s0; p1 += s1; p2 += s2;
+          s0 = __shfl_xor_sync(FULL, p0, 1); s1 = __shfl_xor_sync(FULL, p1, 1); s2 = __shfl_xor_sync(FULL, p2, 1);
+          p0 += s0; p1 += s1; p2 += s2;
           if (cross) {  // both warps are here: exchange the halves of J * va (the block and the old force are already read)
             if (lane == 0) { double* r = sm.red[0][h]; r[2] = p0; r[3] = p1; r[4] = p2; }
             hand_pair_sync(bar_id);
