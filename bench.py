@@ -34,7 +34,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 ENVS_PER_GPU = 4096
-NCU_DRAM_BYTES_PER_LAUNCH = 51.7e6  # profiles/r02_ncu_end.csv: dram__bytes_read.sum (24.5 MB) + dram__bytes_write.sum (27.2 MB) of one captured launch, 4096 envs
+NCU_DRAM_BYTES_PER_LAUNCH = 48.2e6  # profiles/r02_ncu_end.csv: dram__bytes_read.sum (24.1 MB) + dram__bytes_write.sum (24.1 MB) of one captured launch, 4096 envs
 SONG = "TwinkleTwinkleRousseau"
 METRIC = "env-steps/sec at 4096 envs/GPU (piano_with_shadow_hands, 10 substeps/step)"
 
