@@ -143,6 +143,14 @@ int rp_physics_step(rp_batch *, const double *ctrl_dev, int nsub);
 int rp_get_state(rp_batch *, double *qpos, double *qvel, double *qacc_warmstart, int32_t *t_idx);
 int rp_set_state(rp_batch *, const double *qpos, const double *qvel, const double *qacc_warmstart,
                  const int32_t *t_idx);
+/* Checkpoint / resume (the reference has none: its episodes always start from qpos0).  One host blob
+ * with everything a later step depends on: qpos, qvel, qacc_warmstart, the controls and the sustain state of the last
+ * action, t_idx and the episode state, the previous key activation, the musical-metric accumulators, the launch order, and
+ * — when enabled — the hand offsets with their generator states and the MIDI event stream.  A batch of the same model,
+ * size and optional features restored from it continues bit for bit.  Song tables (rp_set_song) are not part of it. */
+size_t rp_checkpoint_bytes(rp_batch *);
+int rp_checkpoint_save(rp_batch *, void *host_buf, size_t bytes);
+int rp_checkpoint_load(rp_batch *, const void *host_buf, size_t bytes);
 /* Diagnostics of the last substep (HOST buffers): ncon [N], niter [N] (PGS sweeps used),
  * flags [N]: bit0 contact overflow (more than RP_MAXCON contacts), bit1 non-finite state, bit2 hand tree too deep,
  * bit3 a hand collider the narrowphase does not cover (box / cylinder / mesh; rp_flat_model.geom_collide == 0) came

@@ -848,6 +848,57 @@ extern "C" int rp_set_state(rp_batch* b, const double* qpos, const double* qvel,
   if (t_idx) CUDA_OK(cudaMemcpy(b->t_idx, t_idx, sizeof(int32_t) * N, cudaMemcpyHostToDevice));
   return 0;
 }
+// ---- checkpoint: every piece of per-environment state a later step depends on, as one host blob (header + arrays in the
+// device layout).  A batch restored from it continues bit for bit (tests/test_gpu_parity.py).
+struct CkptHeader { uint32_t magic, version; int32_t nenv, nv_dev, nu, midi_cap, has_offsets, reserved; };
+struct CkptPart { void* dev; size_t bytes; };
+static std::vector<CkptPart> ckpt_parts(rp_batch* b) {
+  const size_t N = b->nenv, nv = b->model->nv_dev, nu = b->model->nu;
+  std::vector<CkptPart> p = {
+      {b->qpos, N * nv * sizeof(double)}, {b->qvel, N * nv * sizeof(double)}, {b->qacc_ws, N * nv * sizeof(double)},
+      {b->ctrl, N * nu * sizeof(double)}, {b->sustain, N * sizeof(double)}, {b->t_idx, N * sizeof(int32_t)},
+      {b->step_type_state, N * sizeof(int32_t)}, {b->activation, N * RP_NK}, {b->metrics, N * RP_METRICS_STRIDE * sizeof(double)},
+      {b->work, N * sizeof(int32_t)}, {b->order, N * sizeof(int32_t)}};
+  if (b->hand_offset) { p.push_back({b->hand_offset, N * sizeof(double)}); p.push_back({b->rng_state, N * sizeof(uint64_t)}); }
+  if (b->midi_events) { p.push_back({b->midi_events, N * (size_t)b->midi_cap * sizeof(uint32_t)}); p.push_back({b->midi_count, N * sizeof(int32_t)}); }
+  return p;
+}
+extern "C" size_t rp_checkpoint_bytes(rp_batch* b) {
+  size_t n = sizeof(CkptHeader) + sizeof(int32_t);  // + order_valid
+  for (const CkptPart& q : ckpt_parts(b)) n += q.bytes;
+  return n;
+}
+extern "C" int rp_checkpoint_save(rp_batch* b, void* host_buf, size_t bytes) {
+  if (!host_buf || bytes < rp_checkpoint_bytes(b)) return fail("checkpoint buffer too small (rp_checkpoint_bytes)");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  CkptHeader h = {0x52504b43u, 1u, b->nenv, b->model->nv_dev, b->model->nu, b->midi_events ? b->midi_cap : 0, b->hand_offset ? 1 : 0, 0};
+  char* o = (char*)host_buf;
+  memcpy(o, &h, sizeof(h)); o += sizeof(h);
+  int32_t ov = b->order_valid;
+  memcpy(o, &ov, sizeof(ov)); o += sizeof(ov);
+  for (const CkptPart& q : ckpt_parts(b)) { CUDA_OK(cudaMemcpy(o, q.dev, q.bytes, cudaMemcpyDeviceToHost)); o += q.bytes; }
+  return 0;
+}
+extern "C" int rp_checkpoint_load(rp_batch* b, const void* host_buf, size_t bytes) {
+  if (!host_buf || bytes < sizeof(CkptHeader) + sizeof(int32_t)) return fail("checkpoint blob too small");
+  CkptHeader h;
+  memcpy(&h, host_buf, sizeof(h));
+  if (h.magic != 0x52504b43u || h.version != 1u) return fail("not a roboplay checkpoint (magic / version)");
+  if (h.nenv != b->nenv || h.nv_dev != b->model->nv_dev || h.nu != b->model->nu) return fail("checkpoint of a different batch shape or model");
+  if ((h.midi_cap != 0) != (b->midi_events != nullptr) || (h.midi_cap && h.midi_cap != b->midi_cap) || (h.has_offsets != 0) != (b->hand_offset != nullptr))
+    return fail("checkpoint and batch differ in their optional state (rp_midi_enable / rp_randomize_hand_positions before loading)");
+  if (bytes < rp_checkpoint_bytes(b)) return fail("checkpoint blob truncated");
+  CUDA_OK(cudaSetDevice(b->device));
+  CUDA_OK(cudaStreamSynchronize(b->stream));
+  const char* o = (const char*)host_buf + sizeof(h);
+  int32_t ov;
+  memcpy(&ov, o, sizeof(ov)); o += sizeof(ov);
+  for (const CkptPart& q : ckpt_parts(b)) { CUDA_OK(cudaMemcpy(q.dev, o, q.bytes, cudaMemcpyHostToDevice)); o += q.bytes; }
+  b->order_valid = ov;
+  return 0;
+}
+
 extern "C" int rp_get_diag(rp_batch* b, int32_t* ncon, int32_t* niter, int32_t* flags) {
   size_t N = b->nenv;
   std::vector<int32_t> tmp(N * 3);

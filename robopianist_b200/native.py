@@ -22,7 +22,7 @@ EXPORTS = [
     "rp_reward_terms", "rp_batch_create", "rp_batch_destroy", "rp_set_option", "rp_reset", "rp_step",
     "rp_step_host", "rp_physics_step", "rp_get_state", "rp_set_state", "rp_get_diag", "rp_get_aux",
     "rp_launch_count", "rp_step_staged", "rp_host_buffers", "rp_get_metrics", "rp_midi_enable", "rp_get_midi", "rp_set_block_envs", "rp_set_song",
-    "rp_randomize_hand_positions", "rp_get_hand_offsets",
+    "rp_randomize_hand_positions", "rp_get_hand_offsets", "rp_checkpoint_bytes", "rp_checkpoint_save", "rp_checkpoint_load",
 ]
 
 
@@ -68,6 +68,10 @@ def lib():
         L.rp_set_block_envs.argtypes = [vp, C.c_int]
         L.rp_randomize_hand_positions.argtypes = [vp, C.c_int, C.c_uint64]
         L.rp_get_hand_offsets.argtypes = [vp, dp]
+        L.rp_checkpoint_bytes.restype = C.c_size_t
+        L.rp_checkpoint_bytes.argtypes = [vp]
+        L.rp_checkpoint_save.argtypes = [vp, vp, C.c_size_t]
+        L.rp_checkpoint_load.argtypes = [vp, vp, C.c_size_t]
         L.rp_get_midi.argtypes = [vp, C.POINTER(C.c_uint32), ip]
         L.rp_launch_count.restype = C.c_int64
         L.rp_launch_count.argtypes = [vp]
@@ -147,6 +151,17 @@ class Batch:
         out = np.zeros(self.nenv, np.float64)
         _check(lib().rp_get_hand_offsets(self.ptr, _dp(out)))
         return out
+
+    def checkpoint(self) -> np.ndarray:
+        """Everything a later step depends on as one uint8 array (rp_checkpoint_save); `restore` continues bit for bit."""
+        n = lib().rp_checkpoint_bytes(self.ptr)
+        buf = np.empty(n, np.uint8)
+        _check(lib().rp_checkpoint_save(self.ptr, buf.ctypes.data_as(C.c_void_p), n))
+        return buf
+
+    def restore(self, blob: np.ndarray):
+        blob = np.ascontiguousarray(blob, np.uint8)
+        _check(lib().rp_checkpoint_load(self.ptr, blob.ctypes.data_as(C.c_void_p), blob.size))
 
     def reset(self, mask_ptr=None, obs_ptr=None):
         _check(lib().rp_reset(self.ptr, mask_ptr, obs_ptr))

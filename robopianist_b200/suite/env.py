@@ -307,6 +307,20 @@ class BatchedPianoEnv:
         came within reach of the piano — its contact, if any, was not generated."""
         return (self.batch.get_diag()["flags"] & 8) != 0
 
+    def state_dict(self):
+        """Checkpoint of the running batch: the device state (rp_checkpoint_save) plus the host-side song of the running
+        episode; `load_state_dict` on an environment built with the same arguments resumes bit for bit."""
+        return {"device": self.batch.checkpoint(), "goal": self.goal_table.copy(), "fingering": self.fingering_table.copy(),
+                "random_state": self.random_state.get_state()}
+
+    def load_state_dict(self, sd):
+        if sd["goal"].shape != self.goal_table.shape or not (np.array_equal(sd["goal"], self.goal_table)
+                                                              and np.array_equal(sd["fingering"], self.fingering_table)):
+            self.goal_table, self.fingering_table = sd["goal"].copy(), sd["fingering"].copy()
+            self.batch.set_song(self.goal_table, self.fingering_table)
+        self.batch.restore(sd["device"])
+        self.random_state.set_state(sd["random_state"])
+
     def get_state(self):
         return self.batch.get_state()
 

@@ -197,3 +197,51 @@ def test_multi_device_env_matches_one_device():
     torch.cuda.synchronize(0); two.synchronize()
     assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2) and torch.equal(s1, s2)
     one.close(); two.close()
+
+
+def test_checkpoint_resumes_bit_for_bit():
+    """rp_checkpoint_save / rp_checkpoint_load (BatchedPianoEnv.state_dict / load_state_dict): a batch restored in the middle of
+    its episodes — random hand shifts, MIDI recording and hand collisions enabled, some environments past an auto-reset —
+    continues exactly like the one that kept running; a blob of another shape is refused."""
+    from robopianist_b200 import native, suite
+    kw = dict(primitive_fingertip_collisions=True, gravity_compensation=True, trim_silence=True, randomize_hand_positions=True,
+              wrong_press_termination=True)
+    N = 16
+
+    def make():
+        e = suite.load("RoboPianist-debug-TwinkleTwinkleRousseau-v0", seed=3, num_envs=N, task_kwargs=kw)
+        e.enable_midi(512)
+        return e
+
+    a, b = make(), make()
+    acts = helpers.twinkle_actions()
+    rng = np.random.default_rng(2)
+
+    def action(t):
+        x = np.tile(acts[t % 158], (N, 1)); x[:, :44] += rng.normal(0, 0.05, (N, 44))
+        return torch.tensor(x, dtype=torch.float64, device="cuda")
+
+    a.reset()
+    for t in range(15):
+        a.step(action(t))
+    sd = a.state_dict()
+    tail = [action(t) for t in range(15, 30)]
+    outs_a = []
+    for x in tail:
+        o, r, d, s = a.step(x)
+        outs_a.append((o.clone(), r.clone(), d.clone(), s.clone()))
+    b.reset()                      # different random shifts and state until the checkpoint is loaded
+    b.load_state_dict(sd)
+    for x, (o1, r1, d1, s1) in zip(tail, outs_a):
+        o, r, d, s = b.step(x)
+        assert torch.equal(o, o1) and torch.equal(r, r1) and torch.equal(d, d1) and torch.equal(s, s1)
+    qa, qb = a.get_state(), b.get_state()
+    assert all(np.array_equal(x, y) for x, y in zip(qa, qb))
+    assert (a.batch.get_hand_offsets() == b.batch.get_hand_offsets()).all()
+    ma, mb = a.get_all_midi_messages(), b.get_all_midi_messages()
+    assert ma == mb
+    other = suite.load("RoboPianist-debug-TwinkleTwinkleRousseau-v0", seed=3, num_envs=N + 1, task_kwargs=kw)
+    with pytest.raises(native.NativeError):
+        other.batch.restore(sd["device"])
+    for e in (a, b, other):
+        e.close()
