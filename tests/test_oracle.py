@@ -560,3 +560,151 @@ def test_uncovered_colliders_cannot_reach_the_piano_within_joint_limits(hands):
         assert not _uncovered_boxes_near_piano(fm, d, q)
     q = np.zeros(140); q[89] = 0.15; q[91] = 1.57
     assert "rh_shadow_hand/rh_palm_geom1" in _uncovered_boxes_near_piano(fm, d, q)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# hand geoms colliding with each other (disable_hand_collisions=False)
+@pytest.fixture(scope="module")
+def hands_hc():
+    fm = cache.load_scene(gravity_compensation=True, disable_hand_collisions=False)
+    om = O.OracleModel(fm)
+    om.set_option(maxcon=60)
+    return fm, om
+
+
+def _hc_rollout(fm, om, substeps, seed=5, amp=0.6):
+    """Hands driven into each other with slowly varying finger targets: cross-hand, same-hand and piano contacts."""
+    d = O.OracleData(om); d.reset()
+    names = fm.meta["actuator_names"]
+    lo, hi = fm.actuator_ctrlrange[:, 0], fm.actuator_ctrlrange[:, 1]
+    rng = np.random.default_rng(seed); target = rng.random(fm.meta["nu"])
+    for t in range(substeps):
+        if t % 100 == 0:
+            target = rng.random(fm.meta["nu"])
+        if t % 10 == 0:
+            ctrl = lo + (hi - lo) * (0.5 + amp * (target - 0.5))
+            for i, n in enumerate(names):
+                if n.endswith("forearm_tx"):
+                    ctrl[i] = (-0.2 if "rh_" in n else 0.2) * min(1.0, t / 200.0)
+                if n.endswith("forearm_ty"):
+                    ctrl[i] = 0.0
+        d.mj_step(ctrl)
+        yield t, d
+
+
+def test_hand_pair_contacts_geometry_and_jacobian(hands_hc):
+    """Hand : hand contacts of the oracle, independent of how they were computed: the reported distance is the brute-force
+    distance between the two capsule segments minus the radii, the normal points from geom 1 to geom 2 (sphere before capsule),
+    the position lies mid-way between the surfaces; the three Jacobian rows equal finite differences of the kinematics
+    (body 2 minus body 1), and for two bodies of one hand the columns of their common ancestors vanish exactly — the property
+    the kernel's single-record representation of such contacts rests on."""
+    fm, om = hands_hc
+    A = fm.arrays
+    probe = O.OracleData(om)
+    eps = 1e-7
+    seen = {"cross": 0, "self": 0}
+    ts = np.linspace(-1, 1, 2001)
+    for t, d in _hc_rollout(fm, om, 460):
+        if t % 45 != 44:
+            continue
+        d.call("orc_step1")   # mj_step leaves the arrays of the state before integration: rebuild them at the current qpos
+        if d.ncon == 0:
+            continue
+        typ, eid, J = d.efc_type(), d.efc_id(), d.efc("efc_J")
+        cons = d.contacts()
+        rows = [i for i in range(len(typ)) if typ[i] == 2][::3]
+        xpos0, xmat0 = d.xpos.copy(), d.xmat.copy()
+        for i in rows:
+            c = cons[eid[i]]
+            g1, g2 = c["geom1"], c["geom2"]
+            if A["geom_hand"][g1] < 0 or A["geom_hand"][g2] < 0:
+                continue
+            kind = "cross" if A["geom_hand"][g1] != A["geom_hand"][g2] else "self"
+            if seen[kind] >= 6:
+                continue
+            assert A["geom_type"][g1] <= A["geom_type"][g2]          # mj_collideGeoms orders the pair by type
+            # --- geometry
+            seg = []
+            for g in (g1, g2):
+                hl = A["geom_size"][g][1] if A["geom_type"][g] == 3 else 0.0
+                seg.append(d.geom_xpos[g][None, :] + ts[:, None] * hl * d.geom_xmat[g].reshape(3, 3)[:, 2][None, :])
+            d2 = ((seg[0][:, None, :] - seg[1][None, :, :]) ** 2).sum(-1)
+            ia, ib = np.unravel_index(np.argmin(d2), d2.shape)
+            dmin = np.sqrt(d2[ia, ib]) - A["geom_size"][g1][0] - A["geom_size"][g2][0]
+            n = c["frame"][0]
+            assert abs(c["dist"] - dmin) < 2e-6 and abs(np.linalg.norm(n) - 1) < 1e-12
+            assert n @ (seg[1][ib] - seg[0][ia]) > 0                   # from geom 1 towards geom 2
+            assert np.abs(c["pos"] - (seg[0][ia] + n * (A["geom_size"][g1][0] + 0.5 * c["dist"]))).max() < 1e-4
+            # --- Jacobian: finite differences of the two bodies' material points at the contact position
+            b1, b2 = int(A["geom_bodyid"][g1]), int(A["geom_bodyid"][g2])
+            loc = [xmat0[b].reshape(3, 3).T @ (c["pos"] - xpos0[b]) for b in (b1, b2)]
+            chain = lambda b: set(om_chain(fm, b))
+            c1, c2 = chain(b1), chain(b2)
+            for j in sorted(c1 | c2):
+                probe.qpos[:] = d.qpos
+                probe.qpos[j] += eps
+                probe.call("orc_kinematics")
+                p = [probe.xpos[b] + probe.xmat[b].reshape(3, 3) @ l for b, l in zip((b1, b2), loc)]
+                num = c["frame"] @ ((p[1] - p[0]) / eps)
+                assert np.abs(num - J[i:i + 3, j]).max() < 5e-6, (t, i, j)
+            common = c1 & c2
+            if kind == "self":
+                assert len(common) >= 4                                # forearm slides + wrist hinges at least
+                assert np.abs(J[i:i + 3][:, sorted(common)]).max() == 0.0
+                assert len((c1 | c2) - common) <= 10                   # what one contact record of the kernel holds
+            else:
+                assert not common
+            off = [j for j in range(fm.meta["nv"]) if j not in (c1 | c2)][:4]
+            assert np.abs(J[i:i + 3][:, off]).max() == 0
+            seen[kind] += 1
+    assert seen["cross"] >= 3 and seen["self"] >= 3, seen
+
+
+def om_chain(fm, b):
+    """dofs of body b's kinematic chain (root to b)."""
+    out = []
+    while b > 0:
+        out = [int(fm.body_dofadr[b]) + k for k in range(int(fm.body_dofnum[b]))] + out
+        b = int(fm.body_parentid[b])
+    return out
+
+
+def test_pgs_fixed_point_with_hand_contacts_satisfies_the_kkt_conditions(hands_hc):
+    """The optimality conditions of the dual problem (as in test_pgs_fixed_point_satisfies_the_kkt_conditions) with cross-hand
+    and same-hand contacts among the rows: elliptic contacts f in the friction cone, g in its dual cone, f . g = 0."""
+    fm, _ = hands_hc
+    om = O.OracleModel(fm, iterations=6000, tolerance=0.0)
+    om.set_option(maxcon=60)
+    checked = pairs = 0
+    for t, d in _hc_rollout(fm, om, 360):
+        if t % 60 != 59:
+            continue
+        d.call("orc_step1")
+        if d.ncon == 0:
+            continue
+        d.call("orc_smooth"); d.call("orc_solve_init"); d.call("orc_solve_iterate")
+        typ, eid = d.efc_type(), d.efc_id()
+        AR, b, f, loss = d.efc("efc_AR"), d.efc("efc_b"), d.efc("efc_force"), d.efc("efc_frictionloss")
+        g = AR @ f + b
+        sc = 1e-6 * max(1.0, np.abs(b).max())
+        cons = d.contacts()
+        i = 0
+        while i < len(typ):
+            if typ[i] == 0:
+                assert abs(f[i]) <= loss[i] + 1e-12
+                i += 1
+            elif typ[i] == 1:
+                assert f[i] >= 0 and g[i] > -sc
+                i += 1
+            else:
+                c = cons[eid[i]]
+                mu = c["friction"]
+                fn, ft = f[i], np.hypot(f[i + 1], f[i + 2])
+                gn, gt = g[i], np.hypot(g[i + 1], g[i + 2])
+                assert fn >= 0 and ft <= mu * fn + 1e-9
+                assert gn > -sc and mu * gt <= gn + 10 * sc
+                assert abs(f[i:i + 3] @ g[i:i + 3]) < 10 * sc * max(1.0, fn)
+                pairs += int(fm.geom_hand[c["geom1"]] >= 0 and fm.geom_hand[c["geom2"]] >= 0)
+                i += 3
+        checked += 1
+    assert checked >= 4 and pairs >= 4
