@@ -152,7 +152,8 @@ size_t rp_checkpoint_bytes(rp_batch *);
 int rp_checkpoint_save(rp_batch *, void *host_buf, size_t bytes);
 int rp_checkpoint_load(rp_batch *, const void *host_buf, size_t bytes);
 /* Diagnostics of the last substep (HOST buffers): ncon [N], niter [N] (PGS sweeps used),
- * flags [N]: bit0 contact overflow (more than RP_MAXCON contacts), bit1 non-finite state, bit2 hand tree too deep,
+ * flags [N]: bit0 contact overflow (more than RP_MAXCON contact records: a contact across the two hands takes two, every other
+ * contact one; with hand collisions enabled the deepest records are kept), bit1 non-finite state, bit2 hand tree too deep,
  * bit3 a hand collider the narrowphase does not cover (box / cylinder / mesh; rp_flat_model.geom_collide == 0) came
  * within reach of the piano during the last step: its contact, if any, was not generated. */
 int rp_get_diag(rp_batch *, int32_t *ncon, int32_t *niter, int32_t *flags);
