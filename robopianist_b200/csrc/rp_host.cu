@@ -993,6 +993,41 @@ extern "C" int64_t rp_launch_count(const rp_batch* b) { return b->launches; }
 
 // Debug hooks (not part of the public header): stage dump of substep 0 for every env.
 extern "C" int rp_debug_set_record_cap(rp_batch* b, int cap) { b->record_cap = cap; return 0; }
+// Test hooks (host only): the packed per-link and per-geom tables of one hand, so that the packer — bodies without joints
+// fused into their parents' links, merged inertials, padded link slots — can be checked without a GPU.
+// links: [RP_NL][28] = parent, depth, jtype, pos 3, quat 4, jpos 3, jaxis 3, mass, ipos 3, iquat 4, inertia 3, armature
+// geoms: [RP_NGH][9] = link, type, pos 3, axis 3, radius  (rows beyond the hand's geom count are zero); returns the geom count
+extern "C" int rp_debug_link_table(const rp_model* m, int hand, double* out) {
+  const RpDevModel& d = m->dm;
+  if (hand < 0 || hand >= d.nhand) return -1;
+  for (int l = 0; l < RP_NL; l++) {
+    double* o = out + 28 * l;
+    int k = 0;
+    o[k++] = d.link_parent[hand][l]; o[k++] = d.link_depth[hand][l]; o[k++] = d.link_jtype[hand][l];
+    for (int c = 0; c < 3; c++) o[k++] = d.link_pos[hand][l][c];
+    for (int c = 0; c < 4; c++) o[k++] = d.link_quat[hand][l][c];
+    for (int c = 0; c < 3; c++) o[k++] = d.link_jpos[hand][l][c];
+    for (int c = 0; c < 3; c++) o[k++] = d.link_jaxis[hand][l][c];
+    o[k++] = d.link_mass[hand][l];
+    for (int c = 0; c < 3; c++) o[k++] = d.link_ipos[hand][l][c];
+    for (int c = 0; c < 4; c++) o[k++] = d.link_iquat[hand][l][c];
+    for (int c = 0; c < 3; c++) o[k++] = d.link_inertia[hand][l][c];
+    o[k++] = d.link_armature[hand][l];
+  }
+  return d.nobs[hand];
+}
+extern "C" int rp_debug_geom_table(const rp_model* m, int hand, double* out) {
+  const RpDevModel& d = m->dm;
+  if (hand < 0 || hand >= d.nhand) return -1;
+  memset(out, 0, sizeof(double) * RP_NGH * 9);
+  for (int g = 0; g < d.ngeom[hand]; g++) {
+    double* o = out + 9 * g;
+    o[0] = d.geom_link[hand][g]; o[1] = d.geom_type[hand][g];
+    for (int c = 0; c < 3; c++) { o[2 + c] = d.geom_pos[hand][g][c]; o[5 + c] = d.geom_axis[hand][g][c]; }
+    o[8] = d.geom_size[hand][g][0];
+  }
+  return d.ngeom[hand];
+}
 extern "C" int rp_debug_enable(rp_batch* b, int on) {
   CUDA_OK(cudaSetDevice(b->device));
   if (on && !b->dbg) CUDA_OK(dalloc(&b->dbg, (size_t)b->nenv * RP_DBG_STRIDE));

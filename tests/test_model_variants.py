@@ -156,3 +156,92 @@ def test_hand_collision_scene_and_pair_filters():
     ras = cache.load_scene(gravity_compensation=True, disable_hand_collisions=False, reduced_action_space=True)
     n_ras = L.orc_npair(O.OracleModel(ras).ptr)
     assert 0 < n_ras < n
+
+
+def _packed_hand(model, hand):
+    import ctypes as Ct
+    L = native.lib()
+    L.rp_debug_link_table.argtypes = [Ct.c_void_p, Ct.c_int, Ct.POINTER(Ct.c_double)]
+    L.rp_debug_geom_table.argtypes = [Ct.c_void_p, Ct.c_int, Ct.POINTER(Ct.c_double)]
+    links = np.zeros((26, 28)); geoms = np.zeros((20, 9))
+    nl = L.rp_debug_link_table(model.ptr, hand, links.ctypes.data_as(Ct.POINTER(Ct.c_double)))
+    ng = L.rp_debug_geom_table(model.ptr, hand, geoms.ctypes.data_as(Ct.POINTER(Ct.c_double)))
+    return nl, links, ng, geoms
+
+
+def _link_kinematics(links, q):
+    """World pose of every link slot from the packed tables (what the kernel's level loop computes)."""
+    n = links.shape[0]
+    pos, quat, anchor, axis = np.zeros((n, 3)), np.zeros((n, 4)), np.zeros((n, 3)), np.zeros((n, 3))
+    for l in range(n):
+        par = int(links[l, 0])
+        pp, pq = (pos[par], quat[par]) if par >= 0 else (np.zeros(3), np.array([1.0, 0, 0, 0]))
+        p = pp + mu.rotate(pq, links[l, 3:6])
+        qn = mu.quat_mul(pq, links[l, 6:10])
+        anchor[l] = p + mu.rotate(qn, links[l, 10:13]); axis[l] = mu.rotate(qn, links[l, 13:16])
+        if int(links[l, 2]) == 2:
+            p = p + axis[l] * q[l]
+        else:
+            qn = mu.quat_mul(qn, mu.axis_angle_to_quat(links[l, 13:16], q[l]))
+            p = anchor[l] - mu.rotate(qn, links[l, 10:13])
+        pos[l], quat[l] = p, mu.quat_normalize(qn)
+    return pos, quat, anchor, axis
+
+
+@pytest.mark.parametrize("name", ["ras", "ras_fd", "hc_ras", "fdx"])
+def test_packed_links_reproduce_the_flat_model(name):
+    """The C-ABI packer (host side of rp_model_create) against the flat model it was given, at a random in-range pose: bodies
+    without joints (reduced action space, a forearm without dofs) are fused into their parents' links — geoms re-expressed,
+    inertials merged by an eigen-decomposition — and unused link slots padded with inert links.  The mass matrix assembled from
+    the packed links equals the flat model's (bodies kept separate), the packed geoms sit where the flat model's do."""
+    kw = VARIANTS[name]
+    fm = cache.load_scene(gravity_compensation=True, **kw)
+    goal, fing = helpers.song_tables()
+    model = native.Model(fm, goal, fing, kind=0, n_steps_lookahead=1)
+    rng = np.random.default_rng(8)
+    nv = fm.meta["nv"]
+    q = fm.jnt_range[:, 0] + rng.random(nv) * (fm.jnt_range[:, 1] - fm.jnt_range[:, 0])
+    M = np_ref.mass_matrix(fm, q)
+    xpos, xquat, _, _ = np_ref.fk(fm, q)
+    for h in range(2):
+        nl, links, ng, geoms = _packed_hand(model, h)
+        assert nl == fm.arrays["hand_obs_dofid"].shape[1]
+        base = 88 + h * nl
+        qh = np.zeros(26); qh[:nl] = q[base:base + nl]
+        pos, quat, anchor, axis = _link_kinematics(links, qh)
+        # padding links: inert one-dof dummies
+        for l in range(nl, 26):
+            assert links[l, 0] == -1 and links[l, 16] == 0 and links[l, 27] == 1.0
+        # mass matrix from the packed links (Jacobian sum over the link inertials)
+        chain = [[] for _ in range(26)]
+        for l in range(26):
+            par = int(links[l, 0])
+            chain[l] = (chain[par] if par >= 0 else []) + [l]
+        Mp = np.zeros((26, 26))
+        for l in range(nl):
+            m = links[l, 16]
+            if m > 0:
+                com = pos[l] + mu.rotate(quat[l], links[l, 17:20])
+                jp, jr = np.zeros((3, 26)), np.zeros((3, 26))
+                for j in chain[l]:
+                    if int(links[j, 2]) == 3:
+                        jr[:, j] = axis[j]; jp[:, j] = np.cross(axis[j], com - anchor[j])
+                    else:
+                        jp[:, j] = axis[j]
+                R = mu.quat_to_mat(mu.quat_mul(quat[l], links[l, 20:24]))
+                Mp += m * jp.T @ jp + jr.T @ (R @ np.diag(links[l, 24:27]) @ R.T) @ jr
+        Mp[np.diag_indices(26)] += links[:, 27]
+        assert np.abs(Mp[:nl, :nl] - M[base:base + nl, base:base + nl]).max() < 1e-12
+        # packed colliding primitives against the flat model's geoms
+        flat = [g for g in range(fm.meta["ngeom"]) if fm.geom_hand[g] == h and fm.geom_collide[g]]
+        assert ng == len(flat) == 18
+        for gi, g in enumerate(flat):
+            l = int(geoms[gi, 0])
+            b = int(fm.geom_bodyid[g])
+            want = xpos[b] + mu.rotate(xquat[b], fm.geom_pos[g])
+            got = pos[l] + mu.rotate(quat[l], geoms[gi, 2:5])
+            assert np.abs(got - want).max() < 1e-12, (name, h, gi)
+            if int(geoms[gi, 1]) == 3:
+                ax_want = mu.rotate(mu.quat_mul(xquat[b], fm.geom_quat[g]), np.array([0.0, 0, 1]))
+                assert np.abs(mu.rotate(quat[l], geoms[gi, 5:8]) - ax_want).max() < 1e-12
+            assert geoms[gi, 8] == fm.geom_size[g, 0]
