@@ -1016,6 +1016,12 @@ extern "C" int rp_debug_link_table(const rp_model* m, int hand, double* out) {
   }
   return d.nobs[hand];
 }
+// hand geom pairs that may collide, in launch order: out [npair][2] = hand * RP_NGH + index of the hand's colliding primitive; returns npair
+extern "C" int rp_debug_pair_list(const rp_model* m, int32_t* out) {
+  const RpDevModel& d = m->dm;
+  for (int p = 0; p < d.hc_npair; p++) { out[2 * p] = d.hc_pairs[p] & 0xff; out[2 * p + 1] = d.hc_pairs[p] >> 8; }
+  return d.hc_enabled ? d.hc_npair : 0;
+}
 extern "C" int rp_debug_geom_table(const rp_model* m, int hand, double* out) {
   const RpDevModel& d = m->dm;
   if (hand < 0 || hand >= d.nhand) return -1;

@@ -245,3 +245,31 @@ def test_packed_links_reproduce_the_flat_model(name):
                 ax_want = mu.rotate(mu.quat_mul(xquat[b], fm.geom_quat[g]), np.array([0.0, 0, 1]))
                 assert np.abs(mu.rotate(quat[l], geoms[gi, 5:8]) - ax_want).max() < 1e-12
             assert geoms[gi, 8] == fm.geom_size[g, 0]
+
+
+@pytest.mark.parametrize("name", ["hc", "hc_ras"])
+def test_kernel_pair_list_equals_the_oracles(name):
+    """The hand geom pairs the kernel tests (packed by rp_model_create: contype / conaffinity, weld bodies, parent-child,
+    <exclude>) are the oracle's, in the same order — MuJoCo's contact order depends on it."""
+    import ctypes as Ct
+    fm = cache.load_scene(gravity_compensation=True, **VARIANTS[name])
+    goal, fing = helpers.song_tables()
+    model = native.Model(fm, goal, fing, kind=0, n_steps_lookahead=1)
+    L = native.lib()
+    L.rp_debug_pair_list.argtypes = [Ct.c_void_p, Ct.POINTER(Ct.c_int32)]
+    buf = np.zeros((640, 2), np.int32)
+    n = L.rp_debug_pair_list(model.ptr, buf.ctypes.data_as(Ct.POINTER(Ct.c_int32)))
+    flat = [[g for g in range(fm.meta["ngeom"]) if fm.geom_hand[g] == h and fm.geom_collide[g]] for h in (0, 1)]
+    mine = [(flat[a // 20][a % 20], flat[b // 20][b % 20]) for a, b in buf[:n]]
+    om = O.OracleModel(fm)
+    OL = O.lib()
+    OL.orc_npair.argtypes = [Ct.c_void_p]; OL.orc_pair_get.argtypes = [Ct.c_void_p, Ct.c_int, Ct.POINTER(Ct.c_int), Ct.POINTER(Ct.c_int)]
+    theirs = []
+    for i in range(OL.orc_npair(om.ptr)):
+        a, b = Ct.c_int(), Ct.c_int()
+        OL.orc_pair_get(om.ptr, i, Ct.byref(a), Ct.byref(b))
+        theirs.append((a.value, b.value))
+    assert mine == theirs and n > 400
+    # a model without hand collisions has none
+    off = native.Model(cache.load_scene(gravity_compensation=True), goal, fing, kind=0, n_steps_lookahead=1)
+    assert L.rp_debug_pair_list(off.ptr, buf.ctypes.data_as(Ct.POINTER(Ct.c_int32))) == 0
