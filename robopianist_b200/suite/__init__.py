@@ -45,6 +45,15 @@ def load(
 ):
     """Loads a RoboPianist environment backed by the CUDA rollout.
 
+    ``task_kwargs`` are those of ``PianoWithShadowHands`` / ``PianoTask`` (piano_with_shadow_hands.py:50-66, base.py:96-107).
+    All of them are honoured except mesh fingertip colliders: ``primitive_fingertip_collisions=True`` has to be passed (the bare
+    default raises ``NotImplementedError``).  ``disable_hand_collisions=False`` (the default) collides the sphere / capsule geoms
+    of the fingers and thumbs with each other; ``reduced_action_space``, ``attachment_yaw``, ``forearm_dofs`` (tx / ty),
+    ``randomize_hand_positions``, ``augmentations``, ``n_seconds_lookahead``, ``initial_buffer_time``, ``wrong_press_termination``,
+    ``disable_fingering_reward`` / ``disable_forearm_reward``, ``energy_penalty_coef``, ``gravity_compensation``, ``trim_silence``,
+    ``physics_timestep`` / ``control_timestep`` behave as in the reference; ``disable_colorization`` and
+    ``change_color_on_activation`` only concern rendering and are accepted without effect.
+
     ``seed`` seeds the environment's ``numpy.random.RandomState`` (the reference's ``random_state``): the draws of the
     song augmentations (``task_kwargs['augmentations']``, suite/variations.py) and the seed of the per-environment
     streams of ``randomize_hand_positions``.  The scene is flattened once, so ``recompile_physics`` only keeps its one
