@@ -8,7 +8,7 @@ collective and no second process: for one process per GPU (the layout that scale
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence
+from typing import Sequence
 
 from . import sharding
 from .env import BatchedPianoEnv
